@@ -1,0 +1,162 @@
+/*
+ * pof.h — C ABI of libpof.so, the sm_100a (B200) implementation of the DR-SPAAM
+ * per-point scan hot path of huzjkevin/planar_optical_flow.
+ *
+ * The reference has no FFI / plugin layer: its boundary for this path is four
+ * Python callables.  Each entry point below states which one
+ * it replaces (paths relative to the reference root).  The Python host code in
+ * planar_optical_flow_b200/ binds these with ctypes and re-exposes the
+ * reference's own signatures; INTEGRATION.md shows the stub a reference
+ * maintainer would add.
+ *
+ * Conventions (all entry points)
+ *   - every data pointer is a DEVICE pointer into caller-owned memory, except
+ *     where an argument is explicitly described as a host pointer;
+ *   - tensors are dense, row-major, in the layouts written beside each
+ *     argument; float = IEEE binary32, double = binary64, int = int32;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ *     stream); work is enqueued, never synchronised, by the device entry points;
+ *   - return 0 on success, a NEGATIVE pof_status on a bad argument, a POSITIVE
+ *     cudaError_t if the CUDA runtime failed; pof_last_error() then returns a
+ *     thread-local, human readable message;
+ *   - no global mutable state, no allocation that outlives a call (scratch is
+ *     passed in as `ws`), no CPU fallback: without a CUDA device every compute
+ *     entry point fails with a CUDA error.
+ */
+#ifndef POF_H_
+#define POF_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POF_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define POF_API __attribute__((visibility("default")))
+#else
+#define POF_API
+#endif
+
+typedef enum pof_status {
+    POF_OK = 0,
+    POF_ERR_NULL_POINTER = -1,
+    POF_ERR_BAD_SHAPE = -2,
+    POF_ERR_BAD_PARAM = -3,
+    POF_ERR_WORKSPACE = -4,
+    POF_ERR_UNSUPPORTED = -5
+} pof_status;
+
+POF_API int pof_abi_version(void);
+POF_API const char* pof_last_error(void);
+
+/* Number of SMs / compute capability of the current device (for the host side's
+ * sanity checks: it refuses to run on anything that is not sm_100).            */
+POF_API int pof_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------- *
+ * 1. Distance-adaptive polar cutout
+ *    replaces  scans_to_cutout        src/utils/utils.py:259-334
+ *    (and the unused torch port scans_to_cutout_torch, :337-420, whose results
+ *     follow :259-334's mixed fp32/fp64 arithmetic here, not the all-fp32 port)
+ *
+ *    One call = B independent invocations of the reference function (one per
+ *    sequence sample; the area-mode oversampling factor `s_area`, utils.py:308,
+ *    is a per-invocation global and is therefore reduced per b).
+ *
+ *    scans   [B, S, N] float        ranges; S scans per sample, newest last
+ *    phi     [N] float or double    beam angles (`phi_is_f64` selects);
+ *                                   uniform pitch, phi[1]-phi[0] != 0
+ *    out     [B, M, S, P] float     M = ceil(N / stride)   (utils.py:332-334,
+ *                                   batched as dataset_dr_spaam.py:464-468)
+ *    s_area_out [B] int or NULL     the factor each sample used (0 = no point
+ *                                   of that sample was area-resampled)
+ *    ws      pof_cutout_ws_bytes(B) bytes of device scratch
+ *
+ *    window_width, window_depth, padding_val are doubles because the reference
+ *    receives Python floats and rounds them at specific places (utils.py:279,
+ *    326-330).  `fixed`, `centered`, `area_mode` as in the reference.
+ * ------------------------------------------------------------------------- */
+POF_API size_t pof_cutout_ws_bytes(int B);
+
+POF_API int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64,
+                   int B, int S, int N, int stride, int P,
+                   double window_width, double window_depth, double padding_val,
+                   int fixed, int centered, int area_mode,
+                   float* out, int* s_area_out,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * 2. Auto-regressive spatial-attention memory update
+ *    replaces  _SpatialAttention.forward  src/depracted/model/dr_spaam.py:183-215
+ *    (everything after the two embedding convolutions of :176-181, which stay
+ *     on cuDNN) with the neighbour table of _generate_neighbor_mask, :145-160.
+ *
+ *    x, tmpl      [B, N, CL] float  current / remembered per-point features
+ *                                   (CL = 256*14 = 3584 for DR-SPAAM), CL % 4 == 0,
+ *                                   16-byte aligned
+ *    emb_x, emb_t [B, N, E] float   their similarity embeddings, E % 4 == 0
+ *    W                              window size 2*hw+1 (odd, 1..15)
+ *    out_tmpl     [B, N, CL] float  alpha*x + (1-alpha)*sum_j w_ij tmpl_j   (:210-215)
+ *                                   must NOT alias x or tmpl (template rows are
+ *                                   re-read by neighbouring points)
+ *    feat_fused   [B, N, W] float   raw similarities at CLAMPED neighbour indices (:187)
+ *    attn_w       [B, N, W] float or NULL   softmax weights over the UNIQUE in-range
+ *                                   neighbours (0 on clamped duplicates); saved for bwd
+ * ------------------------------------------------------------------------- */
+POF_API int pof_spaam_gate_fwd(const float* x, const float* tmpl,
+                       const float* emb_x, const float* emb_t,
+                       int B, int N, int CL, int E, int W, float alpha,
+                       float* out_tmpl, float* feat_fused, float* attn_w,
+                       void* stream);
+
+/*    Backward of the above for training (autograd through the sequential gate
+ *    loop of SpatialDROW.forward, dr_spaam.py:266-273).
+ *    g_out [B,N,CL], g_feat [B,N,W] (or NULL = zero)  ->
+ *    g_x [B,N,CL], g_tmpl [B,N,CL], g_emb_x [B,N,E], g_emb_t [B,N,E]
+ *    ws: pof_spaam_gate_bwd_ws_bytes(B,N,W) bytes of device scratch.           */
+POF_API size_t pof_spaam_gate_bwd_ws_bytes(int B, int N, int W);
+
+POF_API int pof_spaam_gate_bwd(const float* tmpl, const float* emb_x, const float* emb_t,
+                       const float* attn_w, const float* g_out, const float* g_feat,
+                       int B, int N, int CL, int E, int W, float alpha,
+                       float* g_x, float* g_tmpl, float* g_emb_x, float* g_emb_t,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * 3. Predicted-centre vote / group / NMS
+ *    replaces  nms_predicted_center   src/utils/utils.py:535-571
+ *    (with canonical_to_global :109-116 and rphi_to_xy :47-48)
+ *
+ *    One call = B independent scans.
+ *    scan   [B, N] float or double  (`scan_is_f64`)   ranges
+ *    phi    [N]    float or double  (`phi_is_f64`)    beam angles
+ *    cls    [B, N] float            post-sigmoid confidences (one class)
+ *    reg    [B, N, 2] float         canonical (dx, dy) votes
+ *    Arithmetic follows NumPy's promotion for those dtypes (see oracle/nms.py).
+ *
+ *    order         [B, N] int       point indices by descending confidence
+ *                                   (ties: higher index first)
+ *    keep_idx      [B, N] int       first n_keep[b] entries: ORIGINAL indices of
+ *                                   the surviving centres, descending confidence
+ *    n_keep        [B] int
+ *    instance_mask [B, N] int       1-based id of the last kept centre within
+ *                                   min_dist of each point (utils.py:565)
+ *    det_xy        [B, N, 2] double first n_keep[b] rows valid (utils.py:568)
+ *    det_cls       [B, N] float     first n_keep[b] valid (utils.py:569)
+ *    ws            pof_nms_ws_bytes(B, N) bytes of device scratch
+ * ------------------------------------------------------------------------- */
+POF_API size_t pof_nms_ws_bytes(int B, int N);
+
+POF_API int pof_nms_centers(const void* scan, int scan_is_f64, const void* phi, int phi_is_f64,
+                    const float* cls, const float* reg, int B, int N, double min_dist,
+                    int* order, int* keep_idx, int* n_keep, int* instance_mask,
+                    double* det_xy, float* det_cls,
+                    void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POF_H_ */

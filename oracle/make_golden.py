@@ -1,0 +1,130 @@
+"""Freeze outputs of the UNMODIFIED reference into tests/golden/*.npz.
+
+TEST INFRASTRUCTURE.  Run in the build container (needs /root/reference):
+
+    python -m oracle.make_golden
+
+The reference itself carries no golden vectors, KATs or fixtures for this path
+(SURVEY.md §4), so these files are the pin: inputs come from the seeded
+generators in planar_optical_flow_b200/synth.py, outputs from the reference's
+own `scans_to_cutout`, `nms_predicted_center` and `SpatialDROW`
+(/root/reference/src/utils/utils.py:259-334,535-571;
+ /root/reference/src/depracted/model/dr_spaam.py:124-277) executed on this
+container's CPU (NumPy 2.3.5, torch 2.11.0).  The fixtures travel to the GPU
+box; /root/reference does not.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import model as omodel  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+from planar_optical_flow_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+CFG = dict(fixed=True, centered=True, window_width=1.0, window_depth=0.5,
+           num_cutout_pts=56, padding_val=29.99, area_mode=True)
+
+
+def weights_digest(sd):
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().numpy().tobytes())
+    return h.hexdigest()
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("%-40s %8.1f KB" % (name, os.path.getsize(path) / 1024))
+
+
+def cutout_cases(ru):
+    cases = [
+        ("cutout_drow_adversarial", "drow", synth.adversarial_scans(2, 450, seed=21), dict()),
+        ("cutout_drow_structured_lastref", "drow",
+         synth.structured_sequence(3, 450, seed=22, phi=synth.drow_phi()), dict(fixed=False)),
+        ("cutout_drow_edge", "drow", synth.edge_scans(450, seed=23), dict()),
+        ("cutout_jrdb_adversarial", "jrdb", synth.adversarial_scans(1, 1091, seed=24), dict()),
+        ("cutout_jrdb_structured_raw", "jrdb",
+         synth.structured_sequence(2, 1091, seed=25, phi=synth.jrdb_phi()), dict(centered=False)),
+        ("cutout_drow_linear48", "drow", synth.adversarial_scans(2, 450, seed=26),
+         dict(area_mode=False, window_width=1.66, window_depth=1.0, num_cutout_pts=48)),
+    ]
+    for name, shape, scans, flags in cases:
+        kw = dict(CFG, **flags)
+        phi = synth.phi_for(shape)
+        out = ru.scans_to_cutout(scans, phi, stride=1, **kw)
+        save(name, scans=scans, phi=phi, out=out,
+             kwargs=np.array(repr(sorted(kw.items()))))
+
+
+def nms_cases(ru):
+    for name, shape, dt, seed in [("nms_drow_f32scan", "drow", np.float32, 31),
+                                  ("nms_drow_f64scan", "drow", np.float64, 32),
+                                  ("nms_jrdb_f32scan", "jrdb", np.float32, 33),
+                                  ("nms_jrdb_f64scan", "jrdb", np.float64, 34)]:
+        phi = synth.phi_for(shape)
+        n = len(phi)
+        scan = synth.structured_sequence(1, n, seed=seed, phi=phi)[0].astype(dt)
+        cls = synth.distinct_scores(n, seed)
+        reg = synth.clustered_votes(scan.astype(np.float64), phi, seed)
+        xy, c, mask = ru.nms_predicted_center(scan, phi, cls, reg)
+        save(name, scan=scan, phi=phi, cls=cls, reg=reg, det_xys=xy, det_cls=c, instance_mask=mask)
+
+
+def model_cases(rm):
+    # streaming branch, 3 steps, memory carried (dr_spaam.py:239-250)
+    seed, n, b = 41, 40, 2
+    sd = omodel.randomize_bn_stats(omodel.init_state_dict(56, True, seed=seed), seed=seed + 1)
+    m = rm.SpatialDROW(num_scans=10, num_pts=56, alpha=0.5, window_size=11, pedestrian_only=True)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    phi = synth.drow_phi(n)
+    scans = np.stack([synth.structured_sequence(3, n, seed=seed + 10 + k, phi=phi) for k in range(b)])  # [B,T,N]
+    ru, _ = ref_shim.load()
+    arrays = dict(scans=scans, phi=phi, weights_sha256=np.array(weights_digest(sd)),
+                  seed=np.array(seed))
+    tmpl = None
+    with torch.no_grad():
+        for t in range(scans.shape[1]):
+            ct = np.stack([ru.scans_to_cutout(scans[k, t:t + 1], phi, stride=1, **CFG) for k in range(b)])
+            cls, reg, tmpl, ff = m(torch.from_numpy(ct), testing=True, fea_template=tmpl)
+            arrays["cls_%d" % t] = cls.numpy()
+            arrays["reg_%d" % t] = reg.numpy()
+            arrays["feat_fused_%d" % t] = ff.numpy()
+        arrays["template_last_sample"] = tmpl.numpy()[:, ::8, ::16]      # spot rows, keeps the file small
+        arrays["template_last_sum"] = tmpl.double().sum(dim=(2, 3)).numpy()
+    save("model_stream_drow40", **arrays)
+
+    # the gate alone on seeded feature-like inputs (dr_spaam.py:163-217)
+    seed, n, b = 51, 24, 1
+    sd = omodel.randomize_bn_stats(omodel.init_state_dict(56, True, seed=seed), seed=seed + 1)
+    gate = rm._SpatialAttention(n_pts=14, n_channel=256, alpha=0.5, window_size=11)
+    gate.load_state_dict({k[len("gate."):]: v for k, v in sd.items() if k.startswith("gate.")}, strict=True)
+    gate.eval()
+    x = synth.feature_like((b, n, 256, 14), seed + 2)
+    t = synth.feature_like((b, n, 256, 14), seed + 3)
+    with torch.no_grad():
+        out, ff = gate(torch.from_numpy(x), torch.from_numpy(t))
+    save("gate_n24", out_temp=out.numpy(), feat_fused=ff.numpy(), seed=np.array(seed),
+         weights_sha256=np.array(weights_digest(sd)))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ru, rm = ref_shim.load()
+    cutout_cases(ru)
+    nms_cases(ru)
+    model_cases(rm)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,451 @@
+// Kernel 2 — auto-regressive spatial-attention memory update (forward).
+//
+// Replaces everything after the two embedding convolutions in
+// _SpatialAttention.forward (/root/reference/src/depracted/model/dr_spaam.py:183-215):
+// the reference forms a dense [N, N] similarity, masks it to the +-hw window,
+// soft-maxes and multiplies the dense weights with the [N, C*L] template
+// (8.5 GFLOP of multiplications by zero per JRDB scan).  Here one fused kernel
+// does the windowed form:
+//
+//   sim[i,k]   = <emb_x[i], emb_t[clamp(i-hw+k)]>             k = 0..W-1     (:184,:187)
+//   w[i,.]     = softmax over the UNIQUE in-range neighbours                  (:197-201)
+//   out[i,:]   = alpha*x[i,:] + (1-alpha) * sum_k w[i,k] * tmpl[i-hw+k,:]     (:210-215)
+//
+// HBM-bound: per point it must read x (14 KB) and the template row (14 KB) and
+// write out (14 KB).  Layout of the work on B200:
+//   * a CTA owns (sequence b, a chunk of consecutive points, a slice of 4*T
+//     channels, T = 128); thread t owns 4 adjacent channels (one float4) and MARCHES along
+//     the chunk's points;
+//   * the W template rows a point needs are kept in a per-thread circular
+//     REGISTER window (W + D float4), so each template element is loaded from
+//     global memory once per chunk (plus the 2*hw halo rows at the chunk ends,
+//     which neighbouring CTAs hit in L2) and the 11-fold neighbour re-use costs
+//     no memory traffic at all; the loop is unrolled by the window size so every
+//     window slot is a fixed register;
+//   * D rows of the template and the next x row are requested ahead of use, so a
+//     thread keeps D+1 16-byte loads in flight (≈ 41 KB per SM at 5 CTAs x 128 threads);
+//   * the similarities and soft-max weights of the chunk are computed once in a
+//     prologue (one warp per point: neighbour embeddings are 512-byte rows read
+//     as one float4 per lane, dot products finished with warp shuffles) and
+//     broadcast from shared memory in the streaming loop.
+#include <math.h>
+
+#include "pof_common.cuh"
+
+namespace pof {
+namespace {
+
+constexpr int kMaxChunk = 160;     // points per CTA (upper bound, sizes the weight table)
+#ifndef POF_GATE_THREADS
+#define POF_GATE_THREADS 128
+#endif
+#ifndef POF_GATE_MINBLOCKS
+#define POF_GATE_MINBLOCKS 5
+#endif
+#ifndef POF_GATE_AHEAD
+#define POF_GATE_AHEAD 3
+#endif
+// 128 threads x float4 = 512 channels per CTA: DR-SPAAM's 3584 = 7 slices exactly; one
+// warp per SM sub-partition, 5 CTAs/SM -> 96 registers per thread (the register file is
+// split per sub-partition, so 7-warp CTAs would lose a sixth of it).
+constexpr int kGateThreads = POF_GATE_THREADS;
+constexpr int kGateMinBlocks = POF_GATE_MINBLOCKS;
+constexpr int kAhead = POF_GATE_AHEAD;   // template rows requested ahead of use (odd, so W + kAhead is even)
+
+struct GateArgs {
+    const float* x;
+    const float* tmpl;
+    const float* emb_x;
+    const float* emb_t;
+    float* out;
+    float* out2;         // backward only: g_x
+    float* feat_fused;
+    float* attn_w;
+    int B, N, CL, E;
+    int chunk_len, n_chunks;
+    float alpha, beta;   // beta = (float)(1.0 - alpha)
+};
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void f4_fma(float4& acc, float w, const float4& v) {
+    acc.x = fmaf(w, v.x, acc.x);
+    acc.y = fmaf(w, v.y, acc.y);
+    acc.z = fmaf(w, v.z, acc.z);
+    acc.w = fmaf(w, v.w, acc.w);
+}
+
+// Similarities + soft-max weights for the chunk's points; one warp per point.
+template <int W>
+__device__ __forceinline__ void chunk_weights(const GateArgs& a, int b, int i0, int len, bool write_global,
+                                              float (*w_s)[(W + 3) & ~3]) {
+    constexpr int HW = W / 2;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int n_warps = blockDim.x >> 5;
+    const float* ex_b = a.emb_x + (size_t)b * a.N * a.E;
+    const float* et_b = a.emb_t + (size_t)b * a.N * a.E;
+    for (int p = warp; p < len; p += n_warps) {
+        const int i = i0 + p;
+        float part[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) part[k] = 0.f;
+        for (int e = lane * 4; e < a.E; e += 128) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(ex_b + (size_t)i * a.E + e));
+#pragma unroll
+            for (int k = 0; k < W; ++k) {
+                const int j = min(max(i - HW + k, 0), a.N - 1);      // clamped neighbour (:152)
+                const float4 t = __ldg(reinterpret_cast<const float4*>(et_b + (size_t)j * a.E + e));
+                part[k] = fmaf(q.x, t.x, fmaf(q.y, t.y, fmaf(q.z, t.z, fmaf(q.w, t.w, part[k]))));
+            }
+        }
+        float mine = 0.f;   // lane k ends up owning similarity k
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            const float s = warp_sum(part[k]);
+            if (lane == k) mine = s;
+        }
+        const int j_raw = i - HW + lane;
+        const bool in_window = lane < W && j_raw >= 0 && j_raw <= a.N - 1;
+        const float top = warp_max(in_window ? mine : -INFINITY);
+        const float ex = in_window ? expf(mine - top) : 0.f;
+        const float wgt = ex / warp_sum(ex);
+        if (lane < W) {
+            w_s[p][lane] = wgt;
+            if (write_global) {
+                const size_t o = ((size_t)b * a.N + i) * W + lane;
+                a.feat_fused[o] = mine;
+                if (a.attn_w) a.attn_w[o] = wgt;
+            }
+        }
+    }
+}
+
+// Transposed weights for the backward stream: g_tmpl[j] = beta * sum_k' wT[j][k'] * g_out[j-hw+k']
+// with wT[j][k'] = w[j-hw+k'][W-1-k'] (0 when that point does not exist).
+template <int W>
+__device__ __forceinline__ void chunk_weights_transposed(const GateArgs& a, int b, int i0, int len,
+                                                         float (*w_s)[(W + 3) & ~3]) {
+    constexpr int HW = W / 2;
+    const float* wb = a.attn_w + (size_t)b * a.N * W;
+    for (int t = threadIdx.x; t < len * W; t += blockDim.x) {
+        const int p = t / W, k = t - p * W;
+        const int i = i0 + p - HW + k;
+        w_s[p][k] = (i >= 0 && i < a.N) ? __ldg(wb + (size_t)i * W + (W - 1 - k)) : 0.f;
+    }
+}
+
+// MODE 0 (forward):  out[i]  = alpha*x[i] + beta * sum_k w[i][k]  * tmpl[i-hw+k]
+// MODE 1 (backward): out[j]  = beta * sum_k wT[j][k] * g_out[j-hw+k]   (g_tmpl; `tmpl` = g_out)
+//                    out2[j] = alpha * g_out[j]                         (g_x)
+template <int W, int MODE>
+__global__ void __launch_bounds__(kGateThreads, kGateMinBlocks) gate_stream_kernel(const GateArgs a) {
+    constexpr int HW = W / 2;
+    constexpr int D = kAhead;
+    constexpr int WIN = W + D;
+    constexpr int WPAD = (W + 3) & ~3;
+    static_assert((WIN & 1) == 0, "window + prefetch depth must be even (x double buffer parity)");
+    __shared__ __align__(16) float w_s[kMaxChunk][WPAD];
+
+    const int b = blockIdx.z;
+    const int i0 = blockIdx.x * a.chunk_len;
+    const int len = min(a.chunk_len, a.N - i0);
+    const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    const bool active = ch < a.CL;
+    const int row_max = min(a.N - 1, i0 + len - 1 + HW);     // last template row this chunk needs
+    const size_t seq = (size_t)b * a.N * a.CL;
+    const float* t_col = a.tmpl + seq + (active ? ch : 0);
+    const float* x_col = a.x + seq + (active ? ch : 0);
+    float* o_col = a.out + seq + (active ? ch : 0);
+    const size_t CL = (size_t)a.CL;
+
+    // Weights first: their live registers (W partial sums + operands) must not
+    // overlap the primed window or ptxas spills the window around the prologue.
+    if (MODE == 0) chunk_weights<W>(a, b, i0, len, blockIdx.y == 0, w_s);
+    else chunk_weights_transposed<W>(a, b, i0, len, w_s);
+    __syncthreads();
+
+    // prime the register window with rows i0-hw .. i0+hw-1+D
+    float4 win[WIN];
+#pragma unroll
+    for (int t = 0; t < WIN - 1; ++t) {
+        const int r = i0 - HW + t;
+        win[t] = (active && r >= 0 && r <= row_max) ? ld_stream_f4(reinterpret_cast<const float4*>(t_col + r * CL))
+                                                    : f4_zero();
+    }
+    win[WIN - 1] = f4_zero();
+    float4 xr[2];
+    xr[0] = (MODE == 0 && active) ? ld_stream_f4(reinterpret_cast<const float4*>(x_col + (size_t)i0 * CL)) : f4_zero();
+    xr[1] = f4_zero();
+
+    const float alpha = a.alpha, beta = a.beta;
+    for (int p0 = 0; p0 < len; p0 += WIN) {
+#pragma unroll
+        for (int u = 0; u < WIN; ++u) {
+            const int p = p0 + u;
+            if (p < len) {
+                const int i = i0 + p;
+                {   // request template row i+hw+D into the slot row i-hw-1 just vacated
+                    const int r = i + HW + D;
+                    win[(u + WIN - 1) % WIN] =
+                        (active && r <= row_max) ? ld_stream_f4(reinterpret_cast<const float4*>(t_col + r * CL)) : f4_zero();
+                }
+                if (MODE == 0)
+                    xr[(u + 1) & 1] = (active && p + 1 < len)
+                                          ? ld_stream_f4(reinterpret_cast<const float4*>(x_col + (size_t)(i + 1) * CL))
+                                          : f4_zero();
+                float wk[WPAD];
+#pragma unroll
+                for (int k4 = 0; k4 < WPAD; k4 += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(&w_s[p][k4]);
+                    wk[k4] = w4.x; wk[k4 + 1] = w4.y; wk[k4 + 2] = w4.z; wk[k4 + 3] = w4.w;
+                }
+                float4 acc = f4_zero();
+#pragma unroll
+                for (int k = 0; k < W; ++k) f4_fma(acc, wk[k], win[(u + k) % WIN]);
+                if (MODE == 0) {
+                    const float4 xv = xr[u & 1];
+                    float4 o;
+                    o.x = fmaf(alpha, xv.x, beta * acc.x);
+                    o.y = fmaf(alpha, xv.y, beta * acc.y);
+                    o.z = fmaf(alpha, xv.z, beta * acc.z);
+                    o.w = fmaf(alpha, xv.w, beta * acc.w);
+                    if (active) st_stream_f4(reinterpret_cast<float4*>(o_col + (size_t)i * CL), o);
+                } else {
+                    const float4 c = win[(u + HW) % WIN];     // g_out[j] itself
+                    if (active) {
+                        st_stream_f4(reinterpret_cast<float4*>(o_col + (size_t)i * CL),
+                                     make_float4(beta * acc.x, beta * acc.y, beta * acc.z, beta * acc.w));
+                        st_stream_f4(reinterpret_cast<float4*>(a.out2 + seq + ch + (size_t)i * CL),
+                                     make_float4(alpha * c.x, alpha * c.y, alpha * c.z, alpha * c.w));
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int W, int MODE>
+int launch_gate_stream(const GateArgs& a, dim3 grid, int threads, cudaStream_t stream) {
+    gate_stream_kernel<W, MODE><<<grid, threads, 0, stream>>>(a);
+    POF_CUDA(cudaGetLastError());
+    return POF_OK;
+}
+
+template <int MODE>
+int dispatch_gate_stream(int W, const GateArgs& a, dim3 grid, int threads, cudaStream_t stream) {
+    switch (W) {
+        case 1: return launch_gate_stream<1, MODE>(a, grid, threads, stream);
+        case 3: return launch_gate_stream<3, MODE>(a, grid, threads, stream);
+        case 5: return launch_gate_stream<5, MODE>(a, grid, threads, stream);
+        case 7: return launch_gate_stream<7, MODE>(a, grid, threads, stream);
+        case 9: return launch_gate_stream<9, MODE>(a, grid, threads, stream);
+        case 11: return launch_gate_stream<11, MODE>(a, grid, threads, stream);
+        case 13: return launch_gate_stream<13, MODE>(a, grid, threads, stream);
+        case 15: return launch_gate_stream<15, MODE>(a, grid, threads, stream);
+    }
+    set_error("spaam gate: unsupported window %d", W);
+    return POF_ERR_UNSUPPORTED;
+}
+
+// Chunking of the points of one sequence: <= kMaxChunk points per CTA, and short
+// enough that the grid covers the machine (3 CTAs/SM) about 4 times when the
+// batch is small, but never below 16 points (halo overhead 2*hw/len).
+void plan_chunks(int B, int N, int CL, GateArgs& a, dim3& grid) {
+    const int slices = (CL + kGateThreads * 4 - 1) / (kGateThreads * 4);
+    const long long want_ctas = 4ll * kGateMinBlocks * sm_count();
+    int n_chunks = (N + 127) / 128;
+    const long long per_chunk = (long long)B * slices;
+    if (per_chunk * n_chunks < want_ctas) n_chunks = (int)((want_ctas + per_chunk - 1) / per_chunk);
+    n_chunks = max(1, min(n_chunks, (N + 15) / 16));
+    int chunk_len = (N + n_chunks - 1) / n_chunks;
+    if (chunk_len > kMaxChunk) chunk_len = kMaxChunk;
+    n_chunks = (N + chunk_len - 1) / chunk_len;
+    a.chunk_len = chunk_len;
+    a.n_chunks = n_chunks;
+    grid = dim3((unsigned)n_chunks, (unsigned)slices, (unsigned)B);
+}
+
+// ---- backward helpers -------------------------------------------------------------------------
+// g_w[i,k] = beta * <g_out[i], tmpl[i-hw+k]>, then the soft-max Jacobian and the direct
+// feat_fused gradient:  g_s[i,k] = w[i,k] * (g_w[i,k] - sum_k' w[i,k'] g_w[i,k']) + g_feat[i,k].
+// One warp per point; template rows are re-read by neighbouring warps out of L2.
+template <int W>
+__global__ void __launch_bounds__(256) gate_bwd_scores_kernel(const GateArgs a, const float* __restrict__ g_out,
+                                                              const float* __restrict__ g_feat, float* __restrict__ g_s) {
+    constexpr int HW = W / 2;
+    const int lane = threadIdx.x & 31;
+    const long long pt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pt >= (long long)a.B * a.N) return;
+    const int b = (int)(pt / a.N), i = (int)(pt - (long long)b * a.N);
+    const size_t seq = (size_t)b * a.N * a.CL;
+    const float4* g4 = reinterpret_cast<const float4*>(g_out + seq + (size_t)i * a.CL);
+    float part[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) part[k] = 0.f;
+    for (int c = lane; c < a.CL / 4; c += 32) {
+        const float4 g = __ldg(g4 + c);
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            const int j = i - HW + k;
+            if (j >= 0 && j < a.N) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(a.tmpl + seq + (size_t)j * a.CL) + c);
+                part[k] = fmaf(g.x, t.x, fmaf(g.y, t.y, fmaf(g.z, t.z, fmaf(g.w, t.w, part[k]))));
+            }
+        }
+    }
+    float gw = 0.f;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        const float s = warp_sum(part[k]);
+        if (lane == k) gw = a.beta * s;
+    }
+    const size_t o = ((size_t)b * a.N + i) * W + lane;
+    const float w = lane < W ? a.attn_w[o] : 0.f;
+    const float mean = warp_sum(w * gw);
+    if (lane < W) g_s[o] = w * (gw - mean) + (g_feat ? g_feat[o] : 0.f);
+}
+
+// g_emb_x[i] = sum_k g_s[i,k] emb_t[clamp(i-hw+k)];  g_emb_t[j] = sum_{(i,k): clamp(i-hw+k)=j} g_s[i,k] emb_x[i].
+template <int W>
+__global__ void __launch_bounds__(256) gate_bwd_embed_kernel(const GateArgs a, const float* __restrict__ g_s,
+                                                             float* __restrict__ g_ex, float* __restrict__ g_et) {
+    constexpr int HW = W / 2;
+    const int lane = threadIdx.x & 31;
+    const long long pt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pt >= (long long)a.B * a.N) return;
+    const int b = (int)(pt / a.N), i = (int)(pt - (long long)b * a.N);
+    const int N = a.N, E = a.E;
+    const float* ex = a.emb_x + (size_t)b * N * E;
+    const float* et = a.emb_t + (size_t)b * N * E;
+    const float* gs = g_s + (size_t)b * N * W;
+    for (int e = lane * 4; e < E; e += 128) {
+        float4 acc = f4_zero();
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            const int j = min(max(i - HW + k, 0), N - 1);
+            f4_fma(acc, gs[(size_t)i * W + k], __ldg(reinterpret_cast<const float4*>(et + (size_t)j * E + e)));
+        }
+        *reinterpret_cast<float4*>(g_ex + ((size_t)b * N + i) * E + e) = acc;
+
+        // transposed: this point as template row j = i
+        const int j = i;
+        float4 acc_t = f4_zero();
+        for (int q = max(0, j - HW); q <= min(N - 1, j + HW); ++q)
+            f4_fma(acc_t, gs[(size_t)q * W + (j - q + HW)], __ldg(reinterpret_cast<const float4*>(ex + (size_t)q * E + e)));
+        if (j == 0)          // clamped-low duplicates: q - hw + k < 0
+            for (int q = 0; q < min(HW, N); ++q)
+                for (int k = 0; k < HW - q; ++k)
+                    f4_fma(acc_t, gs[(size_t)q * W + k], __ldg(reinterpret_cast<const float4*>(ex + (size_t)q * E + e)));
+        if (j == N - 1)      // clamped-high duplicates: q - hw + k > N-1
+            for (int q = max(0, N - HW); q < N; ++q)
+                for (int k = N - q + HW; k < W; ++k)
+                    f4_fma(acc_t, gs[(size_t)q * W + k], __ldg(reinterpret_cast<const float4*>(ex + (size_t)q * E + e)));
+        *reinterpret_cast<float4*>(g_et + ((size_t)b * N + i) * E + e) = acc_t;
+    }
+}
+
+template <int W>
+int launch_gate_bwd_small(const GateArgs& a, const float* g_out, const float* g_feat, float* g_s, float* g_ex, float* g_et,
+                          cudaStream_t stream) {
+    const long long pts = (long long)a.B * a.N;
+    const unsigned grid = (unsigned)((pts + 7) / 8);
+    gate_bwd_scores_kernel<W><<<grid, 256, 0, stream>>>(a, g_out, g_feat, g_s);
+    POF_CUDA(cudaGetLastError());
+    gate_bwd_embed_kernel<W><<<grid, 256, 0, stream>>>(a, g_s, g_ex, g_et);
+    POF_CUDA(cudaGetLastError());
+    return POF_OK;
+}
+
+}  // namespace
+}  // namespace pof
+
+extern "C" {
+
+int pof_spaam_gate_fwd(const float* x, const float* tmpl, const float* emb_x, const float* emb_t, int B, int N, int CL,
+                       int E, int W, float alpha, float* out_tmpl, float* feat_fused, float* attn_w, void* stream_) {
+    using namespace pof;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    POF_REQUIRE(x && tmpl && emb_x && emb_t && out_tmpl && feat_fused, POF_ERR_NULL_POINTER,
+                "pof_spaam_gate_fwd: null tensor pointer");
+    POF_REQUIRE(B >= 0 && N >= 1 && CL >= 4 && E >= 4, POF_ERR_BAD_SHAPE, "pof_spaam_gate_fwd: bad shape B=%d N=%d CL=%d E=%d", B,
+                N, CL, E);
+    POF_REQUIRE((CL % 4) == 0 && (E % 4) == 0, POF_ERR_BAD_SHAPE, "pof_spaam_gate_fwd: CL and E must be multiples of 4");
+    POF_REQUIRE(W >= 1 && (W & 1) && W <= 15, POF_ERR_UNSUPPORTED,
+                "pof_spaam_gate_fwd: window must be odd and <= 15 (got %d)", W);
+    POF_REQUIRE(out_tmpl != tmpl && out_tmpl != x, POF_ERR_BAD_PARAM,
+                "pof_spaam_gate_fwd: out_tmpl must not alias x or tmpl (neighbouring points re-read template rows)");
+    const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(tmpl) |
+                         reinterpret_cast<uintptr_t>(emb_x) | reinterpret_cast<uintptr_t>(emb_t) |
+                         reinterpret_cast<uintptr_t>(out_tmpl);
+    POF_REQUIRE((al & 15) == 0, POF_ERR_BAD_PARAM, "pof_spaam_gate_fwd: tensors must be 16-byte aligned");
+    POF_REQUIRE(B <= 65535, POF_ERR_BAD_SHAPE, "pof_spaam_gate_fwd: B must be <= 65535");
+    if (B == 0) return POF_OK;
+
+    GateArgs a;
+    a.x = x; a.tmpl = tmpl; a.emb_x = emb_x; a.emb_t = emb_t;
+    a.out = out_tmpl; a.feat_fused = feat_fused; a.attn_w = attn_w;
+    a.B = B; a.N = N; a.CL = CL; a.E = E;
+    a.alpha = alpha;
+    a.beta = (float)(1.0 - (double)alpha);
+
+    a.out2 = nullptr;
+    dim3 grid;
+    plan_chunks(B, N, CL, a, grid);
+    return dispatch_gate_stream<0>(W, a, grid, kGateThreads, stream);
+}
+
+size_t pof_spaam_gate_bwd_ws_bytes(int B, int N, int W) {
+    return (B > 0 && N > 0 && W > 0) ? (size_t)B * N * W * sizeof(float) : 0;
+}
+
+int pof_spaam_gate_bwd(const float* tmpl, const float* emb_x, const float* emb_t, const float* attn_w, const float* g_out,
+                       const float* g_feat, int B, int N, int CL, int E, int W, float alpha, float* g_x, float* g_tmpl,
+                       float* g_emb_x, float* g_emb_t, void* ws, size_t ws_bytes, void* stream_) {
+    using namespace pof;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    POF_REQUIRE(tmpl && emb_x && emb_t && attn_w && g_out && g_x && g_tmpl && g_emb_x && g_emb_t, POF_ERR_NULL_POINTER,
+                "pof_spaam_gate_bwd: null tensor pointer");
+    POF_REQUIRE(B >= 0 && N >= 1 && CL >= 4 && E >= 4 && (CL % 4) == 0 && (E % 4) == 0, POF_ERR_BAD_SHAPE,
+                "pof_spaam_gate_bwd: bad shape B=%d N=%d CL=%d E=%d", B, N, CL, E);
+    POF_REQUIRE(W >= 1 && (W & 1) && W <= 15, POF_ERR_UNSUPPORTED, "pof_spaam_gate_bwd: window must be odd and <= 15 (got %d)", W);
+    POF_REQUIRE(B <= 65535, POF_ERR_BAD_SHAPE, "pof_spaam_gate_bwd: B must be <= 65535");
+    POF_REQUIRE(g_tmpl != g_out && g_x != g_out, POF_ERR_BAD_PARAM, "pof_spaam_gate_bwd: gradients must not alias g_out");
+    if (B == 0) return POF_OK;
+    POF_REQUIRE(ws && ws_bytes >= pof_spaam_gate_bwd_ws_bytes(B, N, W), POF_ERR_WORKSPACE,
+                "pof_spaam_gate_bwd: workspace too small (%zu < %zu)", ws_bytes, pof_spaam_gate_bwd_ws_bytes(B, N, W));
+
+    GateArgs a;
+    a.x = nullptr; a.tmpl = tmpl; a.emb_x = emb_x; a.emb_t = emb_t;
+    a.out = nullptr; a.out2 = nullptr; a.feat_fused = nullptr;
+    a.attn_w = const_cast<float*>(attn_w);
+    a.B = B; a.N = N; a.CL = CL; a.E = E;
+    a.alpha = alpha;
+    a.beta = (float)(1.0 - (double)alpha);
+    a.chunk_len = 0; a.n_chunks = 0;
+    float* g_s = reinterpret_cast<float*>(ws);
+
+    int rc = POF_ERR_UNSUPPORTED;
+    switch (W) {
+        case 1: rc = launch_gate_bwd_small<1>(a, g_out, g_feat, g_s, g_emb_x, g_emb_t, stream); break;
+        case 3: rc = launch_gate_bwd_small<3>(a, g_out, g_feat, g_s, g_emb_x, g_emb_t, stream); break;
+        case 5: rc = launch_gate_bwd_small<5>(a, g_out, g_feat, g_s, g_emb_x, g_emb_t, stream); break;
+        case 7: rc = launch_gate_bwd_small<7>(a, g_out, g_feat, g_s, g_emb_x, g_emb_t, stream); break;
+        case 9: rc = launch_gate_bwd_small<9>(a, g_out, g_feat, g_s, g_emb_x, g_emb_t, stream); break;
+        case 11: rc = launch_gate_bwd_small<11>(a, g_out, g_feat, g_s, g_emb_x, g_emb_t, stream); break;
+        case 13: rc = launch_gate_bwd_small<13>(a, g_out, g_feat, g_s, g_emb_x, g_emb_t, stream); break;
+        case 15: rc = launch_gate_bwd_small<15>(a, g_out, g_feat, g_s, g_emb_x, g_emb_t, stream); break;
+    }
+    if (rc != POF_OK) return rc;
+
+    // streaming part: g_tmpl (windowed, transposed weights) and g_x, one pass over g_out
+    GateArgs s = a;
+    s.tmpl = g_out;      // the register window marches over g_out rows
+    s.x = g_out;
+    s.out = g_tmpl;
+    s.out2 = g_x;
+    dim3 grid;
+    plan_chunks(B, N, CL, s, grid);
+    return dispatch_gate_stream<1>(W, s, grid, kGateThreads, stream);
+}
+
+}  // extern "C"

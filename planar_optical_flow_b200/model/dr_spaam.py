@@ -1,0 +1,148 @@
+"""DROW3 / DR-SPAAM host modules with the reference's API and checkpoint layout.
+
+Mirrors /root/reference/src/depracted/model/dr_spaam.py:
+    DROW               :41-121    constructor args, forward(x) -> (pred_cls, pred_reg)
+    _SpatialAttention  :124-217   (n_pts, n_channel, alpha, window_size); forward(x, x_template)
+    SpatialDROW        :220-277   forward(x, testing=False, fea_template=None)
+`state_dict()` keys and shapes equal the reference's, so `torch.load(f)["model_state"]`
+from a reference checkpoint loads with strict=True.
+
+What changed underneath:
+  * the gate no longer builds dense [N, N] similarity / weight matrices: after the two
+    embedding convolutions (cuDNN) it calls ONE fused sm_100a kernel
+    (csrc/pof_gate.cu) through `ops.gate`, differentiable via its own backward kernels;
+  * no neighbour table is cached on the module, so one instance serves any N
+    (the reference locks an instance to its first N);
+  * the 1-D conv backbone stays on PyTorch/cuDNN: it is the only dense contraction.
+The modules only run on CUDA tensors; there is no CPU path.
+"""
+from math import ceil
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from .loss_utils import BinaryFocalLoss, FocalLoss, flow_loss
+
+_SLOPE = 0.1
+
+
+def _conv(in_channel, out_channel, kernel_size, padding):
+    return nn.Sequential(
+        nn.Conv1d(in_channel, out_channel, kernel_size=kernel_size, padding=padding),
+        nn.BatchNorm1d(out_channel),
+        nn.LeakyReLU(negative_slope=_SLOPE, inplace=True),
+    )
+
+
+def _stack(*channels):
+    """Chain of k=3, p=1 conv-bn-lrelu layers through the given channel counts."""
+    return nn.Sequential(*[_conv(cin, cout, 3, 1) for cin, cout in zip(channels[:-1], channels[1:])])
+
+
+def _init_like_reference(module):
+    for m in module.modules():
+        if isinstance(m, (nn.Conv1d, nn.Conv2d)):
+            nn.init.kaiming_normal_(m.weight, a=_SLOPE, nonlinearity="leaky_relu")
+        elif isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d)):
+            nn.init.constant_(m.weight, 1)
+            nn.init.constant_(m.bias, 0)
+
+
+class DROW(nn.Module):
+    def __init__(self, dropout=0.5, num_scans=5, num_pts=48, focal_loss_gamma=0.0, pedestrian_only=False):
+        super().__init__()
+        self.dropout = 0.0                       # the reference forces dropout off (:46-47)
+        self.conv_block_1 = _stack(1, 64, 64, 128)
+        self.conv_block_2 = _stack(128, 128, 128, 256)
+        self.conv_block_3 = _stack(256, 256, 256, 512)
+        self.conv_block_4 = _stack(512, 256, 128)
+        if pedestrian_only:
+            self.conv_cls = nn.Conv1d(128, 1, kernel_size=1)
+            self.cls_loss = BinaryFocalLoss(gamma=focal_loss_gamma) if focal_loss_gamma > 0.0 \
+                else F.binary_cross_entropy
+        else:
+            self.conv_cls = nn.Conv1d(128, 4, kernel_size=1)
+            self.cls_loss = FocalLoss(gamma=focal_loss_gamma) if focal_loss_gamma > 0.0 else F.cross_entropy
+        self.conv_reg = nn.Conv1d(128, 2, kernel_size=1)
+        _init_like_reference(self)
+
+    # -- per-cutout feature extractor: [B, N, S, P] -> [B, N, S, 256, P/4]   (:87-97)
+    def _forward_cutout(self, x):
+        b, n, s, p = x.shape
+        y = x.reshape(b * n * s, 1, p)
+        y = F.max_pool1d(self.conv_block_1(y), kernel_size=2)
+        y = F.max_pool1d(self.conv_block_2(y), kernel_size=2)
+        return y.view(b, n, s, y.shape[-2], y.shape[-1])
+
+    def _fuse_cutout(self, x):
+        return torch.sum(x, dim=2)
+
+    # -- fused feature -> votes: [B, N, 256, L] -> ([B, N, C], [B, N, 2])     (:102-114)
+    def _forward_fused_cutout(self, x):
+        b, n, c, l = x.shape
+        y = x.reshape(b * n, c, l)
+        y = F.max_pool1d(self.conv_block_3(y), kernel_size=2)
+        y = self.conv_block_4(y)
+        y = F.avg_pool1d(y, kernel_size=y.shape[-1])
+        return self.conv_cls(y).view(b, n, -1), self.conv_reg(y).view(b, n, 2)
+
+    def forward(self, x):
+        return self._forward_fused_cutout(self._fuse_cutout(self._forward_cutout(x)))
+
+
+class _SpatialAttention(nn.Module):
+    def __init__(self, n_pts, n_channel, alpha=0.5, window_size=7):
+        super().__init__()
+        self._alpha = alpha
+        self._window_size = window_size
+        self.conv = _conv(n_channel, 128, kernel_size=n_pts, padding=0)
+        _init_like_reference(self)
+
+    @property
+    def window(self):
+        """Effective window 2*hw+1 (the reference uses hw = int(window_size / 2), :148)."""
+        return 2 * int(self._window_size / 2) + 1
+
+    def embed(self, feat):
+        b, n, c, l = feat.shape
+        return self.conv(feat.reshape(b * n, c, l)).view(b, n, -1)
+
+    def forward(self, x, x_template):
+        """(x, x_template) [B, N, C, L] -> (out_temp [B, N, C, L], feat_fused [B, N, W])."""
+        emb_x = self.embed(x)                    # :176-177
+        emb_t = self.embed(x_template)           # :180-181
+        return ops.gate(x, x_template, emb_x, emb_t, self._alpha, self.window)   # :183-215 fused
+
+
+class SpatialDROW(DROW):
+    def __init__(self, dropout=0.5, num_scans=5, num_pts=48, focal_loss_gamma=0.0, alpha=0.5, window_size=7,
+                 pedestrian_only=False):
+        super().__init__(dropout=dropout, num_scans=num_scans, num_pts=num_pts,
+                         focal_loss_gamma=focal_loss_gamma, pedestrian_only=pedestrian_only)
+        self.gate = _SpatialAttention(n_pts=int(ceil(num_pts / 4)), n_channel=256, alpha=alpha,
+                                      window_size=window_size)
+        self.loss_fn = flow_loss
+
+    def _scan_features(self, x, s):
+        return self._forward_cutout(x[:, :, s, :].unsqueeze(2)).squeeze(2)
+
+    def forward(self, x, testing=False, fea_template=None):
+        if testing:                                                   # streaming branch (:239-250)
+            out = self._scan_features(x, 0)
+            if fea_template is None:
+                out_template = out.clone()                            # first frame: memory := features
+                _, feat_fused = self.gate(out, out_template)
+            else:
+                out_template, feat_fused = self.gate(out, fea_template)
+            pred_cls, pred_reg = self._forward_fused_cutout(out_template)
+            return pred_cls, pred_reg, out_template, feat_fused
+
+        n_scan = x.shape[2]                                           # training / eval branch (:262-277)
+        out_template = self._scan_features(x, 0)
+        feat_fused = None
+        for s in range(1, max(n_scan, 2)):          # a single-scan input gates scan 0 with itself (:271-273)
+            out_template, feat_fused = self.gate(self._scan_features(x, min(s, n_scan - 1)), out_template)
+        pred_cls, pred_reg = self._forward_fused_cutout(out_template)
+        return pred_cls, pred_reg, feat_fused

@@ -1,0 +1,176 @@
+"""Device-level operators: torch CUDA tensors in, torch CUDA tensors out.
+
+Thin, allocation-only wrappers over the C ABI (include/pof.h).  torch is used
+for device memory, streams and autograd plumbing; all arithmetic of the three
+hot-path stages happens in libpof.so.  There is no CPU implementation: every
+function raises if handed a CPU tensor.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, current_stream_ptr, require_cuda_tensor
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+# --------------------------------------------------------------------------- cutout
+def cutout(scans, phi, stride=1, centered=True, fixed=False, window_width=1.66, window_depth=1.0,
+           num_cutout_pts=48, padding_val=29.99, area_mode=False, out=None, return_s_area=False):
+    """Batched `scans_to_cutout` (reference: src/utils/utils.py:259-334).
+
+    scans [B, S, N] float32 CUDA, phi [N] float32|float64 CUDA  ->  [B, M, S, P] float32,
+    M = ceil(N / stride).  Each b is one independent reference call (its own `s_area`).
+    """
+    require_cuda_tensor(scans, "scans", torch.float32)
+    require_cuda_tensor(phi, "phi")
+    if scans.dim() != 3:
+        raise ValueError("scans must be [B, S, N] (got %s)" % (tuple(scans.shape),))
+    if phi.dtype not in (torch.float32, torch.float64):
+        raise TypeError("phi must be float32 or float64 (got %s)" % phi.dtype)
+    B, S, N = scans.shape
+    if phi.numel() != N:
+        raise ValueError("phi has %d angles for %d-point scans" % (phi.numel(), N))
+    P = int(num_cutout_pts)
+    M = (N + stride - 1) // stride
+    dev = scans.device
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((B, M, S, P), dtype=torch.float32, device=dev)
+        else:
+            require_cuda_tensor(out, "out", torch.float32)
+            if tuple(out.shape) != (B, M, S, P):
+                raise ValueError("out must be %s" % ((B, M, S, P),))
+        L = _lib.lib()
+        ws_bytes = L.pof_cutout_ws_bytes(B)
+        ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
+        s_area = torch.empty(max(B, 1), dtype=torch.int32, device=dev) if return_s_area else None
+        check(L.pof_cutout_fwd(_ptr(scans), _ptr(phi), int(phi.dtype == torch.float64), B, S, N, int(stride), P,
+                               float(window_width), float(window_depth), float(padding_val),
+                               int(bool(fixed)), int(bool(centered)), int(bool(area_mode)),
+                               _ptr(out), _ptr(s_area), _ptr(ws), ws_bytes, current_stream_ptr(dev)),
+              "pof_cutout_fwd")
+    if return_s_area:
+        return out, s_area[:B]
+    return out
+
+
+# --------------------------------------------------------------------------- gate
+def gate_forward(x, tmpl, emb_x, emb_t, alpha, window, want_weights=False, out=None):
+    """Windowed attention memory update (reference: dr_spaam.py:183-215).
+
+    x, tmpl [B, N, C, L] (or [B, N, CL]) float32; emb_* [B, N, E] float32; window = 2*hw+1.
+    Returns (out_tmpl like x, feat_fused [B, N, W], attn_w [B, N, W] or None).
+    """
+    for name, t in (("x", x), ("tmpl", tmpl), ("emb_x", emb_x), ("emb_t", emb_t)):
+        require_cuda_tensor(t, name, torch.float32)
+    if x.shape != tmpl.shape:
+        raise ValueError("x %s and template %s differ" % (tuple(x.shape), tuple(tmpl.shape)))
+    B, N = x.shape[0], x.shape[1]
+    CL = x[0, 0].numel()
+    E = emb_x.shape[-1]
+    if tuple(emb_x.shape) != (B, N, E) or tuple(emb_t.shape) != (B, N, E):
+        raise ValueError("embeddings must be [B, N, E]")
+    dev = x.device
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty_like(x)
+        feat = torch.empty((B, N, window), dtype=torch.float32, device=dev)
+        attn = torch.empty((B, N, window), dtype=torch.float32, device=dev) if want_weights else None
+        check(_lib.lib().pof_spaam_gate_fwd(_ptr(x), _ptr(tmpl), _ptr(emb_x), _ptr(emb_t), B, N, CL, E, int(window),
+                                            float(alpha), _ptr(out), _ptr(feat), _ptr(attn), current_stream_ptr(dev)),
+              "pof_spaam_gate_fwd")
+    return out, feat, attn
+
+
+def gate_backward(tmpl, emb_x, emb_t, attn_w, g_out, g_feat, alpha, window):
+    """Gradients of `gate_forward` w.r.t. (x, tmpl, emb_x, emb_t)."""
+    B, N = tmpl.shape[0], tmpl.shape[1]
+    CL = tmpl[0, 0].numel()
+    E = emb_x.shape[-1]
+    dev = tmpl.device
+    g_out = g_out.contiguous()
+    g_feat = g_feat.contiguous() if g_feat is not None else None
+    with torch.cuda.device(dev):
+        g_x = torch.empty_like(tmpl)
+        g_t = torch.empty_like(tmpl)
+        g_ex = torch.empty_like(emb_x)
+        g_et = torch.empty_like(emb_t)
+        L = _lib.lib()
+        ws_bytes = L.pof_spaam_gate_bwd_ws_bytes(B, N, int(window))
+        ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=dev)
+        check(L.pof_spaam_gate_bwd(_ptr(tmpl), _ptr(emb_x), _ptr(emb_t), _ptr(attn_w), _ptr(g_out), _ptr(g_feat),
+                                   B, N, CL, E, int(window), float(alpha),
+                                   _ptr(g_x), _ptr(g_t), _ptr(g_ex), _ptr(g_et), _ptr(ws), ws_bytes,
+                                   current_stream_ptr(dev)),
+              "pof_spaam_gate_bwd")
+    return g_x, g_t, g_ex, g_et
+
+
+class _GateFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, tmpl, emb_x, emb_t, alpha, window):
+        x, tmpl = x.contiguous(), tmpl.contiguous()
+        emb_x, emb_t = emb_x.contiguous(), emb_t.contiguous()
+        need = any(ctx.needs_input_grad[:4])
+        out, feat, attn = gate_forward(x, tmpl, emb_x, emb_t, alpha, window, want_weights=need)
+        if need:
+            ctx.save_for_backward(tmpl, emb_x, emb_t, attn)
+        ctx.alpha, ctx.window = alpha, window
+        return out, feat
+
+    @staticmethod
+    def backward(ctx, g_out, g_feat):
+        tmpl, emb_x, emb_t, attn = ctx.saved_tensors
+        g_x, g_t, g_ex, g_et = gate_backward(tmpl, emb_x, emb_t, attn, g_out, g_feat, ctx.alpha, ctx.window)
+        return g_x, g_t, g_ex, g_et, None, None
+
+
+def gate(x, tmpl, emb_x, emb_t, alpha, window):
+    """Differentiable fused gate: returns (out_tmpl, feat_fused)."""
+    return _GateFn.apply(x, tmpl, emb_x, emb_t, float(alpha), int(window))
+
+
+# --------------------------------------------------------------------------- nms
+def nms_centers(scan, phi, cls, reg, min_dist=0.5):
+    """Batched `nms_predicted_center` (reference: src/utils/utils.py:535-571).
+
+    scan [B, N] float32|float64, phi [N] float32|float64, cls [B, N] float32 (post-sigmoid),
+    reg [B, N, 2] float32; all CUDA.  Returns a dict of device tensors:
+      order [B,N] i32, keep_idx [B,N] i32, n_keep [B] i32, instance_mask [B,N] i32,
+      det_xy [B,N,2] f64, det_cls [B,N] f32  (first n_keep[b] rows of the last three are valid).
+    """
+    require_cuda_tensor(scan, "scan")
+    require_cuda_tensor(phi, "phi")
+    require_cuda_tensor(cls, "cls", torch.float32)
+    require_cuda_tensor(reg, "reg", torch.float32)
+    for name, t in (("scan", scan), ("phi", phi)):
+        if t.dtype not in (torch.float32, torch.float64):
+            raise TypeError("%s must be float32 or float64" % name)
+    B, N = scan.shape
+    if tuple(cls.shape) != (B, N) or tuple(reg.shape) != (B, N, 2) or phi.numel() != N:
+        raise ValueError("shape mismatch: scan %s cls %s reg %s phi %s" %
+                         (tuple(scan.shape), tuple(cls.shape), tuple(reg.shape), tuple(phi.shape)))
+    dev = scan.device
+    with torch.cuda.device(dev):
+        i32 = dict(dtype=torch.int32, device=dev)
+        res = {
+            "order": torch.empty((B, N), **i32),
+            "keep_idx": torch.empty((B, N), **i32),
+            "n_keep": torch.empty((B,), **i32),
+            "instance_mask": torch.empty((B, N), **i32),
+            "det_xy": torch.empty((B, N, 2), dtype=torch.float64, device=dev),
+            "det_cls": torch.empty((B, N), dtype=torch.float32, device=dev),
+        }
+        L = _lib.lib()
+        ws_bytes = L.pof_nms_ws_bytes(B, N)
+        ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=dev)
+        check(L.pof_nms_centers(_ptr(scan), int(scan.dtype == torch.float64), _ptr(phi), int(phi.dtype == torch.float64),
+                                _ptr(cls), _ptr(reg), B, N, float(min_dist),
+                                _ptr(res["order"]), _ptr(res["keep_idx"]), _ptr(res["n_keep"]), _ptr(res["instance_mask"]),
+                                _ptr(res["det_xy"]), _ptr(res["det_cls"]), _ptr(ws), ws_bytes, current_stream_ptr(dev)),
+              "pof_nms_centers")
+    return res

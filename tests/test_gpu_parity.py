@@ -1,0 +1,331 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden
+reference fixtures.  Needs a B200: run with `-m gpu`."""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cutout as ocut
+from oracle import model as omodel
+from oracle import nms as onms
+from planar_optical_flow_b200 import ops, synth, utils
+from planar_optical_flow_b200.model import SpatialDROW, _SpatialAttention
+from tests.helpers import REL_TOL, assert_rel, cutout_mismatch_report, rel_err
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(fixed=True, centered=True, window_width=1.0, window_depth=0.5,
+           num_cutout_pts=56, padding_val=29.99, area_mode=True)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def strict_fp32():
+    """Parity mode: no TF32 anywhere (the 1e-5 bar is an fp32 bar)."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_device_is_blackwell_and_extension_loaded():
+    from planar_optical_flow_b200 import _lib
+
+    sm, major, minor = _lib.device_info()
+    assert major == 10, "libpof.so is built for sm_100a only"
+    assert sm >= 100
+
+
+# ------------------------------------------------------------------ cutout
+def _check_cutout(scans, phi, kw, stride=1):
+    want = ocut.scans_to_cutout(scans, phi, stride=stride, **kw)
+    got = utils.scans_to_cutout(scans, phi, stride=stride, **kw)
+    assert got.dtype == np.float32 and got.shape == want.shape
+    diag = ocut.cutout_diagnostics(scans, phi, stride=stride, **kw)
+    n_bad, n_excused, worst = cutout_mismatch_report(got, want, diag)
+    assert n_bad == n_excused, "%d samples off by more than 1e-5 away from any rounding boundary (worst %.3g)" % (
+        n_bad - n_excused, worst)
+    assert n_bad <= max(4, got.size // 20000), "too many boundary flips: %d of %d" % (n_bad, got.size)
+    return n_bad, float((got == want).mean())
+
+
+@pytest.mark.parametrize("shape", ["drow", "jrdb"])
+@pytest.mark.parametrize("kind", ["adversarial", "structured", "edge"])
+@pytest.mark.parametrize("flags", [dict(), dict(fixed=False), dict(centered=False), dict(area_mode=False),
+                                   dict(window_width=1.66, window_depth=1.0, num_cutout_pts=48)])
+def test_cutout_matches_oracle(shape, kind, flags):
+    phi = synth.phi_for(shape)
+    n = len(phi)
+    scans = {"adversarial": lambda: synth.adversarial_scans(3, n, seed=11),
+             "structured": lambda: synth.structured_sequence(3, n, seed=12, phi=phi),
+             "edge": lambda: synth.edge_scans(n, seed=13)}[kind]()
+    n_bad, frac_equal = _check_cutout(scans, phi, dict(CFG, **flags))
+    assert frac_equal > 0.999        # essentially bit-equal; the rest within 1e-5
+
+
+@pytest.mark.parametrize("name", ["cutout_drow_adversarial", "cutout_drow_structured_lastref", "cutout_drow_edge",
+                                  "cutout_jrdb_adversarial", "cutout_jrdb_structured_raw", "cutout_drow_linear48"])
+def test_cutout_matches_reference_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    kw = dict(ast.literal_eval(str(g["kwargs"])))
+    got = utils.scans_to_cutout(g["scans"], g["phi"], stride=1, **kw)
+    diag = ocut.cutout_diagnostics(g["scans"], g["phi"], stride=1, **kw)
+    n_bad, n_excused, worst = cutout_mismatch_report(got, g["out"], diag)
+    assert n_bad == n_excused and n_bad <= 4, (n_bad, n_excused, worst)
+
+
+def test_cutout_stride_ragged_and_batched():
+    phi = synth.drow_phi()
+    scans = synth.adversarial_scans(2, 450, seed=3)
+    for stride in (2, 3, 7):
+        _check_cutout(scans, phi, CFG, stride=stride)
+    # odd point counts, tiny scans
+    for n in (2, 5, 33, 129):
+        p = synth.drow_phi(n)
+        _check_cutout(synth.adversarial_scans(2, n, seed=n), p, CFG)
+    # batched entry point == per-sample calls, each with its own s_area
+    batch = np.stack([synth.adversarial_scans(3, 450, seed=50 + b, lo=0.3 + 0.4 * b) for b in range(5)])
+    out, s_area = ops.cutout(torch.from_numpy(batch).cuda(), torch.from_numpy(phi).cuda(), return_s_area=True, **CFG)
+    for b in range(5):
+        assert np.array_equal(out[b].cpu().numpy(), utils.scans_to_cutout(batch[b], phi, **CFG))
+        assert int(s_area[b]) == ocut.cutout_diagnostics(batch[b], phi, **CFG)["s_area"]
+    assert len(set(s_area.tolist())) > 1          # the per-sample reduction really is per sample
+    empty = ops.cutout(torch.zeros(0, 1, 450, device="cuda"), torch.from_numpy(phi).cuda(), **CFG)
+    assert tuple(empty.shape) == (0, 450, 1, 56)
+
+
+def test_cutout_torch_signature_and_full_size_properties():
+    """BASELINE config 2 size (B=4096 JRDB rows): properties that need no oracle pass."""
+    phi = synth.jrdb_phi()
+    B = 4096
+    g = torch.Generator(device="cuda").manual_seed(0)
+    scans = torch.rand(B, 1, 1091, device="cuda", generator=g) * 24.7 + 0.3
+    out = ops.cutout(scans, torch.from_numpy(phi).cuda(), **CFG)
+    assert tuple(out.shape) == (B, 1091, 1, 56)
+    assert bool(torch.isfinite(out).all()) and float(out.abs().max()) <= 1.0     # centred + depth-normalised
+    # batch-order independence and determinism
+    perm = torch.randperm(B, device="cuda", generator=g)
+    out_p = ops.cutout(scans[perm].contiguous(), torch.from_numpy(phi).cuda(), **CFG)
+    assert torch.equal(out_p, out[perm])
+    # spot rows against the oracle
+    for b in (0, 1777, 4095):
+        want = ocut.scans_to_cutout(scans[b].cpu().numpy(), phi, **CFG)
+        diag = ocut.cutout_diagnostics(scans[b].cpu().numpy(), phi, **CFG)
+        n_bad, n_exc, _ = cutout_mismatch_report(out[b].cpu().numpy(), want, diag)
+        assert n_bad == n_exc
+    t = utils.scans_to_cutout_torch(scans[0], torch.from_numpy(phi).cuda(), **CFG)
+    assert torch.equal(t, out[0])
+
+
+# ------------------------------------------------------------------ gate
+def _gate_inputs(b, n, seed, e=128, cl=(256, 14)):
+    x = torch.from_numpy(synth.feature_like((b, n) + cl, seed))
+    t = torch.from_numpy(synth.feature_like((b, n) + cl, seed + 1))
+    ex = torch.from_numpy(synth.feature_like((b, n, e), seed + 2)) * 0.7
+    et = torch.from_numpy(synth.feature_like((b, n, e), seed + 3)) * 0.7
+    return x, t, ex, et
+
+
+@pytest.mark.parametrize("b,n,window", [(1, 450, 11), (2, 1091, 11), (3, 37, 7), (1, 5, 11), (2, 1, 3), (1, 200, 1),
+                                        (1, 161, 15), (2, 64, 5)])
+def test_gate_kernel_matches_windowed_oracle(b, n, window):
+    x, t, ex, et = _gate_inputs(b, n, seed=7 * n + window)
+    want_out, want_ff, want_w = omodel.gate_windowed(x, t, ex, et, 0.5, window)
+    out, ff, w = ops.gate_forward(x.cuda(), t.cuda(), ex.cuda(), et.cuda(), 0.5, window, want_weights=True)
+    assert_rel(ff.cpu(), want_ff, what="feat_fused")
+    assert_rel(out.cpu(), want_out, what="out_temp")
+    assert_rel(w.cpu(), want_w, tol=1e-4, what="attn weights")
+    assert float(w.sum(-1).sub(1).abs().max()) < 1e-5
+
+
+def test_gate_other_shapes_alpha_and_aliasing_guard():
+    # non-DR-SPAAM feature width (not a multiple of the 512-channel slice), E = 64
+    x, t, ex, et = _gate_inputs(2, 77, seed=5, e=64, cl=(50, 6))
+    for alpha in (0.0, 0.3, 1.0):
+        want_out, want_ff, _ = omodel.gate_windowed(x, t, ex, et, alpha, 11)
+        out, ff, _ = ops.gate_forward(x.cuda(), t.cuda(), ex.cuda(), et.cuda(), alpha, 11)
+        assert_rel(out.cpu(), want_out)
+        assert_rel(ff.cpu(), want_ff)
+    xc, tc = x.cuda(), t.cuda()
+    with pytest.raises(RuntimeError, match="alias"):
+        ops.gate_forward(xc, tc, ex.cuda(), et.cuda(), 0.5, 11, out=tc)
+
+
+def test_gate_module_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "gate_n24.npz"))
+    seed = int(g["seed"])
+    sd = omodel.randomize_bn_stats(omodel.init_state_dict(56, True, seed=seed), seed=seed + 1)
+    gate = _SpatialAttention(n_pts=14, n_channel=256, alpha=0.5, window_size=11)
+    gate.load_state_dict({k[5:]: v for k, v in sd.items() if k.startswith("gate.")}, strict=True)
+    gate.cuda().eval()
+    x = torch.from_numpy(synth.feature_like((1, 24, 256, 14), seed + 2)).cuda()
+    t = torch.from_numpy(synth.feature_like((1, 24, 256, 14), seed + 3)).cuda()
+    with torch.no_grad():
+        out, ff = gate(x, t)
+    assert_rel(ff.cpu().numpy(), g["feat_fused"], what="feat_fused vs reference")
+    assert_rel(out.cpu().numpy(), g["out_temp"], what="out_temp vs reference")
+
+
+def test_gate_ablation_uniform_weights():
+    """Reference ablation (dr_spaam.py:166-169): with identical embeddings everywhere the
+    weights are uniform over the in-range window, so out = alpha*x + (1-alpha)*window mean."""
+    b, n, window = 1, 40, 11
+    x, t, _, _ = _gate_inputs(b, n, seed=9)
+    ex = torch.ones(b, n, 128)
+    out, ff, w = ops.gate_forward(x.cuda(), t.cuda(), ex.cuda(), ex.cuda(), 0.5, window, want_weights=True)
+    flat = t.reshape(b, n, -1)
+    for i in (0, 3, 20, 39):
+        lo, hi = max(0, i - 5), min(n - 1, i + 5)
+        want = 0.5 * x.reshape(b, n, -1)[0, i] + 0.5 * flat[0, lo:hi + 1].mean(0)
+        assert_rel(out.cpu().reshape(b, n, -1)[0, i], want)
+    assert float((ff.cpu() - 128.0).abs().max()) == 0.0
+
+
+def test_gate_backward_matches_autograd_of_oracle():
+    b, n, window = 2, 53, 11
+    x, t, ex, et = _gate_inputs(b, n, seed=21, cl=(32, 6))
+    ins_cpu = [v.clone().double().requires_grad_(True) for v in (x, t, ex, et)]
+    out_c, ff_c, _ = omodel.gate_windowed(*ins_cpu, 0.5, window)
+    g_out = torch.from_numpy(synth.feature_like(tuple(out_c.shape), 31))
+    g_ff = torch.from_numpy(synth.feature_like(tuple(ff_c.shape), 32)) * 0.1
+    (out_c * g_out.double()).sum().add((ff_c * g_ff.double()).sum()).backward()
+
+    ins = [v.clone().cuda().requires_grad_(True) for v in (x, t, ex, et)]
+    out, ff = ops.gate(*ins, 0.5, window)
+    ((out * g_out.cuda()).sum() + (ff * g_ff.cuda()).sum()).backward()
+    for got, want, name in zip(ins, ins_cpu, ("g_x", "g_tmpl", "g_emb_x", "g_emb_t")):
+        assert_rel(got.grad.cpu(), want.grad, tol=2e-5, what=name)
+
+
+# ------------------------------------------------------------------ NMS
+def _nms_case(shape, seed, scan_dtype):
+    phi = synth.phi_for(shape)
+    n = len(phi)
+    scan = synth.structured_sequence(1, n, seed=100 + seed, phi=phi)[0].astype(scan_dtype)
+    return scan, phi, synth.distinct_scores(n, seed), synth.clustered_votes(scan.astype(np.float64), phi, seed)
+
+
+@pytest.mark.parametrize("shape", ["drow", "jrdb"])
+@pytest.mark.parametrize("scan_dtype", [np.float32, np.float64])
+def test_nms_indices_bit_exact(shape, scan_dtype):
+    flips = 0
+    for seed in range(8):
+        scan, phi, cls, reg = _nms_case(shape, seed, scan_dtype)
+        want_xy, want_cls, want_mask = onms.nms_predicted_center(scan, phi, cls, reg)
+        spec = onms.nms_sweep_spec(scan, phi, cls, reg)
+        xy, c, mask = utils.nms_predicted_center(scan, phi, cls, reg)
+        assert mask.dtype == np.int32 and xy.dtype == want_xy.dtype and c.dtype == want_cls.dtype
+        if spec["margin"] < 1e-6 and not np.array_equal(mask, want_mask):
+            flips += 1            # a pair sits within float rounding of the 0.5 m threshold
+            continue
+        assert np.array_equal(mask, want_mask), "instance_mask differs (margin %.3g)" % spec["margin"]
+        assert np.array_equal(c, want_cls)
+        assert xy.shape == want_xy.shape
+        assert_rel(xy, want_xy, tol=1e-6 if scan_dtype == np.float32 else 1e-12)
+    assert flips <= 1
+
+
+@pytest.mark.parametrize("name", ["nms_drow_f32scan", "nms_drow_f64scan", "nms_jrdb_f32scan", "nms_jrdb_f64scan"])
+def test_nms_matches_reference_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    xy, c, mask = utils.nms_predicted_center(g["scan"], g["phi"], g["cls"], g["reg"])
+    assert np.array_equal(mask, g["instance_mask"])
+    assert np.array_equal(c, g["det_cls"])
+    assert_rel(xy, g["det_xys"], tol=1e-6)
+
+
+def test_nms_batched_order_keep_and_edges():
+    phi = synth.jrdb_phi()
+    cases = [_nms_case("jrdb", s, np.float32) for s in range(6)]
+    scan = torch.from_numpy(np.stack([c[0] for c in cases])).cuda()
+    cls = torch.from_numpy(np.stack([c[2][:, 0] for c in cases])).cuda()
+    reg = torch.from_numpy(np.stack([c[3] for c in cases])).cuda()
+    res = ops.nms_centers(scan, torch.from_numpy(phi).cuda(), cls, reg)
+    for b, (s, p, c, r) in enumerate(cases):
+        spec = onms.nms_sweep_spec(s, p, c, r)
+        k = int(res["n_keep"][b])
+        assert np.array_equal(res["order"][b].cpu().numpy(), spec["order"])
+        assert np.array_equal(res["keep_idx"][b, :k].cpu().numpy(), spec["keep_idx"])
+        assert np.array_equal(res["instance_mask"][b].cpu().numpy(), spec["instance_mask"])
+    # single point, all-coincident votes, min_dist = 0 (nothing suppresses anything, not even itself)
+    one = utils.nms_predicted_center(np.array([2.0], np.float32), np.array([0.1]), np.array([[0.7]], np.float32),
+                                     np.zeros((1, 2), np.float32))
+    assert one[0].shape == (1, 2) and one[2].tolist() == [1]
+    n = 70
+    phi70 = synth.drow_phi(n)
+    scan70 = np.full(n, 3.0, np.float32)
+    cls70 = synth.distinct_scores(n, 5)
+    reg70 = synth.clustered_votes(scan70.astype(np.float64), phi70, 5, n_people=1, spread=0.0)
+    for md in (0.5, 0.0, 100.0):
+        want = onms.nms_predicted_center(scan70, phi70, cls70, reg70, min_dist=md)
+        got = utils.nms_predicted_center(scan70, phi70, cls70, reg70, min_dist=md)
+        assert np.array_equal(got[2], want[2]) and got[0].shape == want[0].shape
+    # tied scores: documented rule = stable argsort reversed
+    tied = np.repeat(np.array([[0.9], [0.2], [0.5]], np.float32), 10, axis=0)
+    scan30, phi30 = np.full(30, 4.0, np.float32), synth.drow_phi(30)
+    reg30 = np.zeros((30, 2), np.float32)
+    want = onms.nms_predicted_center(scan30, phi30, tied, reg30)
+    got = utils.nms_predicted_center(scan30, phi30, tied, reg30)
+    assert np.array_equal(got[2], want[2]) and np.array_equal(got[1], want[1])
+
+
+# ------------------------------------------------------------------ whole model
+def _product_model(sd, window=11):
+    m = SpatialDROW(num_scans=10, num_pts=56, alpha=0.5, window_size=window, pedestrian_only=True)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda()
+
+
+def test_streaming_model_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "model_stream_drow40.npz"))
+    seed = int(g["seed"])
+    sd = omodel.randomize_bn_stats(omodel.init_state_dict(56, True, seed=seed), seed=seed + 1)
+    m = _product_model(sd).eval()
+    scans, phi = g["scans"], g["phi"]
+    phi_d = torch.from_numpy(phi).cuda()
+    tmpl = None
+    with torch.no_grad():
+        for t in range(scans.shape[1]):
+            ct = ops.cutout(torch.from_numpy(scans[:, t:t + 1]).cuda(), phi_d, **CFG)
+            cls, reg, tmpl, ff = m(ct, testing=True, fea_template=tmpl)
+            assert_rel(cls.cpu().numpy(), g["cls_%d" % t], tol=2e-5, what="pred_cls step %d" % t)
+            assert_rel(reg.cpu().numpy(), g["reg_%d" % t], tol=2e-5, what="pred_reg step %d" % t)
+            assert_rel(ff.cpu().numpy(), g["feat_fused_%d" % t], tol=2e-5, what="feat_fused step %d" % t)
+    assert_rel(tmpl.cpu().numpy()[:, ::8, ::16], g["template_last_sample"], tol=2e-5)
+
+
+def test_one_instance_serves_any_point_count():
+    """The reference locks a module to its first N; this one must not."""
+    sd = omodel.init_state_dict(56, True, seed=2)
+    m = _product_model(sd).eval()
+    with torch.no_grad():
+        for n in (450, 1091, 64):
+            x = torch.randn(1, n, 1, 56, device="cuda")
+            cls, reg, tmpl, ff = m(x, testing=True)
+            assert tuple(ff.shape) == (1, n, 11) and tuple(tmpl.shape) == (1, n, 256, 14)
+
+
+def test_training_branch_forward_backward_matches_oracle():
+    torch.manual_seed(0)
+    sd = omodel.randomize_bn_stats(omodel.init_state_dict(56, True, seed=8))
+    x = torch.randn(2, 19, 4, 56)
+    # oracle, train-mode BN, autograd through the dense gate
+    sd_o = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    cls_o, reg_o, ff_o = omodel.spatial_drow_sequence(x, sd_o, 0.5, 11, training=True)
+    loss_o = cls_o.square().mean() + reg_o.square().mean() + 1e-3 * ff_o.square().mean()
+    loss_o.backward()
+    m = _product_model(sd).train()
+    cls, reg, ff = m(x.cuda())
+    loss = cls.square().mean() + reg.square().mean() + 1e-3 * ff.square().mean()
+    loss.backward()
+    assert_rel(cls.detach().cpu(), cls_o.detach(), tol=1e-4)
+    assert_rel(ff.detach().cpu(), ff_o.detach(), tol=1e-4)
+    assert abs(loss.item() - loss_o.item()) <= 1e-4 * abs(loss_o.item())
+    for name, p in m.named_parameters():
+        want = sd_o[name].grad
+        assert rel_err(p.grad.cpu(), want) < 2e-3, name      # fp32 conv backward on two devices
+    for name, buf in m.named_buffers():
+        if "running" in name:
+            assert_rel(buf.cpu(), sd_o[name].detach(), tol=1e-4, what=name)
