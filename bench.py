@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the DR-SPAAM per-point scan hot path on B200 (see BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--sequences 256] [--shape jrdb|drow] [--precision fp32|tf32]
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on): DR-SPAAM streaming
+inference with spatial-attention memory over 256 independent JRDB-shaped sequences
+(1091 points, 360 deg) per GPU; one "step" = one scan of every sequence through
+cutout -> conv backbone -> attention memory update -> heads -> sigmoid -> NMS, memory carried.
+
+One JSON line on stdout (rank 0):
+  value      scans/s, whole job, ranges already resident in HBM when the timed region starts
+  e2e        the same through StreamingDetector.step(host buffers): H2D of the ranges and D2H
+             of the detections inside the timed region
+  roofline   the attention-memory kernel (dominant libpof kernel by bytes): algorithmic bytes
+             (N*44,076 B per sequence-step) / mean launch time from CUDA events
+             recorded around every launch inside the timed steps, against MEASURED_PEAKS.json
+  cpu_baseline  the oracle (CPU restatement of the reference, NumPy + torch CPU) timed on this
+             box's host cores on a bounded sample of the same workload
+`--impl reference` times that CPU path alone, as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CUTOUT_KW = dict(fixed=True, centered=True, window_width=1.0, window_depth=0.5, num_cutout_pts=56,
+                 padding_val=29.99, area_mode=True)          # config/dr_spaam.yaml:21-28
+ALPHA, WINDOW = 0.5, 11                                      # config/dr_spaam.yaml:16-18
+METRIC = "DR-SPAAM scans/sec (JRDB 1091-pt)"
+FALLBACK_HBM_GBS = 6650.0                                    # /opt/skills/guides/B200_PROFILING.md
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sequences", type=int, default=256, help="sequences per GPU")
+    ap.add_argument("--shape", default="jrdb", choices=["jrdb", "drow"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--cpu-scans", type=int, default=24, help="scans in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extra-tf32", action="store_true", help="also report a TF32 throughput-mode number")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- synthetic workload
+def make_sequences(shape, n_seq, n_steps, seed0):
+    """[n_steps, n_seq, N] float32 ranges; sequence id seeds the generator."""
+    import numpy as np
+
+    from planar_optical_flow_b200 import synth
+
+    phi = synth.phi_for(shape)
+    n = len(phi)
+    # a handful of structured walks, tiled with per-sequence noise: generation cost stays bounded
+    base = [synth.structured_sequence(n_steps, n, seed=seed0 + k, phi=phi) for k in range(min(n_seq, 16))]
+    rs = np.random.RandomState(seed0)
+    out = np.empty((n_steps, n_seq, n), dtype=np.float32)
+    for b in range(n_seq):
+        jitter = rs.normal(0.0, 0.02, size=(n_steps, n)).astype(np.float32)
+        out[:, b] = np.clip(base[b % len(base)] + jitter, 0.05, 29.99)
+    return phi, out
+
+
+def build_model(seed=0):
+    import torch
+
+    from planar_optical_flow_b200.model import SpatialDROW
+
+    torch.manual_seed(seed)
+    m = SpatialDROW(num_scans=10, num_pts=CUTOUT_KW["num_cutout_pts"], alpha=ALPHA, window_size=WINDOW,
+                    pedestrian_only=True)
+    # non-trivial BN statistics so folding is exercised (random-init weights, no checkpoint offline)
+    g = torch.Generator().manual_seed(seed + 1)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=g) * 0.1)
+            mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) * 0.5 + 0.75)
+    return m.eval()
+
+
+# ----------------------------------------------------------------------------- CPU reference path
+def cpu_reference_scans_per_s(shape, n_scans, warmup=2, sequences=1):
+    """The reference's algorithm on the host cores (oracle/, all threads torch can use).
+
+    Streams `sequences` independent sequences one scan at a time exactly like the reference loop
+    (depracted_scripts/infer_person_flow.py:101-139): NumPy cutout -> torch-CPU SpatialDROW with
+    dense attention -> sigmoid -> NumPy NMS.
+    """
+    import numpy as np
+    import torch
+
+    from oracle import cutout as ocut
+    from oracle import model as omodel
+    from oracle import nms as onms
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = build_model()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    per_seq = -(-(n_scans + warmup * sequences) // sequences)
+    phi, scans = make_sequences(shape, sequences, per_seq, seed0=900)
+    tmpl = [None] * sequences
+    done, t0 = 0, None
+    stage = {"cutout": 0.0, "model": 0.0, "nms": 0.0}
+    with torch.no_grad():
+        for t in range(per_seq):
+            for b in range(sequences):
+                if done == warmup * sequences:
+                    t0 = time.perf_counter()
+                    stage = {k: 0.0 for k in stage}
+                a = time.perf_counter()
+                ct = ocut.scans_to_cutout(scans[t, b][None], phi, stride=1, **CUTOUT_KW)
+                c = time.perf_counter()
+                cls, reg, tmpl[b], _ = omodel.spatial_drow_stream(torch.from_numpy(ct)[None], sd, ALPHA, WINDOW, tmpl[b])
+                conf = torch.sigmoid(cls[0]).numpy()
+                d = time.perf_counter()
+                onms.nms_predicted_center(scans[t, b], phi, conf, reg[0].numpy())
+                e = time.perf_counter()
+                stage["cutout"] += c - a
+                stage["model"] += d - c
+                stage["nms"] += e - d
+                done += 1
+    timed = done - warmup * sequences
+    dt = time.perf_counter() - t0
+    return timed / dt, cores, timed, {k: 1e3 * v / timed for k, v in stage.items()}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:      # noqa: BLE001  (nvidia-smi hiccup: skip the sample)
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:      # noqa: BLE001
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from planar_optical_flow_b200.engine import StreamingDetector
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, K, W = args.sequences, args.steps, args.warmup
+    phi, scans = make_sequences(args.shape, B, W + K, seed0=1000 * rank)      # every rank owns ITS sequences
+    N = len(phi)
+    model = build_model()
+
+    def timed_run(precision, host_path, record):
+        det = StreamingDetector(model, phi, CUTOUT_KW, B, device=dev, precision=precision, record_events=record)
+        d_scans = torch.from_numpy(scans).to(dev)
+        run = (lambda t: det.step(scans[t])) if host_path else (lambda t: det.step_device(d_scans[t]))
+        checksum = 0
+        for t in range(W):
+            run(t)
+        det.events = {k: [] for k in det.events}
+        launches0 = det.kernel_launches
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t in range(W, W + K):
+            res = run(t)
+            if host_path:
+                checksum += int(res["n_keep"].sum())
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if not host_path:
+            checksum = int(res["n_keep"].sum().item())
+        return float(ms.item()), det, det.kernel_launches - launches0, checksum
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_dev, det, launches, _ = timed_run(args.precision, host_path=False, record=True)
+    gate_ms = det.event_ms("gate")
+    cut_ms = det.event_ms("cutout")
+    nms_ms = det.event_ms("nms")
+    chunk_seqs = det.seq_chunk
+    h2d, d2h = det.h2d_bytes_per_step, det.d2h_bytes_per_step
+    del det
+    torch.cuda.empty_cache()
+    ms_e2e, det2, _, n_det = timed_run(args.precision, host_path=True, record=False)
+    del det2
+    torch.cuda.empty_cache()
+    clocks = sampler.stop() if sampler else None
+    extra = None
+    if args.extra_tf32:
+        ms_tf32, d3, _, _ = timed_run("tf32", host_path=False, record=False)
+        del d3
+        extra = {"precision": "tf32 convolutions (PyTorch default on GPU; ~1e-3, NOT the parity mode)",
+                 "value": world * B * K / (ms_tf32 / 1e3), "unit": "scans/s", "ms_per_step": ms_tf32 / K}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_hbm_peak()
+    # algorithmic bytes per launch: SURVEY.md §8d per-unit figure x sequences in one launch
+    gate_bytes_per_seq = N * 44076
+    per_launch_seqs = [min(chunk_seqs, B - b0) for b0 in range(0, B, chunk_seqs)]
+    seqs_per_launch = sum(per_launch_seqs) / len(per_launch_seqs)
+    gate_avg_ms = sum(gate_ms) / len(gate_ms)
+    gate_gbs = gate_bytes_per_seq * seqs_per_launch / (gate_avg_ms * 1e-3) / 1e9
+    cut_avg_ms = sum(cut_ms) / len(cut_ms)
+    cut_gbs = N * 228 * seqs_per_launch / (cut_avg_ms * 1e-3) / 1e9
+    out = {
+        "metric": METRIC, "value": world * B * K / (ms_dev / 1e3), "unit": "scans/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+        "impl": "ours",
+        "config": {"workload": "DR-SPAAM streaming inference, %d independent %s-shaped sequences per GPU (%d pts), "
+                               "cutout+backbone+attention memory+heads+NMS per scan" % (B, args.shape.upper(), N),
+                   "sequences_per_gpu": B, "points": N, "cutout_pts": CUTOUT_KW["num_cutout_pts"], "window": WINDOW,
+                   "alpha": ALPHA, "precision": args.precision, "weights": "random-init",
+                   "l2_policy": "inputs larger than L2: per step the path streams %.1f GB of attention memory "
+                                "and features (L2 = 126 MB)" % (3 * B * N * 3584 * 4 / 1e9)},
+        "e2e": {"value": world * B * K / (ms_e2e / 1e3), "unit": "scans/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K, "detections_in_timed_region": n_det,
+                "api": "StreamingDetector.step(host ranges) -> host detections"},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "gate_stream_kernel<11,0> (attention memory update)", "bound": "hbm",
+                     "achieved": gate_gbs, "peak": peak, "unit": "GB/s", "frac": gate_gbs / peak, "traffic": None,
+                     "peak_source": peak_src, "avg_launch_ms": gate_avg_ms, "launches_timed": len(gate_ms),
+                     "algorithmic_bytes_per_launch": gate_bytes_per_seq * seqs_per_launch,
+                     "frac_of_nominal_8TBs": gate_gbs / 8000.0},
+        "roofline_cutout": {"kernel": "cutout_kernel (+span pre-pass)", "bound": "hbm", "achieved": cut_gbs, "peak": peak,
+                            "unit": "GB/s", "frac": cut_gbs / peak, "avg_launch_ms": cut_avg_ms,
+                            "algorithmic_bytes_per_launch": N * 228 * seqs_per_launch},
+        "stage_ms_per_step": {"cutout": sum(cut_ms) / K, "gate": sum(gate_ms) / K, "nms": sum(nms_ms) / K,
+                              "backbone_cudnn_and_rest": ms_dev / K - (sum(cut_ms) + sum(gate_ms) + sum(nms_ms)) / K},
+        "clocks": clocks,
+    }
+    if extra:
+        out["throughput_mode"] = extra
+    if not args.no_cpu_baseline and world == 1:
+        v, cores, n, stage = cpu_reference_scans_per_s(args.shape, args.cpu_scans)
+        out["cpu_baseline"] = {"value": v, "unit": "scans/s", "cores": cores, "kind": "port",
+                               "sample": "%d scans of one %s-shaped sequence streamed through the oracle "
+                                         "(NumPy cutout, torch-CPU SpatialDROW with dense attention, NumPy NMS)" % (n, args.shape.upper()),
+                               "stage_ms_per_scan": stage}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    seqs_per_step = 4                      # bounded sample: one step = one scan of 4 sequences
+    n = args.steps * seqs_per_step
+    v, cores, timed, stage = cpu_reference_scans_per_s(args.shape, n, warmup=args.warmup, sequences=seqs_per_step)
+    sample = ("each step = one scan of %d of the %d %s-shaped sequences, streamed through the oracle port of the "
+              "reference's CPU path" % (seqs_per_step, args.sequences, args.shape.upper()))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * seqs_per_step / v, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "DR-SPAAM streaming inference, %s-shaped sequences, CPU reference path" % args.shape.upper(),
+                   "sample_sequences_per_step": seqs_per_step},
+        "cpu_baseline": {"value": v, "unit": "scans/s", "cores": cores, "kind": "port", "sample": sample,
+                         "stage_ms_per_scan": stage},
+        "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

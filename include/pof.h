@@ -73,6 +73,14 @@ POF_API int pof_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *                                   batched as dataset_dr_spaam.py:464-468)
  *    s_area_out [B] int or NULL     the factor each sample used (0 = no point
  *                                   of that sample was area-resampled)
+ *    half_alpha_in  [B, S, M] float or NULL   window half-angles to use INSTEAD of
+ *                                   atan(0.5*window_width / max(d, 1e-2)) (utils.py:279).
+ *                                   NumPy's float32 arctan is a platform-specific SIMD
+ *                                   kernel (1-2 ulp from correctly rounded), the one
+ *                                   step no other machine can reproduce bit for bit;
+ *                                   parity tests feed the reference's own values here
+ *                                   to prove every other operation exact.
+ *    half_alpha_out [B, S, M] float or NULL   the half-angles this call used
  *    ws      pof_cutout_ws_bytes(B) bytes of device scratch
  *
  *    window_width, window_depth, padding_val are doubles because the reference
@@ -86,6 +94,7 @@ POF_API int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64,
                    double window_width, double window_depth, double padding_val,
                    int fixed, int centered, int area_mode,
                    float* out, int* s_area_out,
+                   const float* half_alpha_in, float* half_alpha_out,
                    void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- *

@@ -35,10 +35,13 @@ import numpy as np
 
 def scans_to_cutout(scans, scan_phi, stride=1, centered=True, fixed=False,
                     window_width=1.66, window_depth=1.0, num_cutout_pts=48,
-                    padding_val=29.99, area_mode=False):
+                    padding_val=29.99, area_mode=False, half_alpha=None):
     """Return the cutout tensor [M, S, P] float32, M = ceil(N / stride).
 
-    Same signature, defaults and result as utils.py:259-334.
+    Same signature, defaults and result as utils.py:259-334.  `half_alpha`
+    ([S, M], test-only) overrides the arctangent of :279 so that the one
+    platform-dependent step (NumPy's SIMD float32 arctan) can be held fixed or
+    perturbed by an ulp when comparing implementations.
     """
     scans = np.asarray(scans)
     scan_phi = np.asarray(scan_phi)
@@ -52,7 +55,8 @@ def scans_to_cutout(scans, scan_phi, stride=1, centered=True, fixed=False,
     last = n_pts - 1
 
     # window half-angle, scan dtype                                   utils.py:279
-    half = np.arctan(0.5 * window_width / np.maximum(centre_r, 1e-2))
+    half = window_half_angle(scans, stride, fixed, window_width) if half_alpha is None \
+        else np.asarray(half_alpha, dtype=centre_r.dtype)
     origin = scan_phi[0]
     pitch = scan_phi[1] - scan_phi[0]
 
@@ -103,6 +107,15 @@ def scans_to_cutout(scans, scan_phi, stride=1, centered=True, fixed=False,
     return np.ascontiguousarray(ct.transpose(1, 0, 2), dtype=np.float32)
 
 
+def window_half_angle(scans, stride=1, fixed=False, window_width=1.66):
+    """atan(0.5 * window_width / max(d, 1e-2)) in the scan dtype, [S, M]   (utils.py:274-279)."""
+    scans = np.asarray(scans)
+    centre_r = scans[:, ::stride]
+    if not fixed:
+        centre_r = np.broadcast_to(scans[-1, ::stride], centre_r.shape)
+    return np.arctan(0.5 * window_width / np.maximum(centre_r, 1e-2))
+
+
 def cutout_diagnostics(scans, scan_phi, stride=1, window_width=1.66,
                        num_cutout_pts=48, fixed=False, **_unused):
     """Per-sample rounding margins used by the parity tests.
@@ -129,7 +142,7 @@ def cutout_diagnostics(scans, scan_phi, stride=1, window_width=1.66,
         centre_r = np.broadcast_to(scans[-1, ::stride], centre_r.shape)
     centre_phi = scan_phi[::stride]
     last = n_pts - 1
-    half = np.arctan(0.5 * window_width / np.maximum(centre_r, 1e-2))
+    half = window_half_angle(scans, stride, fixed, window_width)
     origin, pitch = scan_phi[0], scan_phi[1] - scan_phi[0]
 
     def fractional_index(n):

@@ -62,7 +62,11 @@ def cutout_cases(ru):
         kw = dict(CFG, **flags)
         phi = synth.phi_for(shape)
         out = ru.scans_to_cutout(scans, phi, stride=1, **kw)
-        save(name, scans=scans, phi=phi, out=out,
+        # the half-angles NumPy's float32 arctan produced on THIS machine (utils.py:279):
+        # the only platform-dependent step, frozen so the fixture is self-contained
+        ref = scans if kw["fixed"] else np.broadcast_to(scans[-1], scans.shape)
+        half_alpha = np.arctan(0.5 * kw["window_width"] / np.maximum(ref, 1e-2))
+        save(name, scans=scans, phi=phi, out=out, half_alpha=half_alpha,
              kwargs=np.array(repr(sorted(kw.items()))))
 
 

@@ -35,6 +35,8 @@ struct CutoutArgs {
     float* out;
     unsigned long long* span_bits;  // [B]
     int* s_area_out;                // [B] or null
+    const float* half_alpha_in;     // [B, S, M] or null: caller-supplied window half-angles
+    float* half_alpha_out;          // [B, S, M] or null: the half-angles this call used
     int B, S, N, M, stride, P;
     long long rows;     // B*M*S
     float half_width;   // (float)(0.5 * window_width)      utils.py:279
@@ -70,7 +72,10 @@ __device__ __forceinline__ RowGeom row_geometry(const CutoutArgs& a, long long r
     RowGeom g;
     g.src = src;
     g.range = __ldg(a.scans + ref + i);
-    const float ha = atan_f32(__fdiv_rn(a.half_width, fmaxf(g.range, 1e-2f)));   // :279
+    const size_t ha_slot = ((size_t)b * a.S + s) * a.M + m;
+    const float ha = a.half_alpha_in ? __ldg(a.half_alpha_in + ha_slot)
+                                     : atan_f32(__fdiv_rn(a.half_width, fmaxf(g.range, 1e-2f)));   // :279
+    if (a.half_alpha_out) a.half_alpha_out[ha_slot] = ha;
     g.two_ha = 2.0f * ha;
     g.step = __fdiv_rn(g.two_ha, (float)(a.P - 1));                  // :282
     const PhiT* phi = reinterpret_cast<const PhiT*>(a.phi);
@@ -116,7 +121,6 @@ __global__ void __launch_bounds__(kThreads) cutout_span_kernel(const CutoutArgs 
 template <typename PhiT>
 __global__ void __launch_bounds__(kThreads) cutout_kernel(const CutoutArgs a) {
     __shared__ RowGeom geom[kTileRows];
-    __shared__ int s_area_of[2];   // a tile touches at most two samples when rows/sample >= kTileRows
     const PhiT* phi = reinterpret_cast<const PhiT*>(a.phi);
     const double origin = (double)phi[0];
     const double pitch = (double)(PhiT)(phi[1] - phi[0]);
@@ -201,7 +205,6 @@ __global__ void __launch_bounds__(kThreads) cutout_kernel(const CutoutArgs a) {
             a.s_area_out[b] = (mx > Pd) ? (int)ceil(__ddiv_rn(mx, Pd)) : 0;
         }
     }
-    (void)s_area_of;
 }
 
 }  // namespace
@@ -213,9 +216,11 @@ size_t pof_cutout_ws_bytes(int B) { return B > 0 ? (size_t)B * sizeof(unsigned l
 
 int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64, int B, int S, int N, int stride, int P,
                    double window_width, double window_depth, double padding_val, int fixed, int centered,
-                   int area_mode, float* out, int* s_area_out, void* ws, size_t ws_bytes, void* stream_) {
+                   int area_mode, float* out, int* s_area_out, const float* half_alpha_in, float* half_alpha_out,
+                   void* ws, size_t ws_bytes, void* stream_) {
     using namespace pof;
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (B == 0) return POF_OK;
     POF_REQUIRE(scans && phi && out, POF_ERR_NULL_POINTER, "pof_cutout_fwd: null scans/phi/out");
     POF_REQUIRE(B >= 0 && S >= 1 && N >= 2 && stride >= 1, POF_ERR_BAD_SHAPE,
                 "pof_cutout_fwd: need B>=0, S>=1, N>=2, stride>=1 (got B=%d S=%d N=%d stride=%d)", B, S, N, stride);
@@ -224,7 +229,6 @@ int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64, int B, i
     POF_REQUIRE(window_depth != 0.0, POF_ERR_BAD_PARAM, "pof_cutout_fwd: window_depth must be non-zero");
     POF_REQUIRE((long long)B * S * N < (1ll << 31), POF_ERR_BAD_SHAPE, "pof_cutout_fwd: B*S*N must fit int32");
     POF_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, POF_ERR_BAD_PARAM, "pof_cutout_fwd: out must be 16-byte aligned");
-    if (B == 0) return POF_OK;
     POF_REQUIRE(ws && ws_bytes >= pof_cutout_ws_bytes(B), POF_ERR_WORKSPACE,
                 "pof_cutout_fwd: workspace too small (%zu < %zu)", ws_bytes, pof_cutout_ws_bytes(B));
 
@@ -234,6 +238,8 @@ int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64, int B, i
     a.out = out;
     a.span_bits = reinterpret_cast<unsigned long long*>(ws);
     a.s_area_out = s_area_out;
+    a.half_alpha_in = half_alpha_in;
+    a.half_alpha_out = half_alpha_out;
     a.B = B; a.S = S; a.N = N; a.stride = stride; a.P = P;
     a.M = (N + stride - 1) / stride;
     a.rows = (long long)B * a.M * S;

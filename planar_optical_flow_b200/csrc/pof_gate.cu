@@ -365,6 +365,7 @@ int pof_spaam_gate_fwd(const float* x, const float* tmpl, const float* emb_x, co
                        int E, int W, float alpha, float* out_tmpl, float* feat_fused, float* attn_w, void* stream_) {
     using namespace pof;
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (B == 0) return POF_OK;
     POF_REQUIRE(x && tmpl && emb_x && emb_t && out_tmpl && feat_fused, POF_ERR_NULL_POINTER,
                 "pof_spaam_gate_fwd: null tensor pointer");
     POF_REQUIRE(B >= 0 && N >= 1 && CL >= 4 && E >= 4, POF_ERR_BAD_SHAPE, "pof_spaam_gate_fwd: bad shape B=%d N=%d CL=%d E=%d", B,
@@ -403,6 +404,7 @@ int pof_spaam_gate_bwd(const float* tmpl, const float* emb_x, const float* emb_t
                        float* g_emb_x, float* g_emb_t, void* ws, size_t ws_bytes, void* stream_) {
     using namespace pof;
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (B == 0) return POF_OK;
     POF_REQUIRE(tmpl && emb_x && emb_t && attn_w && g_out && g_x && g_tmpl && g_emb_x && g_emb_t, POF_ERR_NULL_POINTER,
                 "pof_spaam_gate_bwd: null tensor pointer");
     POF_REQUIRE(B >= 0 && N >= 1 && CL >= 4 && E >= 4 && (CL % 4) == 0 && (E % 4) == 0, POF_ERR_BAD_SHAPE,

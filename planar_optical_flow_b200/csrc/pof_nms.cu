@@ -253,6 +253,7 @@ int pof_nms_centers(const void* scan, int scan_is_f64, const void* phi, int phi_
                     int* instance_mask, double* det_xy, float* det_cls, void* ws, size_t ws_bytes, void* stream_) {
     using namespace pof;
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (B == 0) return POF_OK;
     POF_REQUIRE(scan && phi && cls && reg && order && keep_idx && n_keep && instance_mask && det_xy && det_cls,
                 POF_ERR_NULL_POINTER, "pof_nms_centers: null pointer argument");
     POF_REQUIRE(B >= 0 && N >= 1 && N <= kMaxPoints, POF_ERR_BAD_SHAPE, "pof_nms_centers: need 1 <= N <= %d (got %d)",

@@ -1,0 +1,231 @@
+"""Batched streaming DR-SPAAM inference with the whole per-scan chain on the device.
+
+The reference's streaming loop (depracted_scripts/infer_person_flow.py:101-139) handles ONE
+sequence, one scan at a time, and crosses the host boundary twice per scan: CPU cutout ->
+H2D -> network -> D2H -> CPU NMS.  `StreamingDetector` runs B independent sequences in
+lock-step with nothing but the raw ranges going up and the detections coming down:
+
+    ranges [B, N] --H2D--> cutout kernel -> conv blocks 1-2 (cuDNN) -> embeddings (cuDNN)
+        -> fused attention-memory kernel (memory [B, N, 256, 14] stays resident, ping-pong)
+        -> conv blocks 3-4 + heads (cuDNN) -> sigmoid -> NMS kernels --D2H--> detections
+
+Sequences never interact, so multi-GPU use is one detector per rank over a
+disjoint set of sequences with no data-path collective.
+
+Numerics: `precision="fp32"` (default) keeps every convolution in IEEE fp32 and matches the
+reference's CPU path to ~1e-6 relative (BatchNorm is folded into the convolutions in eval
+mode, which re-associates a multiply); `"tf32"` allows TF32 tensor-core convolutions (the
+PyTorch default on GPU, ~1e-3) and is reported separately as a throughput mode.
+"""
+import contextlib
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+_SLOPE = 0.1
+
+
+def fold_conv_bn(seq):
+    """(Conv1d, BatchNorm1d, LeakyReLU) in eval mode -> (weight, bias) of the equivalent conv."""
+    conv, bn = seq[0], seq[1]
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    w = conv.weight * scale[:, None, None]
+    b = (conv.bias - bn.running_mean) * scale + bn.bias
+    return w.detach().contiguous(), b.detach().contiguous()
+
+
+class _FoldedStack:
+    """A conv block with BN folded: conv1d(+bias) -> leaky_relu_, per layer."""
+
+    def __init__(self, block, padding):
+        self.layers = [fold_conv_bn(layer) for layer in block]
+        self.padding = padding
+
+    def __call__(self, x):
+        for w, b in self.layers:
+            x = F.leaky_relu_(F.conv1d(x, w, b, padding=self.padding), _SLOPE)
+        return x
+
+
+class StreamingDetector:
+    """B sequences in lock-step; owns their attention memory.
+
+    model          planar_optical_flow_b200.model.SpatialDROW (weights are read at construction)
+    scan_phi       [N] beam angles (NumPy float32/float64; dtype selects the cutout arithmetic)
+    cutout_kwargs  the reference's `cutout_kwargs` (config/dr_spaam.yaml:21-28)
+    """
+
+    def __init__(self, model, scan_phi, cutout_kwargs, num_sequences, device=None, precision="fp32",
+                 min_dist=0.5, seq_chunk=None, record_events=False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("StreamingDetector needs a CUDA device; there is no CPU path")
+        if precision not in ("fp32", "tf32"):
+            raise ValueError("precision must be 'fp32' or 'tf32'")
+        self.device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self.precision = precision
+        self.cutout_kwargs = dict(cutout_kwargs)
+        self.min_dist = float(min_dist)
+        self.B = int(num_sequences)
+        phi = np.ascontiguousarray(scan_phi)
+        if phi.dtype not in (np.float32, np.float64):
+            phi = phi.astype(np.float64)
+        self.N = int(phi.shape[0])
+        self.phi = torch.from_numpy(phi).to(self.device)
+        self.P = int(self.cutout_kwargs.get("num_cutout_pts", 48))
+
+        model = model.to(self.device).eval()
+        self.alpha = float(model.gate._alpha)
+        self.window = int(model.gate.window)
+        with torch.no_grad():
+            self.block1 = _FoldedStack(model.conv_block_1, 1)
+            self.block2 = _FoldedStack(model.conv_block_2, 1)
+            self.block3 = _FoldedStack(model.conv_block_3, 1)
+            self.block4 = _FoldedStack(model.conv_block_4, 1)
+            self.embed = _FoldedStack([model.gate.conv], 0)
+            self.w_cls, self.b_cls = model.conv_cls.weight.detach().clone(), model.conv_cls.bias.detach().clone()
+            self.w_reg, self.b_reg = model.conv_reg.weight.detach().clone(), model.conv_reg.bias.detach().clone()
+        if self.w_cls.shape[0] != 1:
+            raise ValueError("the NMS stage needs a one-class head (pedestrian_only=True), as utils.py:536 asserts")
+
+        # sequences are processed in chunks so that the widest activation (128 ch x 56 x 4 B per
+        # point) stays a few GB regardless of B
+        if seq_chunk:
+            self.seq_chunk = int(seq_chunk)
+        else:
+            n_chunks = max(1, -(-self.B * self.N // (1 << 18)))
+            self.seq_chunk = -(-self.B // n_chunks)
+        C, L = 256, int(np.ceil(self.P / 4))
+        self.memory = [torch.empty((self.B, self.N, C, L), dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.cur = 0                       # index of the buffer holding the current memory
+        self.has_memory = False
+        self.steps_done = 0
+
+        # pinned staging for the host-facing call
+        self.h_scans = torch.empty((self.B, self.N), dtype=torch.float32).pin_memory()
+        self.d_scans = torch.empty((self.B, self.N), dtype=torch.float32, device=self.device)
+        self.h_out = {
+            "n_keep": torch.empty((self.B,), dtype=torch.int32).pin_memory(),
+            "keep_idx": torch.empty((self.B, self.N), dtype=torch.int32).pin_memory(),
+            "instance_mask": torch.empty((self.B, self.N), dtype=torch.int32).pin_memory(),
+            "det_xy": torch.empty((self.B, self.N, 2), dtype=torch.float64).pin_memory(),
+            "det_cls": torch.empty((self.B, self.N), dtype=torch.float32).pin_memory(),
+        }
+        self.h2d_bytes_per_step = self.h_scans.numel() * 4
+        self.d2h_bytes_per_step = sum(t.numel() * t.element_size() for t in self.h_out.values())
+        self.record_events = record_events
+        self.events = {"cutout": [], "gate": [], "nms": []}
+        self.kernel_launches = 0           # launches of libpof kernels (not cuDNN / torch)
+
+    # ------------------------------------------------------------------ helpers
+    def reset(self):
+        self.has_memory = False
+        self.steps_done = 0
+
+    @contextlib.contextmanager
+    def _precision(self):
+        old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        allow = self.precision == "tf32"
+        torch.backends.cudnn.allow_tf32 = allow
+        torch.backends.cuda.matmul.allow_tf32 = allow
+        try:
+            yield
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+    @contextlib.contextmanager
+    def _timed(self, name):
+        if not self.record_events:
+            yield
+            return
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        yield
+        e.record()
+        self.events[name].append((s, e))
+
+    def event_ms(self, name):
+        """Durations (ms) of the recorded launches of one stage; call after a synchronize."""
+        return [s.elapsed_time(e) for s, e in self.events[name]]
+
+    # ------------------------------------------------------------------ the step
+    @torch.no_grad()
+    def step_device(self, scans):
+        """One scan per sequence, all on the device.  scans: [B, N] float32 CUDA tensor.
+
+        Returns a dict of device tensors: pred_cls [B, N] (post-sigmoid), pred_reg [B, N, 2],
+        feat_fused [B, N, W] and the NMS outputs of `ops.nms_centers`.
+        """
+        B, N = self.B, self.N
+        if tuple(scans.shape) != (B, N):
+            raise ValueError("scans must be [%d, %d]" % (B, N))
+        prev, nxt = self.memory[self.cur], self.memory[1 - self.cur]
+        pred_cls = torch.empty((B, N), dtype=torch.float32, device=self.device)
+        pred_reg = torch.empty((B, N, 2), dtype=torch.float32, device=self.device)
+        feat_fused = torch.empty((B, N, self.window), dtype=torch.float32, device=self.device)
+        first = not self.has_memory
+        with self._precision():
+            for b0 in range(0, B, self.seq_chunk):
+                b1 = min(B, b0 + self.seq_chunk)
+                nb = b1 - b0
+                with self._timed("cutout"):
+                    ct = ops.cutout(scans[b0:b1].unsqueeze(1), self.phi, **self.cutout_kwargs)      # [nb, N, 1, P]
+                self.kernel_launches += 2 if self.cutout_kwargs.get("area_mode") else 1
+                y = ct.view(nb * N, 1, self.P)
+                y = F.max_pool1d(self.block1(y), 2)
+                y = F.max_pool1d(self.block2(y), 2)                                                 # [nb*N, 256, L]
+                feat = y.view(nb, N, y.shape[-2], y.shape[-1])
+                emb_x = self.embed(y).view(nb, N, -1)
+                if first:
+                    # first frame: memory := features, similarities against itself (dr_spaam.py:242-244)
+                    nxt[b0:b1].copy_(feat)
+                    with self._timed("gate"):
+                        _, ff, _ = ops.gate_forward(feat, nxt[b0:b1], emb_x, emb_x, self.alpha, self.window,
+                                                    out=prev[b0:b1])          # blended output is discarded
+                else:
+                    emb_t = self.embed(prev[b0:b1].view(nb * N, y.shape[-2], y.shape[-1])).view(nb, N, -1)
+                    with self._timed("gate"):
+                        _, ff, _ = ops.gate_forward(feat, prev[b0:b1], emb_x, emb_t, self.alpha, self.window,
+                                                    out=nxt[b0:b1])
+                self.kernel_launches += 1
+                feat_fused[b0:b1] = ff
+                z = nxt[b0:b1].view(nb * N, y.shape[-2], y.shape[-1])
+                z = F.max_pool1d(self.block3(z), 2)
+                z = self.block4(z)
+                z = F.avg_pool1d(z, z.shape[-1])
+                pred_cls[b0:b1] = torch.sigmoid(F.conv1d(z, self.w_cls, self.b_cls).view(nb, N))
+                pred_reg[b0:b1] = F.conv1d(z, self.w_reg, self.b_reg).view(nb, N, 2)
+            with self._timed("nms"):
+                res = ops.nms_centers(scans, self.phi, pred_cls, pred_reg, min_dist=self.min_dist)
+            self.kernel_launches += 3
+        self.cur = 1 - self.cur
+        self.has_memory = True
+        self.steps_done += 1
+        res.update(pred_cls=pred_cls, pred_reg=pred_reg, feat_fused=feat_fused)
+        self._last = res
+        return res
+
+    @property
+    def template(self):
+        """The current attention memory [B, N, 256, L] (what the reference returns as out_template)."""
+        return self.memory[self.cur]
+
+    def step(self, scans_host):
+        """Host-facing call: NumPy/CPU-tensor ranges [B, N] in, detections (NumPy views of pinned
+        buffers) out.  Includes the H2D copy of the ranges and the D2H copy of the results."""
+        src = torch.as_tensor(scans_host, dtype=torch.float32)
+        self.h_scans.copy_(src)
+        self.d_scans.copy_(self.h_scans, non_blocking=True)
+        res = self.step_device(self.d_scans)
+        for k, h in self.h_out.items():
+            h.copy_(res[k], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return {k: v.numpy() for k, v in self.h_out.items()}
+
+    def detections(self, host_result, b):
+        """Unpack sequence b of a `step` result into the reference's (det_xys, det_cls, instance_mask)."""
+        k = int(host_result["n_keep"][b])
+        return (host_result["det_xy"][b, :k].copy(), host_result["det_cls"][b, :k].reshape(k, 1).copy(),
+                host_result["instance_mask"][b].copy())

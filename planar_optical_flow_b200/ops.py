@@ -19,7 +19,8 @@ def _ptr(t):
 
 # --------------------------------------------------------------------------- cutout
 def cutout(scans, phi, stride=1, centered=True, fixed=False, window_width=1.66, window_depth=1.0,
-           num_cutout_pts=48, padding_val=29.99, area_mode=False, out=None, return_s_area=False):
+           num_cutout_pts=48, padding_val=29.99, area_mode=False, out=None, return_s_area=False,
+           half_alpha=None, return_half_alpha=False):
     """Batched `scans_to_cutout` (reference: src/utils/utils.py:259-334).
 
     scans [B, S, N] float32 CUDA, phi [N] float32|float64 CUDA  ->  [B, M, S, P] float32,
@@ -48,14 +49,19 @@ def cutout(scans, phi, stride=1, centered=True, fixed=False, window_width=1.66, 
         ws_bytes = L.pof_cutout_ws_bytes(B)
         ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
         s_area = torch.empty(max(B, 1), dtype=torch.int32, device=dev) if return_s_area else None
+        if half_alpha is not None:
+            require_cuda_tensor(half_alpha, "half_alpha", torch.float32)
+            if tuple(half_alpha.shape) != (B, S, M):
+                raise ValueError("half_alpha must be [B, S, M] = %s" % ((B, S, M),))
+        ha_out = torch.empty((B, S, M), dtype=torch.float32, device=dev) if return_half_alpha else None
         check(L.pof_cutout_fwd(_ptr(scans), _ptr(phi), int(phi.dtype == torch.float64), B, S, N, int(stride), P,
                                float(window_width), float(window_depth), float(padding_val),
                                int(bool(fixed)), int(bool(centered)), int(bool(area_mode)),
-                               _ptr(out), _ptr(s_area), _ptr(ws), ws_bytes, current_stream_ptr(dev)),
+                               _ptr(out), _ptr(s_area), _ptr(half_alpha), _ptr(ha_out),
+                               _ptr(ws), ws_bytes, current_stream_ptr(dev)),
               "pof_cutout_fwd")
-    if return_s_area:
-        return out, s_area[:B]
-    return out
+    extra = ([s_area[:B]] if return_s_area else []) + ([ha_out] if return_half_alpha else [])
+    return (out, *extra) if extra else out
 
 
 # --------------------------------------------------------------------------- gate
