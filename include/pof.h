@@ -85,14 +85,19 @@ POF_API int pof_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *
  *    window_width, window_depth, padding_val are doubles because the reference
  *    receives Python floats and rounds them at specific places (utils.py:279,
- *    326-330).  `fixed`, `centered`, `area_mode` as in the reference.
+ *    326-330).  `fixed`, `centered`, `area_mode` as in the reference; window_depth > 0.
+ *    `numerics` selects POF_CUTOUT_EXACT or POF_CUTOUT_FAST (same algorithm, cheaper
+ *    arithmetic; see csrc/pof_cutout.cu).
  * ------------------------------------------------------------------------- */
+#define POF_CUTOUT_EXACT 0   /* every rounding of the reference reproduced (modulo the arctangent) */
+#define POF_CUTOUT_FAST 1    /* fixed-point index line + float32 blend: within ~3e-6 of EXACT        */
+
 POF_API size_t pof_cutout_ws_bytes(int B);
 
 POF_API int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64,
                    int B, int S, int N, int stride, int P,
                    double window_width, double window_depth, double padding_val,
-                   int fixed, int centered, int area_mode,
+                   int fixed, int centered, int area_mode, int numerics,
                    float* out, int* s_area_out,
                    const float* half_alpha_in, float* half_alpha_out,
                    void* ws, size_t ws_bytes, void* stream);

@@ -117,7 +117,7 @@ def window_half_angle(scans, stride=1, fixed=False, window_width=1.66):
 
 
 def cutout_diagnostics(scans, scan_phi, stride=1, window_width=1.66,
-                       num_cutout_pts=48, fixed=False, **_unused):
+                       num_cutout_pts=48, fixed=False, half_alpha=None, **_unused):
     """Per-sample rounding margins used by the parity tests.
 
     Returns dict with
@@ -142,7 +142,8 @@ def cutout_diagnostics(scans, scan_phi, stride=1, window_width=1.66,
         centre_r = np.broadcast_to(scans[-1, ::stride], centre_r.shape)
     centre_phi = scan_phi[::stride]
     last = n_pts - 1
-    half = window_half_angle(scans, stride, fixed, window_width)
+    half = window_half_angle(scans, stride, fixed, window_width) if half_alpha is None \
+        else np.asarray(half_alpha, dtype=centre_r.dtype)
     origin, pitch = scan_phi[0], scan_phi[1] - scan_phi[0]
 
     def fractional_index(n):

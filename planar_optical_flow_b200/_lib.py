@@ -30,7 +30,7 @@ SIGNATURES = {
     "pof_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
     "pof_cutout_ws_bytes": (c_size_t, [c_int]),
     "pof_cutout_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                               c_double, c_double, c_double, c_int, c_int, c_int,
+                               c_double, c_double, c_double, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pof_spaam_gate_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    c_float, c_void_p, c_void_p, c_void_p, c_void_p]),

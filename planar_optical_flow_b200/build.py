@@ -45,6 +45,19 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name, defines):
+    """Tuning aid: build libpof with extra -D flags into _variants/libpof_<name>.so."""
+    vdir = os.path.join(PKG_DIR, "_variants")
+    os.makedirs(vdir, exist_ok=True)
+    out = os.path.join(vdir, "libpof_%s.so" % name)
+    cmd = [find_nvcc()] + [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-D%s" % d for d in defines]
+    cmd += ["-I", INCLUDE, "-I", CSRC, "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(proc.stdout)
+    return out
+
+
 def build(force=False, verbose=False):
     """Compile every CUDA source of the package into libpof.so.  Returns its path."""
     if not force and not _stale():

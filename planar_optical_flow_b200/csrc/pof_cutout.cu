@@ -9,11 +9,21 @@
 // Work decomposition (B200): the output [B, M, S, P] is a dense stream of
 // "rows" of P floats, one row per (sample b, point m, scan s).  A CTA owns
 // kTileRows consecutive rows.  Phase 1: one thread per row derives the row's
-// geometry (range, half-angle, start angle, step) once and parks it in shared
-// memory.  Phase 2: every thread produces 16-byte pieces of the tile in address
-// order, so a warp writes 512 contiguous bytes per store instruction and the
-// P samples of a row never recompute the arctangent.  The gathers from the
-// range row hit L1 (a window spans at most a few 128-byte lines).
+// geometry (range, half-angle, start angle, step, final clip values) once and
+// parks it in shared memory; rows are partitioned into two-tap LINEAR rows and
+// s_area-tap AREA rows so warps do not diverge between them.  Phase 2: every
+// thread produces 16-byte pieces in address order (a warp writes up to 512
+// contiguous bytes per store instruction) and the P samples of a row never
+// recompute the arctangent.  The gathers from the range row hit L1 (a window
+// spans a few 128-byte lines).
+//
+// The kernel is instruction-issue bound, not HBM bound, in EXACT arithmetic
+// (~45 issue slots per 4-byte sample; tools/microbench.cu measured the FP64 and
+// conversion rates this plan is built on: no __ddiv_rn, fmin/fmax(double) or
+// floor(double) in the per-sample path).  POF_CUTOUT_FAST keeps the algorithm but
+// evaluates the index line in 32.32 fixed point and the two-tap blend in float32
+// (<= ~3e-6 of the output range from EXACT, inside the 1e-5 parity bar); it is
+// what the streaming engine uses, EXACT is what `scans_to_cutout` uses.
 //
 // Area mode needs `s_area = ceil(max_span / P)` over a whole reference call
 // (utils.py:308) = over one sample b here; cutout_span_kernel reduces it into
@@ -46,11 +56,27 @@ struct CutoutArgs {
     int fixed, centered, area_mode;
 };
 
+// 32.32 fixed-point view of a row's index line idx(k) = idx0 + k * slope, used by the FAST
+// arithmetic: integer part = floor, fraction = blend ratio, one 64-bit multiply-add per sample.
+struct FixedLine {
+    long long base;    // idx(0) * 2^32
+    long long slope;   // d idx / d k * 2^32 (round to nearest: error <= k * 2^-33 index units)
+};
+__device__ __forceinline__ long long to_fixed(double v) {
+    return __double2ll_rn(v * 4294967296.0);
+}
+
 struct RowGeom {
     double start;   // phi[i] - half_alpha, evaluated in promote(phi, float)
+    FixedLine lin;  // FAST only: index line of the P linear samples
+    FixedLine are;  // FAST only: index line of the s_area*P area taps
     float step;     // 2*half_alpha/(P-1)
-    float two_ha;   // 2*half_alpha
+    float step_a;   // 2*half_alpha/(s_area*P-1) when the row is area-resampled
+    int s_area;     // taps per sample; 0 = two-tap linear row
     float range;    // the point's reference range d
+    float lo_f;     // final value of a sample clipped at d - window_depth
+    float hi_f;     // final value of a sample clipped at d + window_depth
+    float pad_f;    // final value of an out-of-scan sample
     int src;        // element offset of the (b, s) range row
 };
 
@@ -60,8 +86,49 @@ struct RowGeom {
 // any platform-independent code can get (SURVEY.md §7 hard part 1).
 __device__ __forceinline__ float atan_f32(float x) { return (float)atan((double)x); }
 
+// Correctly rounded a / b from y = RN(1/b) in three fused operations (Markstein):
+// q0 = RN(a*y), r = a - b*q0 (exact in an fma), q = RN(q0 + r*y).  __ddiv_rn costs ~14
+// DFMA-equivalents on sm_100 (tools/microbench.cu); b is a per-call constant here.
+__device__ __forceinline__ double div_by(double a, double b, double y) {
+    const double q0 = __dmul_rn(a, y);
+    const double r = fma(-q0, b, a);
+    return fma(r, y, q0);
+}
+
+struct Consts {
+    double origin, pitch, inv_pitch, last;
+    double depth, inv_depth;
+};
+
+// Fractional index of sample k on a row whose angular step is `step`  (:286-288).
+// k*step is exact in double (k < 2^11, step has a 24-bit significand) so the
+// fused form rounds exactly like NumPy's separate multiply and add.
+__device__ __forceinline__ double sample_index(double start, float step, int k, const Consts& c) {
+    const double ang = fma((double)k, (double)step, start);
+    return div_by(__dsub_rn(ang, c.origin), c.pitch, c.inv_pitch);
+}
+
 template <typename PhiT>
-__device__ __forceinline__ RowGeom row_geometry(const CutoutArgs& a, long long row) {
+__device__ __forceinline__ Consts make_consts(const CutoutArgs& a) {
+    const PhiT* phi = reinterpret_cast<const PhiT*>(a.phi);
+    Consts c;
+    c.origin = (double)phi[0];
+    c.pitch = (double)(PhiT)(phi[1] - phi[0]);
+    c.inv_pitch = __drcp_rn(c.pitch);
+    c.last = (double)(a.N - 1);
+    c.depth = a.depth;
+    c.inv_depth = __drcp_rn(a.depth);
+    return c;
+}
+
+// (v - d) / window_depth, or v itself when not centred, rounded to float  (:328-334)
+__device__ __forceinline__ float finish(double v, float range, const Consts& c, int centered) {
+    if (centered) v = div_by(__dsub_rn(v, (double)range), c.depth, c.inv_depth);
+    return (float)v;
+}
+
+template <typename PhiT>
+__device__ __forceinline__ void row_basics(const CutoutArgs& a, long long row, RowGeom& g, float& two_ha, int& b_out) {
     const int s = (int)(row % a.S);
     const long long bm = row / a.S;
     const int m = (int)(bm % a.M);
@@ -69,42 +136,30 @@ __device__ __forceinline__ RowGeom row_geometry(const CutoutArgs& a, long long r
     const int i = m * a.stride;
     const int src = (b * a.S + s) * a.N;
     const int ref = a.fixed ? src : (b * a.S + (a.S - 1)) * a.N;     // utils.py:274-278
-    RowGeom g;
     g.src = src;
     g.range = __ldg(a.scans + ref + i);
     const size_t ha_slot = ((size_t)b * a.S + s) * a.M + m;
     const float ha = a.half_alpha_in ? __ldg(a.half_alpha_in + ha_slot)
                                      : atan_f32(__fdiv_rn(a.half_width, fmaxf(g.range, 1e-2f)));   // :279
     if (a.half_alpha_out) a.half_alpha_out[ha_slot] = ha;
-    g.two_ha = 2.0f * ha;
-    g.step = __fdiv_rn(g.two_ha, (float)(a.P - 1));                  // :282
+    two_ha = 2.0f * ha;
+    g.step = __fdiv_rn(two_ha, (float)(a.P - 1));                    // :282
     const PhiT* phi = reinterpret_cast<const PhiT*>(a.phi);
     g.start = (double)(phi[i] - (PhiT)ha);                           // :284-285
-    return g;
-}
-
-// Fractional index of sample k on a row whose angular step is `step`  (:286-288).
-// k*step is exact in double (k < 2^11, step has a 24-bit significand) so the
-// fused form rounds exactly like NumPy's separate multiply and add.
-__device__ __forceinline__ double sample_index(double start, float step, int k, double origin, double pitch) {
-    const double ang = fma((double)k, (double)step, start);
-    return __ddiv_rn(__dsub_rn(ang, origin), pitch);
+    b_out = b;
 }
 
 template <typename PhiT>
 __global__ void __launch_bounds__(kThreads) cutout_span_kernel(const CutoutArgs a) {
-    const PhiT* phi = reinterpret_cast<const PhiT*>(a.phi);
-    const double origin = (double)phi[0];
-    const double pitch = (double)(PhiT)(phi[1] - phi[0]);
+    const Consts c = make_consts<PhiT>(a);
     const long long row = (long long)blockIdx.x * kThreads + threadIdx.x;
     double span = 0.0;
     int b = -1;
     if (row < a.rows) {
-        const RowGeom g = row_geometry<PhiT>(a, row);
-        const double i0 = sample_index(g.start, g.step, 0, origin, pitch);
-        const double i1 = sample_index(g.start, g.step, a.P - 1, origin, pitch);
-        span = __dsub_rn(i1, i0);                                    // :304
-        b = (int)(row / ((long long)a.S * a.M));
+        RowGeom g;
+        float two_ha;
+        row_basics<PhiT>(a, row, g, two_ha, b);
+        span = __dsub_rn(sample_index(g.start, g.step, a.P - 1, c), sample_index(g.start, g.step, 0, c));   // :304
     }
     if (!(span > 0.0)) span = 0.0;
     // warp-level max when the whole warp belongs to one sample, else per-lane
@@ -118,92 +173,166 @@ __global__ void __launch_bounds__(kThreads) cutout_span_kernel(const CutoutArgs 
     }
 }
 
-template <typename PhiT>
+// EXACT arithmetic: the reference's roundings, operation by operation (see file header).
+__device__ __forceinline__ float sample_exact(const RowGeom& g, const float* __restrict__ src, int k, int s_area,
+                                              const Consts& c, int nm1, int centered) {
+    const double idx = sample_index(g.start, g.step, k, c);
+    const int lo = __double2int_rd(idx);                         // floor; saturates far outside
+    if (lo < 0 || (lo >= nm1 && idx > c.last)) return g.pad_f;   // :289, :326
+    double v;
+    if (s_area > 0) {                                            // :310-323
+        float acc = 0.f;
+        const int k0 = k * s_area;
+        for (int t = 0; t < s_area; ++t) {
+            const double ia = sample_index(g.start, g.step_a, k0 + t, c);
+            // rint(clip(ia, 0, N-1)) == clip(rint(ia), 0, N-1): rint is monotone and fixes integers (:318)
+            const int j = min(max(__double2int_rn(ia), 0), nm1);
+            const float tap = __ldg(src + j);
+            acc = (t == 0) ? tap : __fadd_rn(acc, tap);
+        }
+        v = (double)__fdiv_rn(acc, (float)s_area);
+    } else {                                                     // :292-300
+        const int hi = min(lo + 1, nm1);
+        const double ratio = __dsub_rn(idx, (double)lo);
+        const float v_lo = __ldg(src + lo);
+        const float v_hi = __ldg(src + hi);
+        v = __dadd_rn((double)v_lo, __dmul_rn(ratio, (double)__fsub_rn(v_hi, v_lo)));
+    }
+    return fminf(fmaxf(finish(v, g.range, c, centered), g.lo_f), g.hi_f);
+}
+
+// FAST arithmetic: same algorithm, index line in 32.32 fixed point and the blend / centring in
+// float32.  Differs from EXACT by <= ~3e-6 of the output range (BASELINE tolerance 1e-5).
+__device__ __forceinline__ float sample_fast(const RowGeom& g, const float* __restrict__ src, int k, int s_area, int nm1,
+                                             float scale, float offset) {
+    const long long fx = g.lin.base + (long long)k * g.lin.slope;
+    const int lo = (int)(fx >> 32);
+    const unsigned frac = (unsigned)fx;
+    if (lo < 0 || lo > nm1 || (lo == nm1 && frac != 0u)) return g.pad_f;
+    float v;
+    if (s_area > 0) {
+        float acc = 0.f;
+        long long fa = g.are.base + (long long)(k * s_area) * g.are.slope + 0x80000000ll;   // +0.5: round to nearest
+        for (int t = 0; t < s_area; ++t, fa += g.are.slope) {
+            const int j = min(max((int)(fa >> 32), 0), nm1);
+            const float tap = __ldg(src + j);
+            acc = (t == 0) ? tap : acc + tap;
+        }
+        v = __fdiv_rn(acc, (float)s_area) - offset;
+    } else {
+        const float v_lo = __ldg(src + lo);
+        const float v_hi = __ldg(src + min(lo + 1, nm1));
+        v = fmaf((float)frac, (v_hi - v_lo) * 2.3283064365386963e-10f, v_lo - offset);
+    }
+    return fminf(fmaxf(v * scale, g.lo_f), g.hi_f);
+}
+
+// Tile of kTileRows output rows per CTA.
+//   phase 1  one thread per row: geometry, clip constants, area decision; rows are split into a
+//            LINEAR list and an AREA list (warp ballots) so that phase 2 has no divergence
+//            between the 2-tap rows and the s_area-tap rows;
+//   phase 2  16-byte pieces of the linear rows, then of the area rows, in address order.
+template <typename PhiT, bool FAST>
 __global__ void __launch_bounds__(kThreads) cutout_kernel(const CutoutArgs a) {
     __shared__ RowGeom geom[kTileRows];
-    const PhiT* phi = reinterpret_cast<const PhiT*>(a.phi);
-    const double origin = (double)phi[0];
-    const double pitch = (double)(PhiT)(phi[1] - phi[0]);
-    const double last = (double)(a.N - 1);
+    __shared__ unsigned char order[kTileRows];       // linear rows first, then area rows
+    __shared__ int warp_lin[kTileRows / 32], warp_area[kTileRows / 32];
+    const Consts c = make_consts<PhiT>(a);
     const long long row0 = (long long)blockIdx.x * kTileRows;
     const int rows_here = (int)min((long long)kTileRows, a.rows - row0);
-    const long long rows_per_b = (long long)a.S * a.M;
+    const double Pd = (double)a.P;
+    const int tid = threadIdx.x;
 
-    if (threadIdx.x < rows_here) geom[threadIdx.x] = row_geometry<PhiT>(a, row0 + threadIdx.x);
+    // ---- phase 1 ---------------------------------------------------------------------------------
+    bool is_area = false;
+    unsigned m_area = 0;
+    if (tid < kTileRows) {
+        if (tid < rows_here) {
+            RowGeom g;
+            float two_ha;
+            int b;
+            row_basics<PhiT>(a, row0 + tid, g, two_ha, b);
+            g.step_a = 0.f;
+            g.s_area = 0;
+            g.are.base = g.are.slope = 0;
+            double mx = 0.0;
+            const double i0 = sample_index(g.start, g.step, 0, c);
+            if (a.area_mode) {                                               // :304-310
+                mx = __longlong_as_double((long long)a.span_bits[b]);
+                const double span = __dsub_rn(sample_index(g.start, g.step, a.P - 1, c), i0);
+                if (span > Pd) {
+                    g.s_area = (int)ceil(__ddiv_rn(mx, Pd));                 // :308, one factor per sample b
+                    g.step_a = __fdiv_rn(two_ha, (float)(g.s_area * a.P - 1));
+                    is_area = true;
+                }
+            }
+            // The depth clip, the centring and the float conversion are all monotone, so clipping the
+            // FINAL float against the final values of the two bounds is the same function  (:327-334)
+            g.lo_f = finish((double)(g.range - a.depth_f), g.range, c, a.centered);
+            g.hi_f = finish((double)(g.range + a.depth_f), g.range, c, a.centered);
+            g.pad_f = fminf(fmaxf(finish(a.pad, g.range, c, a.centered), g.lo_f), g.hi_f);      // :326
+            if (FAST) {
+                g.lin.base = to_fixed(i0);
+                g.lin.slope = to_fixed((double)g.step * c.inv_pitch);
+                if (is_area) {
+                    g.are.base = g.lin.base;
+                    g.are.slope = to_fixed((double)g.step_a * c.inv_pitch);
+                }
+            }
+            geom[tid] = g;
+            if (a.s_area_out && (row0 + tid) % ((long long)a.S * a.M) == 0)
+                a.s_area_out[b] = (mx > Pd) ? (int)ceil(__ddiv_rn(mx, Pd)) : 0;
+        }
+        const bool valid = tid < rows_here;
+        m_area = __ballot_sync(0xffffffffu, valid && is_area);
+        const unsigned m_lin = __ballot_sync(0xffffffffu, valid && !is_area);
+        if ((tid & 31) == 0) { warp_area[tid >> 5] = __popc(m_area); warp_lin[tid >> 5] = __popc(m_lin); }
+        __syncwarp();
+    }
+    __syncthreads();
+    int n_lin = 0;
+#pragma unroll
+    for (int w = 0; w < kTileRows / 32; ++w) n_lin += warp_lin[w];
+    if (tid < rows_here) {
+        const int w = tid >> 5;
+        const unsigned lt = (1u << (tid & 31)) - 1u;
+        int pos;
+        if (is_area) {
+            pos = n_lin + __popc(m_area & lt);
+            for (int v = 0; v < w; ++v) pos += warp_area[v];
+        } else {
+            pos = (tid & 31) - __popc(m_area & lt);
+            for (int v = 0; v < w; ++v) pos += warp_lin[v];
+        }
+        order[pos] = (unsigned char)tid;
+    }
     __syncthreads();
 
-    const int vpr = a.P >> 2;                       // 16-byte pieces per row
-    const int pieces = rows_here * vpr;
+    // ---- phase 2 ---------------------------------------------------------------------------------
+    const unsigned vpr = (unsigned)a.P >> 2;                      // pieces per row
+    const unsigned inv_vpr = 0xffffffffu / vpr + 1u;              // q / vpr == umulhi(q, inv_vpr) for q*vpr < 2^32
     float4* out4 = reinterpret_cast<float4*>(a.out + row0 * a.P);
     const float* scans = a.scans;
     const int nm1 = a.N - 1;
-    const double Pd = (double)a.P;
+    const unsigned all_pieces = (unsigned)rows_here * vpr;
+    const float scale = a.centered ? (float)c.inv_depth : 1.0f;
 
-    for (int q = threadIdx.x; q < pieces; q += kThreads) {
-        const int r = q / vpr;
-        const int c0 = (q - r * vpr) << 2;
-        const RowGeom g = geom[r];
+    for (unsigned q = tid; q < all_pieces; q += kThreads) {
+        const unsigned li = __umulhi(q, inv_vpr);
+        const unsigned cq = q - li * vpr;
+        const unsigned r = order[li];
+        const RowGeom& g = geom[r];
         const float* src = scans + g.src;
-        const double lo_b = (double)(g.range - a.depth_f);           // :327 bounds in float32
-        const double hi_b = (double)(g.range + a.depth_f);
-        const double dd = (double)g.range;
-
-        // area-mode decision for this row (:304-308)
-        int s_area = 0;
-        float step_a = 0.f;
-        if (a.area_mode) {
-            const double i0 = sample_index(g.start, g.step, 0, origin, pitch);
-            const double i1 = sample_index(g.start, g.step, a.P - 1, origin, pitch);
-            if (__dsub_rn(i1, i0) > Pd) {
-                const int b = (int)((row0 + r) / rows_per_b);
-                const double mx = __longlong_as_double((long long)a.span_bits[b]);
-                s_area = (int)ceil(__ddiv_rn(mx, Pd));               // :308
-                step_a = __fdiv_rn(g.two_ha, (float)(s_area * a.P - 1));   // :310
-            }
-        }
-
+        const int s_area = g.s_area;          // warp-uniform except where the linear/area lists meet
+        const float offset = a.centered ? g.range : 0.f;
         float res[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int c = c0 + u;
-            const double idx = sample_index(g.start, g.step, c, origin, pitch);
-            double v;
-            if (idx < 0.0 || idx > last) {                           // :289, :326
-                v = a.pad;
-            } else if (s_area > 0) {                                 // :310-323
-                float acc = 0.f;
-                for (int t = 0; t < s_area; ++t) {
-                    double ia = sample_index(g.start, step_a, c * s_area + t, origin, pitch);
-                    ia = fmin(fmax(ia, 0.0), last);
-                    const int j = __double2int_rn(ia);               // rint: half to even (:318)
-                    const float tap = __ldg(src + j);
-                    acc = (t == 0) ? tap : __fadd_rn(acc, tap);
-                }
-                v = (double)__fdiv_rn(acc, (float)s_area);
-            } else {                                                 // :292-300
-                const double fl = floor(idx);
-                const int lo = (int)fl;                              // 0 <= idx <= N-1 here
-                const int hi = min(lo + 1, nm1);
-                const double ratio = __dsub_rn(idx, fl);
-                const float v_lo = __ldg(src + lo);
-                const float v_hi = __ldg(src + hi);
-                v = __dadd_rn((double)v_lo, __dmul_rn(ratio, (double)__fsub_rn(v_hi, v_lo)));
-            }
-            v = fmin(fmax(v, lo_b), hi_b);                           // :327
-            if (a.centered) v = __ddiv_rn(__dsub_rn(v, dd), a.depth);   // :328-330
-            res[u] = (float)v;
+            const int k = (int)(cq << 2) + u;
+            res[u] = FAST ? sample_fast(g, src, k, s_area, nm1, scale, offset)
+                          : sample_exact(g, src, k, s_area, c, nm1, a.centered);
         }
-        st_stream_f4(out4 + q, make_float4(res[0], res[1], res[2], res[3]));
-    }
-
-    // report the factor each sample used (first row of each sample does it)
-    if (a.s_area_out && threadIdx.x < rows_here) {
-        const long long row = row0 + threadIdx.x;
-        if (row % rows_per_b == 0) {
-            const int b = (int)(row / rows_per_b);
-            const double mx = a.area_mode ? __longlong_as_double((long long)a.span_bits[b]) : 0.0;
-            a.s_area_out[b] = (mx > Pd) ? (int)ceil(__ddiv_rn(mx, Pd)) : 0;
-        }
+        st_stream_f4(out4 + r * vpr + cq, make_float4(res[0], res[1], res[2], res[3]));
     }
 }
 
@@ -216,8 +345,8 @@ size_t pof_cutout_ws_bytes(int B) { return B > 0 ? (size_t)B * sizeof(unsigned l
 
 int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64, int B, int S, int N, int stride, int P,
                    double window_width, double window_depth, double padding_val, int fixed, int centered,
-                   int area_mode, float* out, int* s_area_out, const float* half_alpha_in, float* half_alpha_out,
-                   void* ws, size_t ws_bytes, void* stream_) {
+                   int area_mode, int numerics, float* out, int* s_area_out, const float* half_alpha_in,
+                   float* half_alpha_out, void* ws, size_t ws_bytes, void* stream_) {
     using namespace pof;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (B == 0) return POF_OK;
@@ -226,7 +355,9 @@ int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64, int B, i
                 "pof_cutout_fwd: need B>=0, S>=1, N>=2, stride>=1 (got B=%d S=%d N=%d stride=%d)", B, S, N, stride);
     POF_REQUIRE(P >= 4 && (P % 4) == 0 && P <= 1024, POF_ERR_BAD_SHAPE,
                 "pof_cutout_fwd: num_cutout_pts must be a multiple of 4 in [4,1024] (got %d)", P);
-    POF_REQUIRE(window_depth != 0.0, POF_ERR_BAD_PARAM, "pof_cutout_fwd: window_depth must be non-zero");
+    POF_REQUIRE(numerics == POF_CUTOUT_EXACT || numerics == POF_CUTOUT_FAST, POF_ERR_BAD_PARAM,
+                "pof_cutout_fwd: numerics must be POF_CUTOUT_EXACT or POF_CUTOUT_FAST");
+    POF_REQUIRE(window_depth > 0.0, POF_ERR_BAD_PARAM, "pof_cutout_fwd: window_depth must be positive");
     POF_REQUIRE((long long)B * S * N < (1ll << 31), POF_ERR_BAD_SHAPE, "pof_cutout_fwd: B*S*N must fit int32");
     POF_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, POF_ERR_BAD_PARAM, "pof_cutout_fwd: out must be 16-byte aligned");
     POF_REQUIRE(ws && ws_bytes >= pof_cutout_ws_bytes(B), POF_ERR_WORKSPACE,
@@ -257,8 +388,13 @@ int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64, int B, i
         POF_CUDA(cudaGetLastError());
     }
     const unsigned grid = (unsigned)((a.rows + kTileRows - 1) / kTileRows);
-    if (phi_is_f64) cutout_kernel<double><<<grid, kThreads, 0, stream>>>(a);
-    else cutout_kernel<float><<<grid, kThreads, 0, stream>>>(a);
+    if (numerics == POF_CUTOUT_FAST) {
+        if (phi_is_f64) cutout_kernel<double, true><<<grid, kThreads, 0, stream>>>(a);
+        else cutout_kernel<float, true><<<grid, kThreads, 0, stream>>>(a);
+    } else {
+        if (phi_is_f64) cutout_kernel<double, false><<<grid, kThreads, 0, stream>>>(a);
+        else cutout_kernel<float, false><<<grid, kThreads, 0, stream>>>(a);
+    }
     POF_CUDA(cudaGetLastError());
     return POF_OK;
 }

@@ -14,20 +14,26 @@
 // HBM-bound: per point it must read x (14 KB) and the template row (14 KB) and
 // write out (14 KB).  Layout of the work on B200:
 //   * a CTA owns (sequence b, a chunk of consecutive points, a slice of 4*T
-//     channels, T = 128); thread t owns 4 adjacent channels (one float4) and MARCHES along
-//     the chunk's points;
+//     channels, T = 896 = a whole DR-SPAAM row); thread t owns 4 adjacent channels (one float4) and MARCHES
+//     along the chunk's points;
 //   * the W template rows a point needs are kept in a per-thread circular
-//     REGISTER window (W + D float4), so each template element is loaded from
-//     global memory once per chunk (plus the 2*hw halo rows at the chunk ends,
-//     which neighbouring CTAs hit in L2) and the 11-fold neighbour re-use costs
-//     no memory traffic at all; the loop is unrolled by the window size so every
-//     window slot is a fixed register;
-//   * D rows of the template and the next x row are requested ahead of use, so a
-//     thread keeps D+1 16-byte loads in flight (≈ 41 KB per SM at 5 CTAs x 128 threads);
+//     REGISTER window (W float4), so each template element is fetched once per
+//     chunk (plus the 2*hw halo rows at the chunk ends, which neighbouring CTAs
+//     hit in L2) and the 11-fold neighbour re-use costs no memory traffic at all;
+//     the loop is unrolled by the window size so every window slot is a fixed
+//     register;
+//   * rows arrive through a shared-memory RING filled by TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP): one elected thread
+//     keeps kGateRing stages (template row + x row) in flight per CTA.  A first
+//     version prefetched with plain LDG into registers and stalled at 51 % of HBM
+//     peak on long-scoreboard waits (loads share 6 scoreboard slots per warp, so a
+//     deeper register prefetch does not add memory-level parallelism); the ring
+//     decouples bytes in flight from registers and occupancy;
 //   * the similarities and soft-max weights of the chunk are computed once in a
 //     prologue (one warp per point: neighbour embeddings are 512-byte rows read
-//     as one float4 per lane, dot products finished with warp shuffles) and
-//     broadcast from shared memory in the streaming loop.
+//     as one float4 per lane, dot products finished with warp shuffles) while the
+//     first ring stages are already in flight, and are broadcast from shared
+//     memory in the streaming loop.
 #include <math.h>
 
 #include "pof_common.cuh"
@@ -37,20 +43,26 @@ namespace {
 
 constexpr int kMaxChunk = 160;     // points per CTA (upper bound, sizes the weight table)
 #ifndef POF_GATE_THREADS
-#define POF_GATE_THREADS 128
+#define POF_GATE_THREADS 896
 #endif
 #ifndef POF_GATE_MINBLOCKS
-#define POF_GATE_MINBLOCKS 5
+#define POF_GATE_MINBLOCKS 1
 #endif
-#ifndef POF_GATE_AHEAD
-#define POF_GATE_AHEAD 3
+#ifndef POF_GATE_RING
+#define POF_GATE_RING 6
 #endif
-// 128 threads x float4 = 512 channels per CTA: DR-SPAAM's 3584 = 7 slices exactly; one
-// warp per SM sub-partition, 5 CTAs/SM -> 96 registers per thread (the register file is
-// split per sub-partition, so 7-warp CTAs would lose a sixth of it).
+#ifndef POF_GATE_CHUNK_TARGET
+#define POF_GATE_CHUNK_TARGET 128
+#endif
+// 896 threads x float4 = 3584 channels per CTA: one CTA streams WHOLE DR-SPAAM rows, so the
+// similarity prologue runs once per point (narrower slices repeat it per slice); one CTA per SM
+// with kGateRing = 6 stages (28 KB each: template row + x row) = 168 KB of HBM reads in flight
+// per SM.  Measured on B200 (tools/tune_gate.py, 128 JRDB sequences, % of the measured 6547 GB/s
+// copy peak): LDG-prefetch version 51 %; TMA ring T128/R8 67 %, T224/R8 71 %, T256/R8 79 %,
+// T448x2/R6 83 %, T448/R12 89 %, T896/R6 96 %.
 constexpr int kGateThreads = POF_GATE_THREADS;
 constexpr int kGateMinBlocks = POF_GATE_MINBLOCKS;
-constexpr int kAhead = POF_GATE_AHEAD;   // template rows requested ahead of use (odd, so W + kAhead is even)
+constexpr int kGateRing = POF_GATE_RING;   // stages (template row + x row) kept in flight per CTA by TMA
 
 struct GateArgs {
     const float* x;
@@ -134,89 +146,135 @@ __device__ __forceinline__ void chunk_weights_transposed(const GateArgs& a, int 
     }
 }
 
+// ---- async-proxy helpers (TMA bulk copies completing on an mbarrier) --------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared (SASS: UBLKCP), bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // MODE 0 (forward):  out[i]  = alpha*x[i] + beta * sum_k w[i][k]  * tmpl[i-hw+k]
 // MODE 1 (backward): out[j]  = beta * sum_k wT[j][k] * g_out[j-hw+k]   (g_tmpl; `tmpl` = g_out)
 //                    out2[j] = alpha * g_out[j]                         (g_x)
+//
+// The chunk is consumed as a sequence of STAGES s = 0 .. len+W-2.  Stage s carries template row
+// clamp(i0-hw+s) and, once the window is full (s >= W-1), the x row of point p = s-(W-1).  One
+// elected thread keeps kGateRing stages in flight with TMA bulk copies into a shared-memory ring
+// (completion on one mbarrier per slot); every thread then moves ITS 16 bytes of the new template
+// row into its register window, so shared memory is only a deep prefetch queue (1 write + 1 read
+// per element) and the W-fold neighbour re-use still costs no memory traffic.
 template <int W, int MODE>
 __global__ void __launch_bounds__(kGateThreads, kGateMinBlocks) gate_stream_kernel(const GateArgs a) {
     constexpr int HW = W / 2;
-    constexpr int D = kAhead;
-    constexpr int WIN = W + D;
     constexpr int WPAD = (W + 3) & ~3;
-    static_assert((WIN & 1) == 0, "window + prefetch depth must be even (x double buffer parity)");
-    __shared__ __align__(16) float w_s[kMaxChunk][WPAD];
+    constexpr int R = kGateRing;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // [R][2][T] float4 stage buffers | weights [kMaxChunk][WPAD] | R mbarriers
+    float4* stage = reinterpret_cast<float4*>(smem_raw);
+    float(*w_s)[WPAD] = reinterpret_cast<float(*)[WPAD]>(smem_raw + (size_t)R * 2 * kGateThreads * sizeof(float4));
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)R * 2 * kGateThreads * sizeof(float4) +
+                                                                     sizeof(float) * kMaxChunk * WPAD);
 
+    const int tid = threadIdx.x;
     const int b = blockIdx.z;
     const int i0 = blockIdx.x * a.chunk_len;
     const int len = min(a.chunk_len, a.N - i0);
-    const int ch = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    const int n_stages = len + W - 1;
+    const int ch0 = blockIdx.y * kGateThreads * 4;                    // first channel of this slice
+    const int ch = ch0 + tid * 4;
     const bool active = ch < a.CL;
-    const int row_max = min(a.N - 1, i0 + len - 1 + HW);     // last template row this chunk needs
+    const unsigned row_bytes = (unsigned)(min(kGateThreads * 4, a.CL - ch0) * sizeof(float));
     const size_t seq = (size_t)b * a.N * a.CL;
-    const float* t_col = a.tmpl + seq + (active ? ch : 0);
-    const float* x_col = a.x + seq + (active ? ch : 0);
-    float* o_col = a.out + seq + (active ? ch : 0);
     const size_t CL = (size_t)a.CL;
+    const float* t_base = a.tmpl + seq + ch0;
+    const float* x_base = a.x + seq + ch0;
+    float* o_col = a.out + seq + (active ? ch : 0);
 
-    // Weights first: their live registers (W partial sums + operands) must not
-    // overlap the primed window or ptxas spills the window around the prologue.
+    auto issue = [&](int s) {        // thread 0 only
+        const int slot = s % R;
+        const bool with_x = (MODE == 0) && s >= W - 1;
+        mbar_expect_tx(&full[slot], with_x ? 2 * row_bytes : row_bytes);
+        const int r = min(max(i0 - HW + s, 0), a.N - 1);              // clamped like the reference's table (:152)
+        bulk_g2s(stage + (size_t)slot * 2 * kGateThreads, t_base + r * CL, row_bytes, &full[slot]);
+        if (with_x)
+            bulk_g2s(stage + ((size_t)slot * 2 + 1) * kGateThreads, x_base + (size_t)(i0 + s - (W - 1)) * CL, row_bytes,
+                     &full[slot]);
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) mbar_init(&full[r], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < min(R, n_stages); ++s) issue(s);          // in flight while the weights are computed
+    }
     if (MODE == 0) chunk_weights<W>(a, b, i0, len, blockIdx.y == 0, w_s);
     else chunk_weights_transposed<W>(a, b, i0, len, w_s);
     __syncthreads();
 
-    // prime the register window with rows i0-hw .. i0+hw-1+D
-    float4 win[WIN];
+    float4 win[W];
 #pragma unroll
-    for (int t = 0; t < WIN - 1; ++t) {
-        const int r = i0 - HW + t;
-        win[t] = (active && r >= 0 && r <= row_max) ? ld_stream_f4(reinterpret_cast<const float4*>(t_col + r * CL))
-                                                    : f4_zero();
-    }
-    win[WIN - 1] = f4_zero();
-    float4 xr[2];
-    xr[0] = (MODE == 0 && active) ? ld_stream_f4(reinterpret_cast<const float4*>(x_col + (size_t)i0 * CL)) : f4_zero();
-    xr[1] = f4_zero();
-
+    for (int k = 0; k < W; ++k) win[k] = f4_zero();
     const float alpha = a.alpha, beta = a.beta;
-    for (int p0 = 0; p0 < len; p0 += WIN) {
+
+    for (int s0 = 0; s0 < n_stages; s0 += W) {
 #pragma unroll
-        for (int u = 0; u < WIN; ++u) {
-            const int p = p0 + u;
-            if (p < len) {
-                const int i = i0 + p;
-                {   // request template row i+hw+D into the slot row i-hw-1 just vacated
-                    const int r = i + HW + D;
-                    win[(u + WIN - 1) % WIN] =
-                        (active && r <= row_max) ? ld_stream_f4(reinterpret_cast<const float4*>(t_col + r * CL)) : f4_zero();
-                }
-                if (MODE == 0)
-                    xr[(u + 1) & 1] = (active && p + 1 < len)
-                                          ? ld_stream_f4(reinterpret_cast<const float4*>(x_col + (size_t)(i + 1) * CL))
-                                          : f4_zero();
-                float wk[WPAD];
+        for (int u = 0; u < W; ++u) {
+            const int s = s0 + u;
+            if (s < n_stages) {
+                const int slot = s % R;
+                mbar_wait(&full[slot], (unsigned)(s / R) & 1u);
+                const float4 tv = stage[(size_t)slot * 2 * kGateThreads + tid];
+                float4 xv = f4_zero();
+                if (MODE == 0 && s >= W - 1) xv = stage[((size_t)slot * 2 + 1) * kGateThreads + tid];
+                __syncthreads();                                       // slot fully read: refill it
+                if (tid == 0 && s + R < n_stages) issue(s + R);
+                win[u] = tv;                                           // row s replaces row s-W
+                if (s >= W - 1) {
+                    const int p = s - (W - 1);
+                    const int i = i0 + p;
+                    float wk[WPAD];
 #pragma unroll
-                for (int k4 = 0; k4 < WPAD; k4 += 4) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(&w_s[p][k4]);
-                    wk[k4] = w4.x; wk[k4 + 1] = w4.y; wk[k4 + 2] = w4.z; wk[k4 + 3] = w4.w;
-                }
-                float4 acc = f4_zero();
+                    for (int k4 = 0; k4 < WPAD; k4 += 4) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(&w_s[p][k4]);
+                        wk[k4] = w4.x; wk[k4 + 1] = w4.y; wk[k4 + 2] = w4.z; wk[k4 + 3] = w4.w;
+                    }
+                    float4 acc = f4_zero();
 #pragma unroll
-                for (int k = 0; k < W; ++k) f4_fma(acc, wk[k], win[(u + k) % WIN]);
-                if (MODE == 0) {
-                    const float4 xv = xr[u & 1];
-                    float4 o;
-                    o.x = fmaf(alpha, xv.x, beta * acc.x);
-                    o.y = fmaf(alpha, xv.y, beta * acc.y);
-                    o.z = fmaf(alpha, xv.z, beta * acc.z);
-                    o.w = fmaf(alpha, xv.w, beta * acc.w);
-                    if (active) st_stream_f4(reinterpret_cast<float4*>(o_col + (size_t)i * CL), o);
-                } else {
-                    const float4 c = win[(u + HW) % WIN];     // g_out[j] itself
-                    if (active) {
-                        st_stream_f4(reinterpret_cast<float4*>(o_col + (size_t)i * CL),
-                                     make_float4(beta * acc.x, beta * acc.y, beta * acc.z, beta * acc.w));
-                        st_stream_f4(reinterpret_cast<float4*>(a.out2 + seq + ch + (size_t)i * CL),
-                                     make_float4(alpha * c.x, alpha * c.y, alpha * c.z, alpha * c.w));
+                    for (int k = 0; k < W; ++k) f4_fma(acc, wk[k], win[(u + 1 + k) % W]);   // row p+k
+                    if (MODE == 0) {
+                        float4 o;
+                        o.x = fmaf(alpha, xv.x, beta * acc.x);
+                        o.y = fmaf(alpha, xv.y, beta * acc.y);
+                        o.z = fmaf(alpha, xv.z, beta * acc.z);
+                        o.w = fmaf(alpha, xv.w, beta * acc.w);
+                        if (active) st_stream_f4(reinterpret_cast<float4*>(o_col + (size_t)i * CL), o);
+                    } else {
+                        const float4 c = win[(u + 1 + HW) % W];          // g_out[j] itself
+                        if (active) {
+                            st_stream_f4(reinterpret_cast<float4*>(o_col + (size_t)i * CL),
+                                         make_float4(beta * acc.x, beta * acc.y, beta * acc.z, beta * acc.w));
+                            st_stream_f4(reinterpret_cast<float4*>(a.out2 + seq + ch + (size_t)i * CL),
+                                         make_float4(alpha * c.x, alpha * c.y, alpha * c.z, alpha * c.w));
+                        }
                     }
                 }
             }
@@ -224,9 +282,17 @@ __global__ void __launch_bounds__(kGateThreads, kGateMinBlocks) gate_stream_kern
     }
 }
 
+template <int W>
+constexpr size_t gate_smem_bytes() {
+    return (size_t)kGateRing * 2 * kGateThreads * sizeof(float4) + sizeof(float) * kMaxChunk * ((W + 3) & ~3) +
+           kGateRing * sizeof(unsigned long long);
+}
+
 template <int W, int MODE>
 int launch_gate_stream(const GateArgs& a, dim3 grid, int threads, cudaStream_t stream) {
-    gate_stream_kernel<W, MODE><<<grid, threads, 0, stream>>>(a);
+    constexpr size_t smem = gate_smem_bytes<W>();
+    POF_CUDA(cudaFuncSetAttribute(gate_stream_kernel<W, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gate_stream_kernel<W, MODE><<<grid, threads, smem, stream>>>(a);
     POF_CUDA(cudaGetLastError());
     return POF_OK;
 }
@@ -253,7 +319,7 @@ int dispatch_gate_stream(int W, const GateArgs& a, dim3 grid, int threads, cudaS
 void plan_chunks(int B, int N, int CL, GateArgs& a, dim3& grid) {
     const int slices = (CL + kGateThreads * 4 - 1) / (kGateThreads * 4);
     const long long want_ctas = 4ll * kGateMinBlocks * sm_count();
-    int n_chunks = (N + 127) / 128;
+    int n_chunks = (N + POF_GATE_CHUNK_TARGET - 1) / POF_GATE_CHUNK_TARGET;
     const long long per_chunk = (long long)B * slices;
     if (per_chunk * n_chunks < want_ctas) n_chunks = (int)((want_ctas + per_chunk - 1) / per_chunk);
     n_chunks = max(1, min(n_chunks, (N + 15) / 16));

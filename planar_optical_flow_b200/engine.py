@@ -64,7 +64,7 @@ class StreamingDetector:
             raise RuntimeError("StreamingDetector needs a CUDA device; there is no CPU path")
         if precision not in ("fp32", "tf32"):
             raise ValueError("precision must be 'fp32' or 'tf32'")
-        self.device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.precision = precision
         self.cutout_kwargs = dict(cutout_kwargs)
         self.min_dist = float(min_dist)
@@ -171,7 +171,7 @@ class StreamingDetector:
                 b1 = min(B, b0 + self.seq_chunk)
                 nb = b1 - b0
                 with self._timed("cutout"):
-                    ct = ops.cutout(scans[b0:b1].unsqueeze(1), self.phi, **self.cutout_kwargs)      # [nb, N, 1, P]
+                    ct = ops.cutout(scans[b0:b1].unsqueeze(1), self.phi, fast=True, **self.cutout_kwargs)   # [nb, N, 1, P]
                 self.kernel_launches += 2 if self.cutout_kwargs.get("area_mode") else 1
                 y = ct.view(nb * N, 1, self.P)
                 y = F.max_pool1d(self.block1(y), 2)

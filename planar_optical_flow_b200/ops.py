@@ -20,7 +20,7 @@ def _ptr(t):
 # --------------------------------------------------------------------------- cutout
 def cutout(scans, phi, stride=1, centered=True, fixed=False, window_width=1.66, window_depth=1.0,
            num_cutout_pts=48, padding_val=29.99, area_mode=False, out=None, return_s_area=False,
-           half_alpha=None, return_half_alpha=False):
+           half_alpha=None, return_half_alpha=False, fast=False):
     """Batched `scans_to_cutout` (reference: src/utils/utils.py:259-334).
 
     scans [B, S, N] float32 CUDA, phi [N] float32|float64 CUDA  ->  [B, M, S, P] float32,
@@ -56,7 +56,7 @@ def cutout(scans, phi, stride=1, centered=True, fixed=False, window_width=1.66, 
         ha_out = torch.empty((B, S, M), dtype=torch.float32, device=dev) if return_half_alpha else None
         check(L.pof_cutout_fwd(_ptr(scans), _ptr(phi), int(phi.dtype == torch.float64), B, S, N, int(stride), P,
                                float(window_width), float(window_depth), float(padding_val),
-                               int(bool(fixed)), int(bool(centered)), int(bool(area_mode)),
+                               int(bool(fixed)), int(bool(centered)), int(bool(area_mode)), int(bool(fast)),
                                _ptr(out), _ptr(s_area), _ptr(half_alpha), _ptr(ha_out),
                                _ptr(ws), ws_bytes, current_stream_ptr(dev)),
               "pof_cutout_fwd")

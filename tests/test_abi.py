@@ -52,10 +52,10 @@ def test_argument_validation_happens_before_any_cuda_call(built_lib):
     from planar_optical_flow_b200 import _lib
 
     L = _lib.lib()
-    st = L.pof_cutout_fwd(None, None, 0, 1, 1, 450, 1, 56, 1.0, 0.5, 29.99, 1, 1, 1, None, None, None, None, None, 0, None)
+    st = L.pof_cutout_fwd(None, None, 0, 1, 1, 450, 1, 56, 1.0, 0.5, 29.99, 1, 1, 1, 0, None, None, None, None, None, 0, None)
     assert st == -1 and "null" in _lib.last_error()
     one = ctypes.c_void_p(256)
-    st = L.pof_cutout_fwd(one, one, 0, 1, 1, 450, 1, 55, 1.0, 0.5, 29.99, 1, 1, 1, one, None, None, None, one, 8, None)
+    st = L.pof_cutout_fwd(one, one, 0, 1, 1, 450, 1, 55, 1.0, 0.5, 29.99, 1, 1, 1, 0, one, None, None, None, one, 8, None)
     assert st == -2 and "multiple of 4" in _lib.last_error()
     st = L.pof_spaam_gate_fwd(one, one, one, one, 1, 10, 3584, 128, 10, 0.5, ctypes.c_void_p(512), one, None, None)
     assert st == -5 and "odd" in _lib.last_error()
