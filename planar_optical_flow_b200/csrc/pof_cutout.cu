@@ -1,34 +1,35 @@
 // Kernel 1 — distance-adaptive polar cutout.
 //
-// Replaces scans_to_cutout (/root/reference/src/utils/utils.py:259-334).  The
-// arithmetic below is that function's, operation by operation and rounding by
-// rounding (float32 half-angle and step, float64 sample angle / index / blend,
-// float32 neighbour difference, float32 area means, float32-rounded clip
-// bounds); see oracle/cutout.py for the same recipe in NumPy.
+// Replaces scans_to_cutout (/root/reference/src/utils/utils.py:259-334).  In EXACT
+// arithmetic the code below is that function's, operation by operation and rounding by
+// rounding (float32 half-angle and step, float64 sample angle / index / blend, float32
+// neighbour difference, float32 area means, float32-rounded clip bounds); see
+// oracle/cutout.py for the same recipe in NumPy.
 //
-// Work decomposition (B200): the output [B, M, S, P] is a dense stream of
-// "rows" of P floats, one row per (sample b, point m, scan s).  A CTA owns
-// kTileRows consecutive rows.  Phase 1: one thread per row derives the row's
-// geometry (range, half-angle, start angle, step, final clip values) once and
-// parks it in shared memory; rows are partitioned into two-tap LINEAR rows and
-// s_area-tap AREA rows so warps do not diverge between them.  Phase 2: every
-// thread produces 16-byte pieces in address order (a warp writes up to 512
-// contiguous bytes per store instruction) and the P samples of a row never
-// recompute the arctangent.  The gathers from the range row hit L1 (a window
-// spans a few 128-byte lines).
+// Work decomposition (B200).  The output [B, M, S, P] is made of "rows" of P floats, one per
+// (sample b, point m, scan s).  A CTA owns one scan (b, s) and kTilePts consecutive points:
+//   phase 0  the scan's N ranges are staged in shared memory (4.4 KB for a JRDB scan), so the
+//            2 (linear) or s_area (area mode) gathers per sample are LDS with 32-bit addresses
+//            instead of L1-wavefront-bound global gathers;
+//   phase 1  one thread per point derives the row geometry once (range, half-angle via one
+//            double arctangent, start angle, step, area decision, FINAL clip values) and parks
+//            it in shared memory; rows are partitioned into two-tap LINEAR rows and s_area-tap
+//            AREA rows (warp ballots) so warps do not diverge between the two;
+//   phase 2  every thread produces 16-byte pieces (4 consecutive samples of a row) and stores
+//            them with one streaming 128-bit store; a row is 4*P contiguous bytes.
 //
-// The kernel is instruction-issue bound, not HBM bound, in EXACT arithmetic
-// (~45 issue slots per 4-byte sample; tools/microbench.cu measured the FP64 and
-// conversion rates this plan is built on: no __ddiv_rn, fmin/fmax(double) or
-// floor(double) in the per-sample path).  POF_CUTOUT_FAST keeps the algorithm but
-// evaluates the index line in 32.32 fixed point and the two-tap blend in float32
-// (<= ~3e-6 of the output range from EXACT, inside the 1e-5 parity bar); it is
-// what the streaming engine uses, EXACT is what `scans_to_cutout` uses.
+// Two arithmetic policies, one algorithm (`numerics` argument):
+//   POF_CUTOUT_EXACT  reproduces every rounding of the reference.  Issue bound (~45 slots per
+//            4-byte sample); built on measured sm_100 rates (tools/microbench.cu): no __ddiv_rn
+//            (14 DFMA-equivalents; replaced by Markstein's 3-operation correctly rounded
+//            division by a constant), no fmin/fmax(double) (8), no floor(double) (4) in the
+//            per-sample path; the clip is applied to the final float (all steps are monotone).
+//   POF_CUTOUT_FAST   index line in 32.32 fixed point (one 64-bit add per sample), blend and
+//            centring in float32: <= ~3e-6 of the output range from EXACT (parity bar 1e-5).
+//            Used by the streaming engine; `scans_to_cutout` uses EXACT.
 //
-// Area mode needs `s_area = ceil(max_span / P)` over a whole reference call
-// (utils.py:308) = over one sample b here; cutout_span_kernel reduces it into
-// `ws` first (one 8-byte slot per b, atomicMax on the bit pattern of a
-// non-negative double).
+// Area mode needs `s_area = ceil(max_span / P)` over a whole reference call (utils.py:308) =
+// over one sample b here: cutout_span_kernel (one CTA per b) reduces it into `ws` first.
 #include <math.h>
 
 #include "pof_common.cuh"
@@ -36,19 +37,20 @@
 namespace pof {
 namespace {
 
-constexpr int kTileRows = 128;
-constexpr int kThreads = 256;
+constexpr int kTilePts = 128;
+constexpr int kThreads = 128;
+constexpr int kMaxStagedPts = 8192;   // scans longer than this are gathered from global memory
 
 struct CutoutArgs {
     const float* scans;
     const void* phi;
     float* out;
-    unsigned long long* span_bits;  // [B]
+    double* span_max;               // [B]  max over the sample of idx[P-1] - idx[0]
     int* s_area_out;                // [B] or null
     const float* half_alpha_in;     // [B, S, M] or null: caller-supplied window half-angles
     float* half_alpha_out;          // [B, S, M] or null: the half-angles this call used
     int B, S, N, M, stride, P;
-    long long rows;     // B*M*S
+    int tiles_per_scan;
     float half_width;   // (float)(0.5 * window_width)      utils.py:279
     float depth_f;      // (float)window_depth              utils.py:327
     double depth;       // window_depth                     utils.py:330
@@ -56,53 +58,45 @@ struct CutoutArgs {
     int fixed, centered, area_mode;
 };
 
-// 32.32 fixed-point view of a row's index line idx(k) = idx0 + k * slope, used by the FAST
-// arithmetic: integer part = floor, fraction = blend ratio, one 64-bit multiply-add per sample.
-struct FixedLine {
-    long long base;    // idx(0) * 2^32
-    long long slope;   // d idx / d k * 2^32 (round to nearest: error <= k * 2^-33 index units)
-};
-__device__ __forceinline__ long long to_fixed(double v) {
-    return __double2ll_rn(v * 4294967296.0);
-}
-
 struct RowGeom {
-    double start;   // phi[i] - half_alpha, evaluated in promote(phi, float)
-    FixedLine lin;  // FAST only: index line of the P linear samples
-    FixedLine are;  // FAST only: index line of the s_area*P area taps
-    float step;     // 2*half_alpha/(P-1)
-    float step_a;   // 2*half_alpha/(s_area*P-1) when the row is area-resampled
-    int s_area;     // taps per sample; 0 = two-tap linear row
-    float range;    // the point's reference range d
-    float lo_f;     // final value of a sample clipped at d - window_depth
-    float hi_f;     // final value of a sample clipped at d + window_depth
-    float pad_f;    // final value of an out-of-scan sample
-    int src;        // element offset of the (b, s) range row
+    double start;          // phi[i] - half_alpha, evaluated in promote(phi, float)
+    long long fx_base;     // FAST: idx(0) in 32.32 fixed point
+    long long fx_slope;    // FAST: d idx / d sample, linear samples
+    long long fx_slope_a;  // FAST: d idx / d tap, area taps
+    float step;            // 2*half_alpha/(P-1)
+    float step_a;          // 2*half_alpha/(s_area*P-1) when the row is area-resampled
+    int s_area;            // taps per sample; 0 = two-tap linear row
+    float range;           // the point's reference range d
+    float lo_f;            // final value of a sample clipped at d - window_depth
+    float hi_f;            // final value of a sample clipped at d + window_depth
+    float pad_f;           // final value of an out-of-scan sample
+    int pad_;
 };
-
-// float32 arctangent.  NumPy's float32 arctan is a SIMD kernel that is within
-// 1-2 ulp of the correctly rounded value; rounding the double result is the
-// correctly rounded value in all but double-rounding cases, i.e. the closest
-// any platform-independent code can get (SURVEY.md §7 hard part 1).
-__device__ __forceinline__ float atan_f32(float x) { return (float)atan((double)x); }
-
-// Correctly rounded a / b from y = RN(1/b) in three fused operations (Markstein):
-// q0 = RN(a*y), r = a - b*q0 (exact in an fma), q = RN(q0 + r*y).  __ddiv_rn costs ~14
-// DFMA-equivalents on sm_100 (tools/microbench.cu); b is a per-call constant here.
-__device__ __forceinline__ double div_by(double a, double b, double y) {
-    const double q0 = __dmul_rn(a, y);
-    const double r = fma(-q0, b, a);
-    return fma(r, y, q0);
-}
 
 struct Consts {
     double origin, pitch, inv_pitch, last;
     double depth, inv_depth;
 };
 
-// Fractional index of sample k on a row whose angular step is `step`  (:286-288).
-// k*step is exact in double (k < 2^11, step has a 24-bit significand) so the
-// fused form rounds exactly like NumPy's separate multiply and add.
+// float32 arctangent.  NumPy's float32 arctan is a SIMD kernel that is within 1-2 ulp of the
+// correctly rounded value; rounding the double result is the correctly rounded value in all
+// but double-rounding cases, i.e. the closest any platform-independent code can get
+// (SURVEY.md §7 hard part 1).
+__device__ __forceinline__ float atan_f32(float x) { return (float)atan((double)x); }
+
+// Correctly rounded a / b from y = RN(1/b) in three fused operations (Markstein):
+// q0 = RN(a*y), r = a - b*q0 (exact in an fma), q = RN(q0 + r*y).
+__device__ __forceinline__ double div_by(double a, double b, double y) {
+    const double q0 = __dmul_rn(a, y);
+    const double r = fma(-q0, b, a);
+    return fma(r, y, q0);
+}
+
+__device__ __forceinline__ long long to_fixed(double v) { return __double2ll_rn(v * 4294967296.0); }
+
+// Fractional index of sample k on a row whose angular step is `step`  (:286-288).  k*step is
+// exact in double (k < 2^11, step has a 24-bit significand) so the fused form rounds exactly
+// like NumPy's separate multiply and add.
 __device__ __forceinline__ double sample_index(double start, float step, int k, const Consts& c) {
     const double ang = fma((double)k, (double)step, start);
     return div_by(__dsub_rn(ang, c.origin), c.pitch, c.inv_pitch);
@@ -127,17 +121,12 @@ __device__ __forceinline__ float finish(double v, float range, const Consts& c, 
     return (float)v;
 }
 
+// Range, half-angle, step and start angle of row (b, s, m)   (:274-285)
 template <typename PhiT>
-__device__ __forceinline__ void row_basics(const CutoutArgs& a, long long row, RowGeom& g, float& two_ha, int& b_out) {
-    const int s = (int)(row % a.S);
-    const long long bm = row / a.S;
-    const int m = (int)(bm % a.M);
-    const int b = (int)(bm / a.M);
+__device__ __forceinline__ void row_basics(const CutoutArgs& a, int b, int s, int m, RowGeom& g, float& two_ha) {
     const int i = m * a.stride;
-    const int src = (b * a.S + s) * a.N;
-    const int ref = a.fixed ? src : (b * a.S + (a.S - 1)) * a.N;     // utils.py:274-278
-    g.src = src;
-    g.range = __ldg(a.scans + ref + i);
+    const int ref_scan = a.fixed ? s : a.S - 1;
+    g.range = __ldg(a.scans + ((size_t)b * a.S + ref_scan) * a.N + i);
     const size_t ha_slot = ((size_t)b * a.S + s) * a.M + m;
     const float ha = a.half_alpha_in ? __ldg(a.half_alpha_in + ha_slot)
                                      : atan_f32(__fdiv_rn(a.half_width, fmaxf(g.range, 1e-2f)));   // :279
@@ -146,154 +135,159 @@ __device__ __forceinline__ void row_basics(const CutoutArgs& a, long long row, R
     g.step = __fdiv_rn(two_ha, (float)(a.P - 1));                    // :282
     const PhiT* phi = reinterpret_cast<const PhiT*>(a.phi);
     g.start = (double)(phi[i] - (PhiT)ha);                           // :284-285
-    b_out = b;
 }
 
+// One CTA per sample b: max over its S*M rows of idx[P-1] - idx[0]   (:304, :308)
 template <typename PhiT>
 __global__ void __launch_bounds__(kThreads) cutout_span_kernel(const CutoutArgs a) {
+    __shared__ double warp_max[kThreads / 32];
     const Consts c = make_consts<PhiT>(a);
-    const long long row = (long long)blockIdx.x * kThreads + threadIdx.x;
-    double span = 0.0;
-    int b = -1;
-    if (row < a.rows) {
+    const int b = blockIdx.x;
+    double best = 0.0;
+    for (int r = threadIdx.x; r < a.S * a.M; r += kThreads) {
         RowGeom g;
         float two_ha;
-        row_basics<PhiT>(a, row, g, two_ha, b);
-        span = __dsub_rn(sample_index(g.start, g.step, a.P - 1, c), sample_index(g.start, g.step, 0, c));   // :304
+        row_basics<PhiT>(a, b, r / a.M, r % a.M, g, two_ha);
+        const double span = __dsub_rn(sample_index(g.start, g.step, a.P - 1, c), sample_index(g.start, g.step, 0, c));
+        if (span > best) best = span;
     }
-    if (!(span > 0.0)) span = 0.0;
-    // warp-level max when the whole warp belongs to one sample, else per-lane
-    const int b0 = __shfl_sync(0xffffffffu, b, 0);
-    if (__all_sync(0xffffffffu, b == b0)) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) span = fmax(span, __shfl_xor_sync(0xffffffffu, span, o));
-        if ((threadIdx.x & 31) == 0 && b0 >= 0) atomicMax(a.span_bits + b0, (unsigned long long)__double_as_longlong(span));
-    } else if (b >= 0) {
-        atomicMax(a.span_bits + b, (unsigned long long)__double_as_longlong(span));
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, best, o);
+        if (other > best) best = other;
+    }
+    if ((threadIdx.x & 31) == 0) warp_max[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kThreads / 32; ++w)
+            if (warp_max[w] > best) best = warp_max[w];
+        a.span_max[b] = best;
+        if (a.s_area_out) a.s_area_out[b] = (a.area_mode && best > (double)a.P) ? (int)ceil(__ddiv_rn(best, (double)a.P)) : 0;
     }
 }
 
-// EXACT arithmetic: the reference's roundings, operation by operation (see file header).
-__device__ __forceinline__ float sample_exact(const RowGeom& g, const float* __restrict__ src, int k, int s_area,
-                                              const Consts& c, int nm1, int centered) {
-    const double idx = sample_index(g.start, g.step, k, c);
-    const int lo = __double2int_rd(idx);                         // floor; saturates far outside
-    if (lo < 0 || (lo >= nm1 && idx > c.last)) return g.pad_f;   // :289, :326
-    double v;
-    if (s_area > 0) {                                            // :310-323
-        float acc = 0.f;
-        const int k0 = k * s_area;
-        for (int t = 0; t < s_area; ++t) {
-            const double ia = sample_index(g.start, g.step_a, k0 + t, c);
-            // rint(clip(ia, 0, N-1)) == clip(rint(ia), 0, N-1): rint is monotone and fixes integers (:318)
-            const int j = min(max(__double2int_rn(ia), 0), nm1);
-            const float tap = __ldg(src + j);
-            acc = (t == 0) ? tap : __fadd_rn(acc, tap);
-        }
-        v = (double)__fdiv_rn(acc, (float)s_area);
-    } else {                                                     // :292-300
-        const int hi = min(lo + 1, nm1);
-        const double ratio = __dsub_rn(idx, (double)lo);
-        const float v_lo = __ldg(src + lo);
-        const float v_hi = __ldg(src + hi);
-        v = __dadd_rn((double)v_lo, __dmul_rn(ratio, (double)__fsub_rn(v_hi, v_lo)));
-    }
-    return fminf(fmaxf(finish(v, g.range, c, centered), g.lo_f), g.hi_f);
+// ---- per-sample arithmetic --------------------------------------------------------------------
+// EXACT: the reference's roundings, operation by operation.  `in_scan` (:289) is evaluated by the
+// caller from the same idx.
+__device__ __forceinline__ double index_exact(const RowGeom& g, float step, int k, const Consts& c) {
+    return sample_index(g.start, step, k, c);
+}
+__device__ __forceinline__ bool in_scan(double idx, int lo, int nm1, const Consts& c) {
+    return !(lo < 0 || (lo >= nm1 && idx > c.last));                 // :289
+}
+__device__ __forceinline__ float clip_final(float v, const RowGeom& g) { return fminf(fmaxf(v, g.lo_f), g.hi_f); }
+
+__device__ __forceinline__ float linear_exact(const RowGeom& g, const float* src, int k, const Consts& c, int nm1, int centered) {
+    const double idx = index_exact(g, g.step, k, c);
+    const int lo = __double2int_rd(idx);                             // floor; saturates far outside
+    if (!in_scan(idx, lo, nm1, c)) return g.pad_f;                   // :326
+    const double ratio = __dsub_rn(idx, (double)lo);                 // :292-300
+    const float v_lo = src[lo];
+    const float v_hi = src[min(lo + 1, nm1)];
+    const double v = __dadd_rn((double)v_lo, __dmul_rn(ratio, (double)__fsub_rn(v_hi, v_lo)));
+    return clip_final(finish(v, g.range, c, centered), g);
 }
 
-// FAST arithmetic: same algorithm, index line in 32.32 fixed point and the blend / centring in
-// float32.  Differs from EXACT by <= ~3e-6 of the output range (BASELINE tolerance 1e-5).
-__device__ __forceinline__ float sample_fast(const RowGeom& g, const float* __restrict__ src, int k, int s_area, int nm1,
-                                             float scale, float offset) {
-    const long long fx = g.lin.base + (long long)k * g.lin.slope;
+__device__ __forceinline__ float area_exact(const RowGeom& g, const float* src, int k, const Consts& c, int nm1, int centered) {
+    const double idx = index_exact(g, g.step, k, c);
+    const int lo = __double2int_rd(idx);
+    if (!in_scan(idx, lo, nm1, c)) return g.pad_f;
+    float acc = 0.f;                                                 // :310-323
+    const int k0 = k * g.s_area;
+    for (int t = 0; t < g.s_area; ++t) {
+        const double ia = index_exact(g, g.step_a, k0 + t, c);
+        // rint(clip(ia, 0, N-1)) == clip(rint(ia), 0, N-1): rint is monotone and fixes integers (:318)
+        const int j = min(max(__double2int_rn(ia), 0), nm1);
+        acc = (t == 0) ? src[j] : __fadd_rn(acc, src[j]);
+    }
+    return clip_final(finish((double)__fdiv_rn(acc, (float)g.s_area), g.range, c, centered), g);
+}
+
+// FAST: `fx` is the sample's index in 32.32 fixed point; out = clip(v*scale + bias) with
+// bias = -d*scale when centred.  The blend is one fused multiply-add on the raw fraction.
+__device__ __forceinline__ float linear_fast(const RowGeom& g, const float* src, long long fx, int nm1, float scale,
+                                             float bias, float dscale) {
     const int lo = (int)(fx >> 32);
     const unsigned frac = (unsigned)fx;
-    if (lo < 0 || lo > nm1 || (lo == nm1 && frac != 0u)) return g.pad_f;
-    float v;
-    if (s_area > 0) {
-        float acc = 0.f;
-        long long fa = g.are.base + (long long)(k * s_area) * g.are.slope + 0x80000000ll;   // +0.5: round to nearest
-        for (int t = 0; t < s_area; ++t, fa += g.are.slope) {
-            const int j = min(max((int)(fa >> 32), 0), nm1);
-            const float tap = __ldg(src + j);
-            acc = (t == 0) ? tap : acc + tap;
-        }
-        v = __fdiv_rn(acc, (float)s_area) - offset;
-    } else {
-        const float v_lo = __ldg(src + lo);
-        const float v_hi = __ldg(src + min(lo + 1, nm1));
-        v = fmaf((float)frac, (v_hi - v_lo) * 2.3283064365386963e-10f, v_lo - offset);
+    if ((unsigned)lo < (unsigned)nm1) {                              // interior: beams lo and lo+1 exist
+        const float v_lo = src[lo];
+        const float t = fmaf(v_lo, scale, bias);
+        return clip_final(fmaf((float)frac, (src[lo + 1] - v_lo) * dscale, t), g);
     }
-    return fminf(fmaxf(v * scale, g.lo_f), g.hi_f);
+    if (lo == nm1 && frac == 0u) return clip_final(fmaf(src[nm1], scale, bias), g);   // exactly the last beam
+    return g.pad_f;
 }
 
-// Tile of kTileRows output rows per CTA.
-//   phase 1  one thread per row: geometry, clip constants, area decision; rows are split into a
-//            LINEAR list and an AREA list (warp ballots) so that phase 2 has no divergence
-//            between the 2-tap rows and the s_area-tap rows;
-//   phase 2  16-byte pieces of the linear rows, then of the area rows, in address order.
-template <typename PhiT, bool FAST>
-__global__ void __launch_bounds__(kThreads) cutout_kernel(const CutoutArgs a) {
-    __shared__ RowGeom geom[kTileRows];
-    __shared__ unsigned char order[kTileRows];       // linear rows first, then area rows
-    __shared__ int warp_lin[kTileRows / 32], warp_area[kTileRows / 32];
-    const Consts c = make_consts<PhiT>(a);
-    const long long row0 = (long long)blockIdx.x * kTileRows;
-    const int rows_here = (int)min((long long)kTileRows, a.rows - row0);
-    const double Pd = (double)a.P;
-    const int tid = threadIdx.x;
+__device__ __forceinline__ float area_fast(const RowGeom& g, const float* src, long long fx, int k, int nm1, float scale,
+                                           float bias) {
+    const int lo = (int)(fx >> 32);
+    if (!((unsigned)lo < (unsigned)nm1 || (lo == nm1 && (unsigned)fx == 0u))) return g.pad_f;
+    float acc = 0.f;
+    long long fa = g.fx_base + (long long)(k * g.s_area) * g.fx_slope_a + 0x80000000ll;   // +0.5: nearest tap
+    for (int t = 0; t < g.s_area; ++t, fa += g.fx_slope_a) acc += src[min(max((int)(fa >> 32), 0), nm1)];
+    return clip_final(fmaf(__fdiv_rn(acc, (float)g.s_area), scale, bias), g);
+}
 
-    // ---- phase 1 ---------------------------------------------------------------------------------
+template <typename PhiT, bool FAST, bool STAGED>
+__global__ void __launch_bounds__(kThreads) cutout_kernel(const CutoutArgs a) {
+    extern __shared__ __align__(16) float staged[];       // STAGED: the scan's N ranges
+    __shared__ RowGeom geom[kTilePts];
+    __shared__ unsigned char order[kTilePts];              // linear rows first, then area rows
+    __shared__ int warp_lin[kTilePts / 32], warp_area[kTilePts / 32];
+    const Consts c = make_consts<PhiT>(a);
+    const int tid = threadIdx.x;
+    const int bs = blockIdx.x / a.tiles_per_scan;          // b * S + s
+    const int m0 = (blockIdx.x - bs * a.tiles_per_scan) * kTilePts;
+    const int b = bs / a.S, s = bs - b * a.S;
+    const int rows_here = min(kTilePts, a.M - m0);
+    const double Pd = (double)a.P;
+    const float* scan = a.scans + (size_t)bs * a.N;
+
+    // ---- phase 0: stage the scan ---------------------------------------------------------------
+    if (STAGED)
+        for (int i = tid; i < a.N; i += kThreads) staged[i] = __ldg(scan + i);
+    const float* src = STAGED ? staged : scan;
+
+    // ---- phase 1: one thread per point ---------------------------------------------------------
+    static_assert(kThreads == kTilePts, "phase 1 maps one thread to one point");
     bool is_area = false;
-    unsigned m_area = 0;
-    if (tid < kTileRows) {
-        if (tid < rows_here) {
-            RowGeom g;
-            float two_ha;
-            int b;
-            row_basics<PhiT>(a, row0 + tid, g, two_ha, b);
-            g.step_a = 0.f;
-            g.s_area = 0;
-            g.are.base = g.are.slope = 0;
-            double mx = 0.0;
-            const double i0 = sample_index(g.start, g.step, 0, c);
-            if (a.area_mode) {                                               // :304-310
-                mx = __longlong_as_double((long long)a.span_bits[b]);
-                const double span = __dsub_rn(sample_index(g.start, g.step, a.P - 1, c), i0);
-                if (span > Pd) {
-                    g.s_area = (int)ceil(__ddiv_rn(mx, Pd));                 // :308, one factor per sample b
-                    g.step_a = __fdiv_rn(two_ha, (float)(g.s_area * a.P - 1));
-                    is_area = true;
-                }
+    const bool valid = tid < rows_here;
+    if (valid) {
+        RowGeom g;
+        float two_ha;
+        row_basics<PhiT>(a, b, s, m0 + tid, g, two_ha);
+        g.step_a = 0.f;
+        g.s_area = 0;
+        g.fx_base = g.fx_slope = g.fx_slope_a = 0;
+        const double i0 = sample_index(g.start, g.step, 0, c);
+        if (a.area_mode) {                                               // :304-310
+            const double span = __dsub_rn(sample_index(g.start, g.step, a.P - 1, c), i0);
+            if (span > Pd) {
+                g.s_area = (int)ceil(__ddiv_rn(a.span_max[b], Pd));      // :308, one factor per sample b
+                g.step_a = __fdiv_rn(two_ha, (float)(g.s_area * a.P - 1));
+                is_area = true;
             }
-            // The depth clip, the centring and the float conversion are all monotone, so clipping the
-            // FINAL float against the final values of the two bounds is the same function  (:327-334)
-            g.lo_f = finish((double)(g.range - a.depth_f), g.range, c, a.centered);
-            g.hi_f = finish((double)(g.range + a.depth_f), g.range, c, a.centered);
-            g.pad_f = fminf(fmaxf(finish(a.pad, g.range, c, a.centered), g.lo_f), g.hi_f);      // :326
-            if (FAST) {
-                g.lin.base = to_fixed(i0);
-                g.lin.slope = to_fixed((double)g.step * c.inv_pitch);
-                if (is_area) {
-                    g.are.base = g.lin.base;
-                    g.are.slope = to_fixed((double)g.step_a * c.inv_pitch);
-                }
-            }
-            geom[tid] = g;
-            if (a.s_area_out && (row0 + tid) % ((long long)a.S * a.M) == 0)
-                a.s_area_out[b] = (mx > Pd) ? (int)ceil(__ddiv_rn(mx, Pd)) : 0;
         }
-        const bool valid = tid < rows_here;
-        m_area = __ballot_sync(0xffffffffu, valid && is_area);
-        const unsigned m_lin = __ballot_sync(0xffffffffu, valid && !is_area);
-        if ((tid & 31) == 0) { warp_area[tid >> 5] = __popc(m_area); warp_lin[tid >> 5] = __popc(m_lin); }
-        __syncwarp();
+        // The depth clip, the centring and the float conversion are all monotone, so clipping the
+        // FINAL float against the final values of the two bounds is the same function  (:327-334)
+        g.lo_f = finish((double)(g.range - a.depth_f), g.range, c, a.centered);
+        g.hi_f = finish((double)(g.range + a.depth_f), g.range, c, a.centered);
+        g.pad_f = fminf(fmaxf(finish(a.pad, g.range, c, a.centered), g.lo_f), g.hi_f);      // :326
+        if (FAST) {
+            g.fx_base = to_fixed(i0);
+            g.fx_slope = to_fixed((double)g.step * c.inv_pitch);
+            g.fx_slope_a = to_fixed((double)g.step_a * c.inv_pitch);
+        }
+        geom[tid] = g;
     }
+    const unsigned m_area = __ballot_sync(0xffffffffu, valid && is_area);
+    const unsigned m_lin = __ballot_sync(0xffffffffu, valid && !is_area);
+    if ((tid & 31) == 0) { warp_area[tid >> 5] = __popc(m_area); warp_lin[tid >> 5] = __popc(m_lin); }
     __syncthreads();
     int n_lin = 0;
 #pragma unroll
-    for (int w = 0; w < kTileRows / 32; ++w) n_lin += warp_lin[w];
-    if (tid < rows_here) {
+    for (int w = 0; w < kTilePts / 32; ++w) n_lin += warp_lin[w];
+    if (valid) {
         const int w = tid >> 5;
         const unsigned lt = (1u << (tid & 31)) - 1u;
         int pos;
@@ -301,39 +295,70 @@ __global__ void __launch_bounds__(kThreads) cutout_kernel(const CutoutArgs a) {
             pos = n_lin + __popc(m_area & lt);
             for (int v = 0; v < w; ++v) pos += warp_area[v];
         } else {
-            pos = (tid & 31) - __popc(m_area & lt);
+            pos = __popc(m_lin & lt);
             for (int v = 0; v < w; ++v) pos += warp_lin[v];
         }
         order[pos] = (unsigned char)tid;
     }
     __syncthreads();
 
-    // ---- phase 2 ---------------------------------------------------------------------------------
+    // ---- phase 2: 16-byte pieces, linear rows then area rows -----------------------------------
+    // (a warp-per-point mapping with lanes along the samples was measured too: conflict-free
+    //  gathers, but twice the instructions per sample; profiles/cutout_r1_notes.md)
     const unsigned vpr = (unsigned)a.P >> 2;                      // pieces per row
     const unsigned inv_vpr = 0xffffffffu / vpr + 1u;              // q / vpr == umulhi(q, inv_vpr) for q*vpr < 2^32
-    float4* out4 = reinterpret_cast<float4*>(a.out + row0 * a.P);
-    const float* scans = a.scans;
+    const unsigned lin_pieces = (unsigned)n_lin * vpr;
+    const unsigned pieces = (unsigned)rows_here * vpr;
     const int nm1 = a.N - 1;
-    const unsigned all_pieces = (unsigned)rows_here * vpr;
     const float scale = a.centered ? (float)c.inv_depth : 1.0f;
+    const float dscale = scale * 2.3283064365386963e-10f;         // scale * 2^-32
+    // row (b, m, s) starts at ((b*M + m)*S + s)*P floats
+    float4* out4 = reinterpret_cast<float4*>(a.out + (((size_t)b * a.M + m0) * a.S + s) * a.P);
+    const size_t row_pitch4 = (size_t)a.S * vpr;
 
-    for (unsigned q = tid; q < all_pieces; q += kThreads) {
+    for (unsigned q = tid; q < pieces; q += kThreads) {
         const unsigned li = __umulhi(q, inv_vpr);
         const unsigned cq = q - li * vpr;
         const unsigned r = order[li];
-        const RowGeom& g = geom[r];
-        const float* src = scans + g.src;
-        const int s_area = g.s_area;          // warp-uniform except where the linear/area lists meet
-        const float offset = a.centered ? g.range : 0.f;
+        // by value: the store below goes through a generic pointer, so a reference into shared
+        // memory would be reloaded after it
+        const RowGeom g = geom[r];
+        const int k0 = (int)(cq << 2);
+        const bool area = q >= lin_pieces;                         // warp-uniform except in one warp
         float res[4];
+        if (FAST) {
+            const float bias = a.centered ? -g.range * scale : 0.f;
+            long long fx = g.fx_base + (long long)k0 * g.fx_slope;
+            if (!area) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int k = (int)(cq << 2) + u;
-            res[u] = FAST ? sample_fast(g, src, k, s_area, nm1, scale, offset)
-                          : sample_exact(g, src, k, s_area, c, nm1, a.centered);
+                for (int u = 0; u < 4; ++u, fx += g.fx_slope) res[u] = linear_fast(g, src, fx, nm1, scale, bias, dscale);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u, fx += g.fx_slope) res[u] = area_fast(g, src, fx, k0 + u, nm1, scale, bias);
+            }
+        } else {
+            if (!area) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) res[u] = linear_exact(g, src, k0 + u, c, nm1, a.centered);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) res[u] = area_exact(g, src, k0 + u, c, nm1, a.centered);
+            }
         }
-        st_stream_f4(out4 + r * vpr + cq, make_float4(res[0], res[1], res[2], res[3]));
+        st_stream_f4(out4 + r * row_pitch4 + cq, make_float4(res[0], res[1], res[2], res[3]));
     }
+}
+
+template <typename PhiT, bool FAST>
+int launch_cutout(const CutoutArgs& a, cudaStream_t stream) {
+    const unsigned grid = (unsigned)a.tiles_per_scan * (unsigned)(a.B * a.S);
+    if (a.N <= kMaxStagedPts) {
+        cutout_kernel<PhiT, FAST, true><<<grid, kThreads, (size_t)a.N * sizeof(float), stream>>>(a);
+    } else {
+        cutout_kernel<PhiT, FAST, false><<<grid, kThreads, 0, stream>>>(a);
+    }
+    POF_CUDA(cudaGetLastError());
+    return POF_OK;
 }
 
 }  // namespace
@@ -341,7 +366,7 @@ __global__ void __launch_bounds__(kThreads) cutout_kernel(const CutoutArgs a) {
 
 extern "C" {
 
-size_t pof_cutout_ws_bytes(int B) { return B > 0 ? (size_t)B * sizeof(unsigned long long) : 0; }
+size_t pof_cutout_ws_bytes(int B) { return B > 0 ? (size_t)B * sizeof(double) : 0; }
 
 int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64, int B, int S, int N, int stride, int P,
                    double window_width, double window_depth, double padding_val, int fixed, int centered,
@@ -367,36 +392,27 @@ int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64, int B, i
     a.scans = scans;
     a.phi = phi;
     a.out = out;
-    a.span_bits = reinterpret_cast<unsigned long long*>(ws);
+    a.span_max = reinterpret_cast<double*>(ws);
     a.s_area_out = s_area_out;
     a.half_alpha_in = half_alpha_in;
     a.half_alpha_out = half_alpha_out;
     a.B = B; a.S = S; a.N = N; a.stride = stride; a.P = P;
     a.M = (N + stride - 1) / stride;
-    a.rows = (long long)B * a.M * S;
+    a.tiles_per_scan = (a.M + kTilePts - 1) / kTilePts;
     a.half_width = (float)(0.5 * window_width);
     a.depth_f = (float)window_depth;
     a.depth = window_depth;
     a.pad = padding_val;
     a.fixed = fixed; a.centered = centered; a.area_mode = area_mode;
+    POF_REQUIRE((long long)a.tiles_per_scan * B * S < (1ll << 31), POF_ERR_BAD_SHAPE, "pof_cutout_fwd: too many tiles");
 
-    if (area_mode) {
-        POF_CUDA(cudaMemsetAsync(ws, 0, pof_cutout_ws_bytes(B), stream));
-        const unsigned grid = (unsigned)((a.rows + kThreads - 1) / kThreads);
-        if (phi_is_f64) cutout_span_kernel<double><<<grid, kThreads, 0, stream>>>(a);
-        else cutout_span_kernel<float><<<grid, kThreads, 0, stream>>>(a);
+    if (area_mode || s_area_out) {
+        if (phi_is_f64) cutout_span_kernel<double><<<B, kThreads, 0, stream>>>(a);
+        else cutout_span_kernel<float><<<B, kThreads, 0, stream>>>(a);
         POF_CUDA(cudaGetLastError());
     }
-    const unsigned grid = (unsigned)((a.rows + kTileRows - 1) / kTileRows);
-    if (numerics == POF_CUTOUT_FAST) {
-        if (phi_is_f64) cutout_kernel<double, true><<<grid, kThreads, 0, stream>>>(a);
-        else cutout_kernel<float, true><<<grid, kThreads, 0, stream>>>(a);
-    } else {
-        if (phi_is_f64) cutout_kernel<double, false><<<grid, kThreads, 0, stream>>>(a);
-        else cutout_kernel<float, false><<<grid, kThreads, 0, stream>>>(a);
-    }
-    POF_CUDA(cudaGetLastError());
-    return POF_OK;
+    if (numerics == POF_CUTOUT_FAST) return phi_is_f64 ? launch_cutout<double, true>(a, stream) : launch_cutout<float, true>(a, stream);
+    return phi_is_f64 ? launch_cutout<double, false>(a, stream) : launch_cutout<float, false>(a, stream);
 }
 
 }  // extern "C"

@@ -167,13 +167,13 @@ class StreamingDetector:
         feat_fused = torch.empty((B, N, self.window), dtype=torch.float32, device=self.device)
         first = not self.has_memory
         with self._precision():
+            with self._timed("cutout"):      # one launch for all B sequences: [B, N, 1, P]
+                cutouts = ops.cutout(scans.unsqueeze(1), self.phi, fast=True, **self.cutout_kwargs)
+            self.kernel_launches += 2 if self.cutout_kwargs.get("area_mode") else 1
             for b0 in range(0, B, self.seq_chunk):
                 b1 = min(B, b0 + self.seq_chunk)
                 nb = b1 - b0
-                with self._timed("cutout"):
-                    ct = ops.cutout(scans[b0:b1].unsqueeze(1), self.phi, fast=True, **self.cutout_kwargs)   # [nb, N, 1, P]
-                self.kernel_launches += 2 if self.cutout_kwargs.get("area_mode") else 1
-                y = ct.view(nb * N, 1, self.P)
+                y = cutouts[b0:b1].view(nb * N, 1, self.P)
                 y = F.max_pool1d(self.block1(y), 2)
                 y = F.max_pool1d(self.block2(y), 2)                                                 # [nb*N, 256, L]
                 feat = y.view(nb, N, y.shape[-2], y.shape[-1])
