@@ -337,7 +337,8 @@ def run_ours(args):
                                "sample": "%d scans of one %s-shaped sequence streamed through the oracle "
                                          "(NumPy cutout, torch-CPU SpatialDROW with dense attention, NumPy NMS)" % (n, args.shape.upper()),
                                "stage_ms_per_scan": stage}
-    print(json.dumps(out))
+    _JSON_OUT.write(json.dumps(out) + "\n")
+    _JSON_OUT.flush()
     if world > 1:
         dist.destroy_process_group()
 
@@ -352,7 +353,7 @@ def run_reference(args):
     v, cores, timed, stage = cpu_reference_scans_per_s(args.shape, n, warmup=args.warmup, sequences=seqs_per_step)
     sample = ("each step = one scan of %d of the %d %s-shaped sequences, streamed through the oracle port of the "
               "reference's CPU path" % (seqs_per_step, args.sequences, args.shape.upper()))
-    print(json.dumps({
+    _JSON_OUT.write(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * seqs_per_step / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -361,11 +362,21 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": "scans/s", "cores": cores, "kind": "port", "sample": sample,
                          "stage_ms_per_scan": stage},
         "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }) + "\n")
+    _JSON_OUT.flush()
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL's version banner, cuDNN notes) get stderr."""
+    real = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return real
 
 
 if __name__ == "__main__":
     a = parse()
+    _JSON_OUT = _claim_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -170,6 +170,28 @@ POF_API int pof_nms_centers(const void* scan, int scan_is_f64, const void* phi, 
                     double* det_xy, float* det_cls,
                     void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * 4. Backbone glue - used by the streaming engine only.
+ *    The convolutions of DROW / SpatialDROW (src/depracted/model/dr_spaam.py:8-12,
+ *    49-59,87-114) stay on cuDNN; these fuse what runs between them in eval mode
+ *    (bias of the BN-folded convolution, LeakyReLU :12, max_pool1d(2) :81) into one
+ *    pass over channels-last activations, and optionally emit the [hi | lo | hi]
+ *    TF32 operand split that makes tensor-core convolutions fp32-accurate.
+ *
+ *    pof_act_fwd         y [rows_in, C] -> out_plain [rows_in/pool, C] and/or
+ *                        out_split [rows_in/pool, 3C]; bias [C] or NULL; pool in {1,2}
+ *                        (pool = 2 takes the max of consecutive row pairs: rows of one
+ *                        cutout are its L positions, L even); slope = 1 -> identity.
+ *    pof_conv_first_fwd  cutouts [M, P] (x) weight [C, 3], bias [C] -> [M*P, C] / [M*P, 3C]:
+ *                        the 1 -> C, k = 3, zero-padded first layer + LeakyReLU (+ split).
+ * ------------------------------------------------------------------------- */
+POF_API int pof_act_fwd(const float* y, const float* bias, long long rows_in, int C, int pool,
+                        float slope, float* out_plain, float* out_split, void* stream);
+
+POF_API int pof_conv_first_fwd(const float* cutouts, const float* weight, const float* bias,
+                               long long M, int P, int C, float slope,
+                               float* out_plain, float* out_split, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,143 @@
+// Backbone glue for the streaming engine.
+//
+// The 1-D convolutions of DROW / SpatialDROW (/root/reference/src/depracted/model/dr_spaam.py:8-12,
+// 49-59, 87-114) stay on cuDNN tensor cores.  What PyTorch runs BETWEEN them in eval mode — bias add,
+// BatchNorm (folded into the convolution by the engine), LeakyReLU, max-pool — is three to four extra
+// passes over multi-GB activations.  These kernels do all of it in ONE pass over channels-last
+// activations [rows, C] and, optionally, emit the operand split that lets cuDNN's TF32 tensor cores
+// reproduce fp32 accuracy ("3xTF32"):
+//
+//     x = hi + lo,  hi = round_to_tf32(x),  lo = x - hi           (both exact in fp32)
+//     conv(x, w) ~= conv(hi, w_hi) + conv(lo, w_hi) + conv(hi, w_lo)   (dropped lo*lo term: 2^-22)
+//
+// evaluated as ONE convolution over 3*C input channels [hi | lo | hi] against weights
+// [w_hi | w_hi | w_lo]; every product the tensor core forms is exact (11-bit x 11-bit significands)
+// and accumulation is fp32.
+//
+//   pof_act_fwd          y[rows_in, C] (+bias) -> LeakyReLU -> max over `pool` consecutive rows ->
+//                        plain [rows_out, C] and/or split [rows_out, 3C]
+//   pof_conv_first_fwd   the 1 -> C first layer (k = 3, zero padding) straight from the cutouts, fused
+//                        with bias + LeakyReLU + split: cuDNN needs 2.4 ms for these 3 GFLOP.
+// Both are pure streaming kernels (HBM bound): 128-bit accesses, grid-stride.
+#include "pof_common.cuh"
+
+namespace pof {
+namespace {
+
+__device__ __forceinline__ float tf32_round(float x) {
+    // round to nearest even on the 13 dropped significand bits
+    unsigned u = __float_as_uint(x);
+    u += 0x0fffu + ((u >> 13) & 1u);
+    return __uint_as_float(u & 0xffffe000u);
+}
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+__device__ __forceinline__ void emit(float4 v, size_t row, int c, int C, float* plain, float* split) {
+    if (plain) *reinterpret_cast<float4*>(plain + row * C + c) = v;
+    if (split) {
+        const float4 hi = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+        const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+        float* base = split + row * 3 * (size_t)C + c;
+        st_stream_f4(reinterpret_cast<float4*>(base), hi);
+        st_stream_f4(reinterpret_cast<float4*>(base + C), lo);
+        st_stream_f4(reinterpret_cast<float4*>(base + 2 * (size_t)C), hi);
+    }
+}
+
+template <int POOL>
+__global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ y, const float* __restrict__ bias, float slope,
+                                                  int C, long long rows_out, float* plain, float* split) {
+    const int c4n = C >> 2;
+    const long long total = rows_out * c4n;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long row = t / c4n;
+        const int c = (int)(t - row * c4n) << 2;
+        const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = ld_stream_f4(reinterpret_cast<const float4*>(y + (size_t)row * POOL * C + c));
+        if (POOL == 2) {
+            const float4 w = ld_stream_f4(reinterpret_cast<const float4*>(y + ((size_t)row * POOL + 1) * C + c));
+            v = make_float4(fmaxf(v.x, w.x), fmaxf(v.y, w.y), fmaxf(v.z, w.z), fmaxf(v.w, w.w));   // lrelu is monotone
+        }
+        v = make_float4(lrelu(v.x + b.x, slope), lrelu(v.y + b.y, slope), lrelu(v.z + b.z, slope), lrelu(v.w + b.w, slope));
+        emit(v, (size_t)row, c, C, plain, split);
+    }
+}
+
+// out[m, l, c] = lrelu(b[c] + sum_k w[c, k] * x[m, l + k - 1]),  x = cutouts [M, P], zero padded
+__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float slope, int P, int C,
+                                                         long long rows /* M*P */, float* plain, float* split) {
+    extern __shared__ float wsm[];                 // [C][4]: w0, w1, w2, bias
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        wsm[4 * i] = w[3 * i]; wsm[4 * i + 1] = w[3 * i + 1]; wsm[4 * i + 2] = w[3 * i + 2]; wsm[4 * i + 3] = bias[i];
+    }
+    __syncthreads();
+    const int c4n = C >> 2;
+    const long long total = rows * c4n;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long row = t / c4n;
+        const int c = (int)(t - row * c4n) << 2;
+        const int l = (int)(row % P);
+        const float xc = __ldg(x + row);
+        const float xl = l > 0 ? __ldg(x + row - 1) : 0.f;
+        const float xr = l < P - 1 ? __ldg(x + row + 1) : 0.f;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 q = *reinterpret_cast<const float4*>(wsm + 4 * (c + j));
+            o[j] = lrelu(fmaf(q.z, xr, fmaf(q.y, xc, fmaf(q.x, xl, q.w))), slope);
+        }
+        emit(make_float4(o[0], o[1], o[2], o[3]), (size_t)row, c, C, plain, split);
+    }
+}
+
+unsigned stream_grid(long long items, int threads) {
+    const long long want = (items + threads - 1) / threads;
+    const long long cap = (long long)sm_count() * 16;
+    return (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace
+}  // namespace pof
+
+extern "C" {
+
+int pof_act_fwd(const float* y, const float* bias, long long rows_in, int C, int pool, float slope, float* out_plain,
+                float* out_split, void* stream_) {
+    using namespace pof;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (rows_in == 0) return POF_OK;
+    POF_REQUIRE(y && (out_plain || out_split), POF_ERR_NULL_POINTER, "pof_act_fwd: null input or no output");
+    POF_REQUIRE(C >= 4 && (C % 4) == 0, POF_ERR_BAD_SHAPE, "pof_act_fwd: C must be a multiple of 4 (got %d)", C);
+    POF_REQUIRE(pool == 1 || pool == 2, POF_ERR_UNSUPPORTED, "pof_act_fwd: pool must be 1 or 2 (got %d)", pool);
+    POF_REQUIRE(rows_in > 0 && rows_in % pool == 0, POF_ERR_BAD_SHAPE, "pof_act_fwd: rows_in must be a positive multiple of pool");
+    const uintptr_t al = reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias) |
+                         reinterpret_cast<uintptr_t>(out_plain) | reinterpret_cast<uintptr_t>(out_split);
+    POF_REQUIRE((al & 15) == 0, POF_ERR_BAD_PARAM, "pof_act_fwd: tensors must be 16-byte aligned");
+    const long long rows_out = rows_in / pool;
+    const unsigned grid = stream_grid(rows_out * (C >> 2), 256);
+    if (pool == 1) act_kernel<1><<<grid, 256, 0, stream>>>(y, bias, slope, C, rows_out, out_plain, out_split);
+    else act_kernel<2><<<grid, 256, 0, stream>>>(y, bias, slope, C, rows_out, out_plain, out_split);
+    POF_CUDA(cudaGetLastError());
+    return POF_OK;
+}
+
+int pof_conv_first_fwd(const float* cutouts, const float* weight, const float* bias, long long M, int P, int C, float slope,
+                       float* out_plain, float* out_split, void* stream_) {
+    using namespace pof;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (M == 0) return POF_OK;
+    POF_REQUIRE(cutouts && weight && bias && (out_plain || out_split), POF_ERR_NULL_POINTER, "pof_conv_first_fwd: null pointer");
+    POF_REQUIRE(M > 0 && P >= 1 && C >= 4 && (C % 4) == 0 && C <= 1024, POF_ERR_BAD_SHAPE,
+                "pof_conv_first_fwd: bad shape M=%lld P=%d C=%d", M, P, C);
+    const uintptr_t al = reinterpret_cast<uintptr_t>(out_plain) | reinterpret_cast<uintptr_t>(out_split);
+    POF_REQUIRE((al & 15) == 0, POF_ERR_BAD_PARAM, "pof_conv_first_fwd: outputs must be 16-byte aligned");
+    const long long rows = M * P;
+    const unsigned grid = stream_grid(rows * (C >> 2), 256);
+    conv_first_kernel<<<grid, 256, (size_t)C * 4 * sizeof(float), stream>>>(cutouts, weight, bias, slope, P, C, rows, out_plain,
+                                                                           out_split);
+    POF_CUDA(cudaGetLastError());
+    return POF_OK;
+}
+
+}  // extern "C"

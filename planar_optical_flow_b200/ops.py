@@ -140,6 +140,38 @@ def gate(x, tmpl, emb_x, emb_t, alpha, window):
     return _GateFn.apply(x, tmpl, emb_x, emb_t, float(alpha), int(window))
 
 
+# --------------------------------------------------------------------------- backbone glue
+def act(y, bias=None, pool=1, slope=0.1, want_plain=True, want_split=False):
+    """Channels-last activations y [rows, C] -> (+bias) LeakyReLU, max over `pool` consecutive rows.
+
+    Returns (plain [rows/pool, C] or None, split [rows/pool, 3C] = [hi | lo | hi] or None)."""
+    require_cuda_tensor(y, "y", torch.float32)
+    rows, C = y.shape
+    dev = y.device
+    with torch.cuda.device(dev):
+        plain = torch.empty((rows // pool, C), dtype=torch.float32, device=dev) if want_plain else None
+        split = torch.empty((rows // pool, 3 * C), dtype=torch.float32, device=dev) if want_split else None
+        check(_lib.lib().pof_act_fwd(_ptr(y), _ptr(bias), rows, C, int(pool), float(slope), _ptr(plain), _ptr(split),
+                                     current_stream_ptr(dev)), "pof_act_fwd")
+    return plain, split
+
+
+def conv_first(cutouts, weight, bias, slope=0.1, want_plain=False, want_split=True):
+    """cutouts [M, P], weight [C, 3], bias [C] -> first conv layer + LeakyReLU, channels-last [M*P, C] / [M*P, 3C]."""
+    require_cuda_tensor(cutouts, "cutouts", torch.float32)
+    require_cuda_tensor(weight, "weight", torch.float32)
+    require_cuda_tensor(bias, "bias", torch.float32)
+    M, P = cutouts.shape
+    C = weight.shape[0]
+    dev = cutouts.device
+    with torch.cuda.device(dev):
+        plain = torch.empty((M * P, C), dtype=torch.float32, device=dev) if want_plain else None
+        split = torch.empty((M * P, 3 * C), dtype=torch.float32, device=dev) if want_split else None
+        check(_lib.lib().pof_conv_first_fwd(_ptr(cutouts), _ptr(weight), _ptr(bias), M, P, C, float(slope), _ptr(plain),
+                                            _ptr(split), current_stream_ptr(dev)), "pof_conv_first_fwd")
+    return plain, split
+
+
 # --------------------------------------------------------------------------- nms
 def nms_centers(scan, phi, cls, reg, min_dist=0.5):
     """Batched `nms_predicted_center` (reference: src/utils/utils.py:535-571).
