@@ -192,6 +192,14 @@ POF_API int pof_conv_first_fwd(const float* cutouts, const float* weight, const 
                                long long M, int P, int C, float slope,
                                float* out_plain, float* out_split, void* stream);
 
+/*    pof_head_fwd        the tail of DROW._forward_fused_cutout (dr_spaam.py:110-114): y [M, L, C] raw
+ *                        output of the last convolution -> +bias, LeakyReLU -> avg_pool1d over L ->
+ *                        H 1x1-convolution heads (w_head [H, C], b_head [H]; conv_cls rows first, then
+ *                        conv_reg) -> sigmoid on the first n_sigmoid heads -> out [M, H].  H <= 8.       */
+POF_API int pof_head_fwd(const float* y, const float* bias, long long M, int L, int C, float slope,
+                         const float* w_head, const float* b_head, int H, int n_sigmoid,
+                         float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,47 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
     }
 }
 
+// One warp per cutout: y [M, L, C] (raw output of the last convolution, channels last)
+//   -> lrelu(y + bias) -> mean over L -> H heads (1x1 convolutions) -> sigmoid on the first n_sig.
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ y, const float* __restrict__ bias, float slope,
+                                                   int L, int C, const float* __restrict__ w_head,
+                                                   const float* __restrict__ b_head, int H, int n_sig, long long M,
+                                                   float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
+        float acc[8];                              // up to 8 heads
+#pragma unroll
+        for (int h = 0; h < 8; ++h) acc[h] = 0.f;
+        for (int c = lane * 4; c < C; c += 128) {
+            const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int l = 0; l < L; ++l) {
+                const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(y + ((size_t)m * L + l) * C + c));
+                s.x += lrelu(v.x + b.x, slope); s.y += lrelu(v.y + b.y, slope);
+                s.z += lrelu(v.z + b.z, slope); s.w += lrelu(v.w + b.w, slope);
+            }
+            const float fl = (float)L;
+            s.x = __fdiv_rn(s.x, fl); s.y = __fdiv_rn(s.y, fl); s.z = __fdiv_rn(s.z, fl); s.w = __fdiv_rn(s.w, fl);
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                if (h < H) {
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(w_head + (size_t)h * C + c));
+                    acc[h] = fmaf(s.x, w.x, fmaf(s.y, w.y, fmaf(s.z, w.z, fmaf(s.w, w.w, acc[h]))));
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            if (h < H) {
+                float v = warp_sum(acc[h]) + __ldg(b_head + h);
+                if (h < n_sig) v = 1.f / (1.f + expf(-v));
+                if (lane == 0) out[(size_t)m * H + h] = v;
+            }
+        }
+    }
+}
+
 unsigned stream_grid(long long items, int threads) {
     const long long want = (items + threads - 1) / threads;
     const long long cap = (long long)sm_count() * 16;
@@ -136,6 +177,23 @@ int pof_conv_first_fwd(const float* cutouts, const float* weight, const float* b
     const unsigned grid = stream_grid(rows * (C >> 2), 256);
     conv_first_kernel<<<grid, 256, (size_t)C * 4 * sizeof(float), stream>>>(cutouts, weight, bias, slope, P, C, rows, out_plain,
                                                                            out_split);
+    POF_CUDA(cudaGetLastError());
+    return POF_OK;
+}
+
+int pof_head_fwd(const float* y, const float* bias, long long M, int L, int C, float slope, const float* w_head,
+                 const float* b_head, int H, int n_sigmoid, float* out, void* stream_) {
+    using namespace pof;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (M == 0) return POF_OK;
+    POF_REQUIRE(y && w_head && b_head && out, POF_ERR_NULL_POINTER, "pof_head_fwd: null pointer");
+    POF_REQUIRE(M > 0 && L >= 1 && C >= 4 && (C % 4) == 0, POF_ERR_BAD_SHAPE, "pof_head_fwd: bad shape M=%lld L=%d C=%d", M, L, C);
+    POF_REQUIRE(H >= 1 && H <= 8 && n_sigmoid >= 0 && n_sigmoid <= H, POF_ERR_BAD_SHAPE,
+                "pof_head_fwd: 1..8 heads supported (got %d, %d with sigmoid)", H, n_sigmoid);
+    const uintptr_t al = reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(w_head);
+    POF_REQUIRE((al & 15) == 0, POF_ERR_BAD_PARAM, "pof_head_fwd: y, bias and w_head must be 16-byte aligned");
+    const unsigned grid = stream_grid(M * 32, 256);
+    head_kernel<<<grid, 256, 0, stream>>>(y, bias, slope, L, C, w_head, b_head, H, n_sigmoid, M, out);
     POF_CUDA(cudaGetLastError());
     return POF_OK;
 }

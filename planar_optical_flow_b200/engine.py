@@ -12,10 +12,20 @@ lock-step with nothing but the raw ranges going up and the detections coming dow
 Sequences never interact, so multi-GPU use is one detector per rank over a
 disjoint set of sequences with no data-path collective.
 
-Numerics: `precision="fp32"` (default) keeps every convolution in IEEE fp32 and matches the
-reference's CPU path to ~1e-6 relative (BatchNorm is folded into the convolutions in eval
-mode, which re-associates a multiply); `"tf32"` allows TF32 tensor-core convolutions (the
-PyTorch default on GPU, ~1e-3) and is reported separately as a throughput mode.
+Numerics (BatchNorm is folded into the convolutions in eval mode in every mode, which
+re-associates one multiply):
+  * `precision="fp32"`   every convolution in IEEE fp32 on cuDNN's SIMT kernels, NCL layout as in the
+                         reference; ~1e-6 relative to the reference's CPU path.  The strict mode.
+  * `precision="tf32x3"` fp32-ACCURATE convolutions on the TF32 tensor cores: activations and weights
+                         are split x = hi + lo (hi exactly TF32) and each convolution runs once over
+                         [hi | lo | hi] x [w_hi | w_hi | w_lo] with fp32 accumulation, i.e. the three
+                         significant partial products of the fp32 product (the dropped lo*lo term is
+                         2^-22 relative).  Activations are channels-last; libpof's glue kernels
+                         (csrc/pof_backbone.cu) fuse bias + LeakyReLU + max-pool + split into one pass
+                         per layer, and the first layer and the avg-pool/heads/sigmoid tail are theirs too.
+  * `precision="tf32"`   the same channels-last pipeline without the split: plain TF32 (what PyTorch's
+                         defaults give the reference on a GPU, ~1e-3).  Throughput mode, reported
+                         separately.
 """
 import contextlib
 
@@ -50,6 +60,100 @@ class _FoldedStack:
         return x
 
 
+def split_tf32(w):
+    """w = hi + lo, hi = w rounded to TF32 (nearest even on the 13 dropped bits); both exact in fp32."""
+    u = w.contiguous().view(torch.int32)
+    hi = ((u + 0x0fff + ((u >> 13) & 1)) & -8192).view(torch.float32)
+    return hi, w - hi
+
+
+class _ChannelsLastBackbone:
+    """The DROW/SpatialDROW convolutions over channels-last activations [rows = cutout x position, C].
+
+    split=True: operands carry the [hi | lo | hi] TF32 split (3C channels), weights [w_hi | w_hi | w_lo].
+    The convolutions themselves are cuDNN (conv2d NHWC with H = 1), as north_star prescribes for the
+    only dense contraction; everything between them is libpof's fused glue.
+    """
+
+    def __init__(self, model, split):
+        self.split = bool(split)
+        blocks = [model.conv_block_1, model.conv_block_2, model.conv_block_3, model.conv_block_4]
+        folded = [[fold_conv_bn(layer) for layer in blk] for blk in blocks]
+        w0, b0 = folded[0][0]
+        self.w_first, self.b_first = w0.reshape(w0.shape[0], 3).contiguous(), b0
+        self.layers = [[(self._conv_weight(w), b, w.shape[0]) for w, b in blk] for blk in folded]
+        we, be = fold_conv_bn(model.gate.conv)                      # [E, C, L]
+        self.emb_b = be
+        self.emb_w = self._embed_weight(we)                         # [L * Ceff, E]
+        self.w_head = torch.cat([model.conv_cls.weight.detach()[:, :, 0], model.conv_reg.weight.detach()[:, :, 0]]).contiguous()
+        self.b_head = torch.cat([model.conv_cls.bias.detach(), model.conv_reg.bias.detach()]).contiguous()
+        self.n_cls = int(model.conv_cls.weight.shape[0])
+
+    def _cat(self, w, dim):
+        if not self.split:
+            return w
+        hi, lo = split_tf32(w)
+        return torch.cat([hi, hi, lo], dim=dim)
+
+    def _conv_weight(self, w):                                       # [Cout, Cin, 3] -> [Cout, Ceff, 1, 3] NHWC
+        return self._cat(w, 1).unsqueeze(2).contiguous(memory_format=torch.channels_last)
+
+    def _embed_weight(self, w):                                      # [E, C, L] -> [L * Ceff, E]
+        return self._cat(w, 1).permute(2, 1, 0).reshape(-1, w.shape[0]).contiguous()
+
+    def _conv(self, a, M, L, w4, cout):
+        x4 = a.view(M, 1, L, a.shape[1]).permute(0, 3, 1, 2)         # [M, Ceff, 1, L], NHWC strides, no copy
+        y = F.conv2d(x4, w4, None, padding=(0, 1)).permute(0, 2, 3, 1)
+        if not y.is_contiguous():
+            raise RuntimeError("cuDNN returned a non-channels-last convolution output")
+        return y.view(M * L, cout)
+
+    def _act(self, y, bias, pool, plain=False):
+        """-> (plain or None, operand for the next convolution)."""
+        p, s = ops.act(y, bias, pool=pool, slope=_SLOPE, want_plain=plain or not self.split, want_split=self.split)
+        return p, (s if self.split else p)
+
+    def operand(self, plain_rows):
+        """The convolution operand of already-activated rows (the attention memory)."""
+        if not self.split:
+            return plain_rows
+        return ops.act(plain_rows, None, pool=1, slope=1.0, want_plain=False, want_split=True)[1]
+
+    def features(self, cutouts):
+        """cutouts [M, P] -> (features [M * P/4, 256] plain, the same rows as a convolution operand)."""
+        M, L = cutouts.shape
+        p, s = ops.conv_first(cutouts, self.w_first, self.b_first, slope=_SLOPE, want_plain=not self.split,
+                              want_split=self.split)
+        a = s if self.split else p
+        plain = None
+        for bi in (0, 1):
+            todo = self.layers[bi][1:] if bi == 0 else self.layers[bi]
+            for k, (w4, b, cout) in enumerate(todo):
+                y = self._conv(a, M, L, w4, cout)
+                last = k == len(todo) - 1
+                plain, a = self._act(y, b, 2 if last else 1, plain=last and bi == 1)
+                if last:
+                    L //= 2
+        return plain, a
+
+    def embed(self, operand, M):
+        """Gate embedding (Conv1d k = L, no padding == one GEMM over whole rows) + BN + LeakyReLU."""
+        return F.leaky_relu_(torch.addmm(self.emb_b, operand.view(M, -1), self.emb_w), _SLOPE)
+
+    def votes(self, operand, M, L):
+        """memory rows (as operand) [M * L, Ceff] -> [M, n_cls + 2]: (sigmoid(cls) | reg)."""
+        a = operand
+        for bi in (2, 3):
+            for k, (w4, b, cout) in enumerate(self.layers[bi]):
+                y = self._conv(a, M, L, w4, cout)
+                if bi == 3 and k == len(self.layers[bi]) - 1:
+                    return ops.head(y, b, M, L, self.w_head, self.b_head, n_sigmoid=self.n_cls, slope=_SLOPE)
+                last = k == len(self.layers[bi]) - 1
+                _, a = self._act(y, b, 2 if last else 1)
+                if last:
+                    L //= 2
+
+
 class StreamingDetector:
     """B sequences in lock-step; owns their attention memory.
 
@@ -62,8 +166,8 @@ class StreamingDetector:
                  min_dist=0.5, seq_chunk=None, record_events=False):
         if not torch.cuda.is_available():
             raise RuntimeError("StreamingDetector needs a CUDA device; there is no CPU path")
-        if precision not in ("fp32", "tf32"):
-            raise ValueError("precision must be 'fp32' or 'tf32'")
+        if precision not in ("fp32", "tf32x3", "tf32"):
+            raise ValueError("precision must be 'fp32', 'tf32x3' or 'tf32'")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.precision = precision
         self.cutout_kwargs = dict(cutout_kwargs)
@@ -79,7 +183,12 @@ class StreamingDetector:
         model = model.to(self.device).eval()
         self.alpha = float(model.gate._alpha)
         self.window = int(model.gate.window)
+        self.channels_last = precision != "fp32"
         with torch.no_grad():
+            if self.channels_last:
+                if self.P % 4:
+                    raise ValueError("the channels-last pipeline needs num_cutout_pts to be a multiple of 4")
+                self.net = _ChannelsLastBackbone(model, split=precision == "tf32x3")
             self.block1 = _FoldedStack(model.conv_block_1, 1)
             self.block2 = _FoldedStack(model.conv_block_2, 1)
             self.block3 = _FoldedStack(model.conv_block_3, 1)
@@ -95,10 +204,15 @@ class StreamingDetector:
         if seq_chunk:
             self.seq_chunk = int(seq_chunk)
         else:
-            n_chunks = max(1, -(-self.B * self.N // (1 << 18)))
+            # the split operands are 3x wider: keep every activation below 2^30 elements
+            n_chunks = max(1, -(-self.B * self.N // (73728 if self.channels_last else 1 << 18)))
             self.seq_chunk = -(-self.B // n_chunks)
         C, L = 256, int(np.ceil(self.P / 4))
-        self.memory = [torch.empty((self.B, self.N, C, L), dtype=torch.float32, device=self.device) for _ in range(2)]
+        # memory rows are [C, L] (reference layout) or, in the channels-last modes, [L, C]; the gate
+        # kernel only needs x and the memory to agree
+        shape = (self.B, self.N, L, C) if self.channels_last else (self.B, self.N, C, L)
+        self.memory = [torch.empty(shape, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.emb_memory = torch.empty((self.B, self.N, 128), dtype=torch.float32, device=self.device)
         self.cur = 0                       # index of the buffer holding the current memory
         self.has_memory = False
         self.steps_done = 0
@@ -127,7 +241,7 @@ class StreamingDetector:
     @contextlib.contextmanager
     def _precision(self):
         old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
-        allow = self.precision == "tf32"
+        allow = self.precision != "fp32"
         torch.backends.cudnn.allow_tf32 = allow
         torch.backends.cuda.matmul.allow_tf32 = allow
         try:
@@ -150,6 +264,61 @@ class StreamingDetector:
         """Durations (ms) of the recorded launches of one stage; call after a synchronize."""
         return [s.elapsed_time(e) for s, e in self.events[name]]
 
+    # ------------------------------------------------------------------ one chunk of sequences
+    def _chunk_channels_last(self, cutouts, b0, b1, first, prev, nxt, pred_cls, pred_reg, feat_fused):
+        N = self.N
+        nb, M, L = b1 - b0, (b1 - b0) * N, self.P // 4
+        feat, x_op = self.net.features(cutouts[b0:b1].view(M, self.P))
+        feat = feat.view(nb, N, L, -1)
+        emb_x = self.net.embed(x_op, M).view(nb, N, -1)
+        if first:                # memory := features; similarities against itself (dr_spaam.py:242-244)
+            nxt[b0:b1].copy_(feat)
+            with self._timed("gate"):
+                _, ff, _ = ops.gate_forward(feat, nxt[b0:b1], emb_x, emb_x, self.alpha, self.window, out=prev[b0:b1])
+            self.emb_memory[b0:b1] = emb_x
+            t_op = x_op
+        else:
+            with self._timed("gate"):
+                _, ff, _ = ops.gate_forward(feat, prev[b0:b1], emb_x, self.emb_memory[b0:b1], self.alpha,
+                                            self.window, out=nxt[b0:b1])
+            t_op = self.net.operand(nxt[b0:b1].view(M * L, -1))
+            # the embedding of the NEW memory is what the next step's gate needs (dr_spaam.py:180-181)
+            self.emb_memory[b0:b1] = self.net.embed(t_op, M).view(nb, N, -1)
+            self.kernel_launches += 1 if self.net.split else 0
+        feat_fused[b0:b1] = ff
+        v = self.net.votes(t_op, M, L).view(nb, N, -1)
+        self.kernel_launches += 12       # first layer + 9 activation passes + head + gate
+        pred_cls[b0:b1] = v[:, :, 0]
+        pred_reg[b0:b1] = v[:, :, 1:]
+
+    def _chunk_ncl(self, cutouts, b0, b1, first, prev, nxt, pred_cls, pred_reg, feat_fused):
+        N = self.N
+        nb = b1 - b0
+        y = cutouts[b0:b1].view(nb * N, 1, self.P)
+        y = F.max_pool1d(self.block1(y), 2)
+        y = F.max_pool1d(self.block2(y), 2)                                                 # [nb*N, 256, L]
+        feat = y.view(nb, N, y.shape[-2], y.shape[-1])
+        emb_x = self.embed(y).view(nb, N, -1)
+        if first:
+            # first frame: memory := features, similarities against itself (dr_spaam.py:242-244)
+            nxt[b0:b1].copy_(feat)
+            with self._timed("gate"):
+                _, ff, _ = ops.gate_forward(feat, nxt[b0:b1], emb_x, emb_x, self.alpha, self.window,
+                                            out=prev[b0:b1])          # blended output is discarded
+        else:
+            emb_t = self.embed(prev[b0:b1].view(nb * N, y.shape[-2], y.shape[-1])).view(nb, N, -1)
+            with self._timed("gate"):
+                _, ff, _ = ops.gate_forward(feat, prev[b0:b1], emb_x, emb_t, self.alpha, self.window,
+                                            out=nxt[b0:b1])
+        self.kernel_launches += 1
+        feat_fused[b0:b1] = ff
+        z = nxt[b0:b1].view(nb * N, y.shape[-2], y.shape[-1])
+        z = F.max_pool1d(self.block3(z), 2)
+        z = self.block4(z)
+        z = F.avg_pool1d(z, z.shape[-1])
+        pred_cls[b0:b1] = torch.sigmoid(F.conv1d(z, self.w_cls, self.b_cls).view(nb, N))
+        pred_reg[b0:b1] = F.conv1d(z, self.w_reg, self.b_reg).view(nb, N, 2)
+
     # ------------------------------------------------------------------ the step
     @torch.no_grad()
     def step_device(self, scans):
@@ -170,33 +339,9 @@ class StreamingDetector:
             with self._timed("cutout"):      # one launch for all B sequences: [B, N, 1, P]
                 cutouts = ops.cutout(scans.unsqueeze(1), self.phi, fast=True, **self.cutout_kwargs)
             self.kernel_launches += 2 if self.cutout_kwargs.get("area_mode") else 1
+            chunk = self._chunk_channels_last if self.channels_last else self._chunk_ncl
             for b0 in range(0, B, self.seq_chunk):
-                b1 = min(B, b0 + self.seq_chunk)
-                nb = b1 - b0
-                y = cutouts[b0:b1].view(nb * N, 1, self.P)
-                y = F.max_pool1d(self.block1(y), 2)
-                y = F.max_pool1d(self.block2(y), 2)                                                 # [nb*N, 256, L]
-                feat = y.view(nb, N, y.shape[-2], y.shape[-1])
-                emb_x = self.embed(y).view(nb, N, -1)
-                if first:
-                    # first frame: memory := features, similarities against itself (dr_spaam.py:242-244)
-                    nxt[b0:b1].copy_(feat)
-                    with self._timed("gate"):
-                        _, ff, _ = ops.gate_forward(feat, nxt[b0:b1], emb_x, emb_x, self.alpha, self.window,
-                                                    out=prev[b0:b1])          # blended output is discarded
-                else:
-                    emb_t = self.embed(prev[b0:b1].view(nb * N, y.shape[-2], y.shape[-1])).view(nb, N, -1)
-                    with self._timed("gate"):
-                        _, ff, _ = ops.gate_forward(feat, prev[b0:b1], emb_x, emb_t, self.alpha, self.window,
-                                                    out=nxt[b0:b1])
-                self.kernel_launches += 1
-                feat_fused[b0:b1] = ff
-                z = nxt[b0:b1].view(nb * N, y.shape[-2], y.shape[-1])
-                z = F.max_pool1d(self.block3(z), 2)
-                z = self.block4(z)
-                z = F.avg_pool1d(z, z.shape[-1])
-                pred_cls[b0:b1] = torch.sigmoid(F.conv1d(z, self.w_cls, self.b_cls).view(nb, N))
-                pred_reg[b0:b1] = F.conv1d(z, self.w_reg, self.b_reg).view(nb, N, 2)
+                chunk(cutouts, b0, min(B, b0 + self.seq_chunk), first, prev, nxt, pred_cls, pred_reg, feat_fused)
             with self._timed("nms"):
                 res = ops.nms_centers(scans, self.phi, pred_cls, pred_reg, min_dist=self.min_dist)
             self.kernel_launches += 3
@@ -210,7 +355,8 @@ class StreamingDetector:
     @property
     def template(self):
         """The current attention memory [B, N, 256, L] (what the reference returns as out_template)."""
-        return self.memory[self.cur]
+        m = self.memory[self.cur]
+        return m.permute(0, 1, 3, 2) if self.channels_last else m
 
     def step(self, scans_host):
         """Host-facing call: NumPy/CPU-tensor ranges [B, N] in, detections (NumPy views of pinned

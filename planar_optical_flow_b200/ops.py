@@ -172,6 +172,21 @@ def conv_first(cutouts, weight, bias, slope=0.1, want_plain=False, want_split=Tr
     return plain, split
 
 
+def head(y, bias, M, L, w_head, b_head, n_sigmoid, slope=0.1):
+    """y [M*L, C] raw last-conv output -> +bias, LeakyReLU, mean over L, heads [H, C] (+ sigmoid on the first n_sigmoid) -> [M, H]."""
+    require_cuda_tensor(y, "y", torch.float32)
+    require_cuda_tensor(w_head, "w_head", torch.float32)
+    require_cuda_tensor(b_head, "b_head", torch.float32)
+    C = y.shape[-1]
+    H = w_head.shape[0]
+    dev = y.device
+    with torch.cuda.device(dev):
+        out = torch.empty((M, H), dtype=torch.float32, device=dev)
+        check(_lib.lib().pof_head_fwd(_ptr(y), _ptr(bias), M, int(L), C, float(slope), _ptr(w_head), _ptr(b_head), H,
+                                      int(n_sigmoid), _ptr(out), current_stream_ptr(dev)), "pof_head_fwd")
+    return out
+
+
 # --------------------------------------------------------------------------- nms
 def nms_centers(scan, phi, cls, reg, min_dist=0.5):
     """Batched `nms_predicted_center` (reference: src/utils/utils.py:535-571).
