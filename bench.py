@@ -2,7 +2,7 @@
 """Benchmark of the DR-SPAAM per-point scan hot path on B200 (see BASELINE.json).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--sequences 256] [--shape jrdb|drow] [--precision fp32|tf32]
+                    [--sequences 256] [--shape jrdb|drow] [--precision fp32|fp32-simt|tf32x3|tf32]
 
 Workload (BASELINE.json configs[2], the one the metric is quoted on): DR-SPAAM streaming
 inference with spatial-attention memory over 256 independent JRDB-shaped sequences
@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sequences", type=int, default=256, help="sequences per GPU")
     ap.add_argument("--shape", default="jrdb", choices=["jrdb", "drow"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32-simt", "tf32x3", "tf32"])
     ap.add_argument("--cpu-scans", type=int, default=24, help="scans in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extra-precisions", default="", help="comma list of further engine precisions to time (device only)")
@@ -223,6 +223,7 @@ def run_ours(args):
                 checksum += int(res["n_keep"].sum())
         e1.record()
         torch.cuda.synchronize(dev)
+        det.check()
         if world > 1:
             dist.barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -300,7 +301,9 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": world * B * K / (ms_dev / 1e3), "unit": "scans/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 split products, fp32 accumulate)", "tf32": "tf32"}[args.precision], "data": "synthetic",
+        "vs_baseline": None, "dtype": {"fp32": "f32 (3xTF32 split products on tcgen05, chains promoted to fp32 registers; 2-4e-7 per layer vs fp64)",
+                                      "fp32-simt": "f32", "tf32x3": "f32 operands, TF32 tensor-core accumulation (1e-4)",
+                                      "tf32": "tf32"}[args.precision], "data": "synthetic",
         "impl": "ours",
         "config": {"workload": "DR-SPAAM streaming inference, %d independent %s-shaped sequences per GPU (%d pts), "
                                "cutout+backbone+attention memory+heads+NMS per scan" % (B, args.shape.upper(), N),

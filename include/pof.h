@@ -178,19 +178,23 @@ POF_API int pof_nms_centers(const void* scan, int scan_is_f64, const void* phi, 
  *    pass over channels-last activations, and optionally emit the [hi | lo | hi]
  *    TF32 operand split that makes tensor-core convolutions fp32-accurate.
  *
+ *    split_parts = 3: out_split rows are [hi | lo | hi], lo = x - hi exact (operand of a cuDNN TF32
+ *    convolution against [w_hi | w_hi | w_lo]); split_parts = 2: [hi | lo], lo rounded to TF32 (operand
+ *    of pof_conv_tc_fwd).
+ *
  *    pof_act_fwd         y [rows_in, C] -> out_plain [rows_in/pool, C] and/or
- *                        out_split [rows_in/pool, 3C]; bias [C] or NULL; pool in {1,2}
+ *                        out_split [rows_in/pool, split_parts*C]; bias [C] or NULL; pool in {1,2}
  *                        (pool = 2 takes the max of consecutive row pairs: rows of one
  *                        cutout are its L positions, L even); slope = 1 -> identity.
  *    pof_conv_first_fwd  cutouts [M, P] (x) weight [C, 3], bias [C] -> [M*P, C] / [M*P, 3C]:
  *                        the 1 -> C, k = 3, zero-padded first layer + LeakyReLU (+ split).
  * ------------------------------------------------------------------------- */
 POF_API int pof_act_fwd(const float* y, const float* bias, long long rows_in, int C, int pool,
-                        float slope, float* out_plain, float* out_split, void* stream);
+                        float slope, float* out_plain, float* out_split, int split_parts, void* stream);
 
 POF_API int pof_conv_first_fwd(const float* cutouts, const float* weight, const float* bias,
                                long long M, int P, int C, float slope,
-                               float* out_plain, float* out_split, void* stream);
+                               float* out_plain, float* out_split, int split_parts, void* stream);
 
 /*    pof_head_fwd        the tail of DROW._forward_fused_cutout (dr_spaam.py:110-114): y [M, L, C] raw
  *                        output of the last convolution -> +bias, LeakyReLU -> avg_pool1d over L ->
@@ -199,6 +203,22 @@ POF_API int pof_conv_first_fwd(const float* cutouts, const float* weight, const 
 POF_API int pof_head_fwd(const float* y, const float* bias, long long M, int L, int C, float slope,
                          const float* w_head, const float* b_head, int H, int n_sigmoid,
                          float* out, void* stream);
+
+/*    pof_conv_tc_fwd     fp32-accurate convolution / whole-row GEMM on tcgen05 (3xTF32 split products,
+ *                        chained accumulation promoted to fp32 registers):
+ *                          out[m, l, n] = sum_{t < taps, c < Cin} A[m, l + t - pad, c] * W[t][n, c]
+ *                        a_split [Mcut, LA, 2 Cin] = [hi | lo] rows (pof_act_fwd split_parts = 2);
+ *                        w_split [taps, 2, Cout, Cin] = (hi, lo) per tap; rows outside 0 <= l' < LA are zero.
+ *                        Conv1d(k=3,p=1): Lout = LA, taps = 3, pad = 1.  Gate embedding (dr_spaam.py:130-133,
+ *                        Conv1d(k=LA)): Lout = 1, taps = LA, pad = 0.  Epilogue: + bias, LeakyReLU(slope),
+ *                        max over `pool` consecutive rows, -> out_plain [Mcut*Lout/pool, Cout] and/or
+ *                        out_split [.., 2 Cout].  Cin % 32 == 0; Cout in {64, 128, 256 k}.
+ *                        `status` is a device int the caller zeroes: non-zero after the launch means an
+ *                        internal pipeline wait timed out (results invalid).                              */
+POF_API int pof_conv_tc_fwd(const float* a_split, const float* w_split, const float* bias,
+                            long long Mcut, int LA, int Lout, int Cin, int Cout, int taps, int pad,
+                            int pool, float slope, float* out_plain, float* out_split,
+                            int* status, void* stream);
 
 #ifdef __cplusplus
 }

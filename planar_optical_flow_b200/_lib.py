@@ -38,9 +38,11 @@ SIGNATURES = {
     "pof_spaam_gate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int, c_int, c_int, c_int, c_int, c_float,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "pof_act_fwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "pof_act_fwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p]),
     "pof_conv_first_fwd": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_float,
-                                   c_void_p, c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_int, c_void_p]),
+    "pof_conv_tc_fwd": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pof_head_fwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_int,
                              c_void_p, c_void_p]),
     "pof_nms_ws_bytes": (c_size_t, [c_int, c_int]),

@@ -32,21 +32,27 @@ __device__ __forceinline__ float tf32_round(float x) {
 }
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
-__device__ __forceinline__ void emit(float4 v, size_t row, int c, int C, float* plain, float* split) {
+// parts = 3: [hi | lo | hi] with the exact remainder (operand of a cuDNN TF32 convolution against
+//            [w_hi | w_hi | w_lo]);  parts = 2: [hi | lo] with lo rounded to TF32 (operand of pof_conv_tc_fwd).
+__device__ __forceinline__ void emit(float4 v, size_t row, int c, int C, float* plain, float* split, int parts) {
     if (plain) *reinterpret_cast<float4*>(plain + row * C + c) = v;
     if (split) {
         const float4 hi = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
-        const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-        float* base = split + row * 3 * (size_t)C + c;
+        float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+        float* base = split + row * parts * (size_t)C + c;
         st_stream_f4(reinterpret_cast<float4*>(base), hi);
+        if (parts == 3) {
+            st_stream_f4(reinterpret_cast<float4*>(base + 2 * (size_t)C), hi);
+        } else {
+            lo = make_float4(tf32_round(lo.x), tf32_round(lo.y), tf32_round(lo.z), tf32_round(lo.w));
+        }
         st_stream_f4(reinterpret_cast<float4*>(base + C), lo);
-        st_stream_f4(reinterpret_cast<float4*>(base + 2 * (size_t)C), hi);
     }
 }
 
 template <int POOL>
 __global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ y, const float* __restrict__ bias, float slope,
-                                                  int C, long long rows_out, float* plain, float* split) {
+                                                  int C, long long rows_out, float* plain, float* split, int parts) {
     const int c4n = C >> 2;
     const long long total = rows_out * c4n;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -59,14 +65,14 @@ __global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ y, c
             v = make_float4(fmaxf(v.x, w.x), fmaxf(v.y, w.y), fmaxf(v.z, w.z), fmaxf(v.w, w.w));   // lrelu is monotone
         }
         v = make_float4(lrelu(v.x + b.x, slope), lrelu(v.y + b.y, slope), lrelu(v.z + b.z, slope), lrelu(v.w + b.w, slope));
-        emit(v, (size_t)row, c, C, plain, split);
+        emit(v, (size_t)row, c, C, plain, split, parts);
     }
 }
 
 // out[m, l, c] = lrelu(b[c] + sum_k w[c, k] * x[m, l + k - 1]),  x = cutouts [M, P], zero padded
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float slope, int P, int C,
-                                                         long long rows /* M*P */, float* plain, float* split) {
+                                                         long long rows /* M*P */, float* plain, float* split, int parts) {
     extern __shared__ float wsm[];                 // [C][4]: w0, w1, w2, bias
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         wsm[4 * i] = w[3 * i]; wsm[4 * i + 1] = w[3 * i + 1]; wsm[4 * i + 2] = w[3 * i + 2]; wsm[4 * i + 3] = bias[i];
@@ -87,7 +93,7 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
             const float4 q = *reinterpret_cast<const float4*>(wsm + 4 * (c + j));
             o[j] = lrelu(fmaf(q.z, xr, fmaf(q.y, xc, fmaf(q.x, xl, q.w))), slope);
         }
-        emit(make_float4(o[0], o[1], o[2], o[3]), (size_t)row, c, C, plain, split);
+        emit(make_float4(o[0], o[1], o[2], o[3]), (size_t)row, c, C, plain, split, parts);
     }
 }
 
@@ -144,27 +150,28 @@ unsigned stream_grid(long long items, int threads) {
 extern "C" {
 
 int pof_act_fwd(const float* y, const float* bias, long long rows_in, int C, int pool, float slope, float* out_plain,
-                float* out_split, void* stream_) {
+                float* out_split, int split_parts, void* stream_) {
     using namespace pof;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (rows_in == 0) return POF_OK;
     POF_REQUIRE(y && (out_plain || out_split), POF_ERR_NULL_POINTER, "pof_act_fwd: null input or no output");
     POF_REQUIRE(C >= 4 && (C % 4) == 0, POF_ERR_BAD_SHAPE, "pof_act_fwd: C must be a multiple of 4 (got %d)", C);
     POF_REQUIRE(pool == 1 || pool == 2, POF_ERR_UNSUPPORTED, "pof_act_fwd: pool must be 1 or 2 (got %d)", pool);
+    POF_REQUIRE(split_parts == 2 || split_parts == 3, POF_ERR_BAD_PARAM, "pof_act_fwd: split_parts must be 2 or 3");
     POF_REQUIRE(rows_in > 0 && rows_in % pool == 0, POF_ERR_BAD_SHAPE, "pof_act_fwd: rows_in must be a positive multiple of pool");
     const uintptr_t al = reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias) |
                          reinterpret_cast<uintptr_t>(out_plain) | reinterpret_cast<uintptr_t>(out_split);
     POF_REQUIRE((al & 15) == 0, POF_ERR_BAD_PARAM, "pof_act_fwd: tensors must be 16-byte aligned");
     const long long rows_out = rows_in / pool;
     const unsigned grid = stream_grid(rows_out * (C >> 2), 256);
-    if (pool == 1) act_kernel<1><<<grid, 256, 0, stream>>>(y, bias, slope, C, rows_out, out_plain, out_split);
-    else act_kernel<2><<<grid, 256, 0, stream>>>(y, bias, slope, C, rows_out, out_plain, out_split);
+    if (pool == 1) act_kernel<1><<<grid, 256, 0, stream>>>(y, bias, slope, C, rows_out, out_plain, out_split, split_parts);
+    else act_kernel<2><<<grid, 256, 0, stream>>>(y, bias, slope, C, rows_out, out_plain, out_split, split_parts);
     POF_CUDA(cudaGetLastError());
     return POF_OK;
 }
 
 int pof_conv_first_fwd(const float* cutouts, const float* weight, const float* bias, long long M, int P, int C, float slope,
-                       float* out_plain, float* out_split, void* stream_) {
+                       float* out_plain, float* out_split, int split_parts, void* stream_) {
     using namespace pof;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (M == 0) return POF_OK;
@@ -173,10 +180,11 @@ int pof_conv_first_fwd(const float* cutouts, const float* weight, const float* b
                 "pof_conv_first_fwd: bad shape M=%lld P=%d C=%d", M, P, C);
     const uintptr_t al = reinterpret_cast<uintptr_t>(out_plain) | reinterpret_cast<uintptr_t>(out_split);
     POF_REQUIRE((al & 15) == 0, POF_ERR_BAD_PARAM, "pof_conv_first_fwd: outputs must be 16-byte aligned");
+    POF_REQUIRE(split_parts == 2 || split_parts == 3, POF_ERR_BAD_PARAM, "pof_conv_first_fwd: split_parts must be 2 or 3");
     const long long rows = M * P;
     const unsigned grid = stream_grid(rows * (C >> 2), 256);
     conv_first_kernel<<<grid, 256, (size_t)C * 4 * sizeof(float), stream>>>(cutouts, weight, bias, slope, P, C, rows, out_plain,
-                                                                           out_split);
+                                                                           out_split, split_parts);
     POF_CUDA(cudaGetLastError());
     return POF_OK;
 }

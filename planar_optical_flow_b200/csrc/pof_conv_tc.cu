@@ -1,0 +1,411 @@
+// fp32-accurate 1-D convolution / whole-row GEMM on the sm_100a tensor cores.
+//
+// The DROW / SpatialDROW backbone (/root/reference/src/depracted/model/dr_spaam.py:8-12, 49-59, 87-114)
+// is eleven Conv1d(k = 3, p = 1) + BatchNorm + LeakyReLU layers plus the gate's Conv1d(k = L) embedding
+// (:130-133).  With BatchNorm folded and channels-last activations every one of them is
+//
+//     out[m, l, n] = sum_{t < taps} sum_{c < Cin}  A[m, l + t - pad, c] * W[t][n, c]        (zero outside 0 <= l' < LA)
+//
+// i.e. `taps` accumulated GEMMs over row-shifted views of the same matrix.  This kernel runs them on
+// tcgen05 with the operand split x = hi + lo (hi exactly TF32, lo = the rounded remainder; "3xTF32"):
+//
+//     x*w ~= lo*w_hi + hi*w_lo + hi*w_hi                      (dropped lo*w_lo: 2^-22 relative)
+//
+// Why not cuDNN with the same split (engine precision "tf32x3")?  The tensor core accumulates with
+// TRUNCATION: every 8-deep k-step loses ~2^-24 of the running sum, always towards zero, and over the
+// 4608-deep reductions of this network that is a coherent 1e-4 bias (profiles/r1_precision_modes.txt).
+// Here a reduction is cut into CHAINS of one 32-channel block of one tap: inside a chain the two small
+// correction products are issued first (they truncate against a tiny accumulator) and the main product
+// last (4 k-steps); each finished chain is read back from tensor memory and added to a register
+// accumulator with a rounded fp32 add.  That brings the result to fp32 SIMT accuracy.
+//
+// Structure (one persistent CTA per SM, 384 threads, tiles of 128 rows x BN output channels):
+//   warp 0     TMA producer: per k-block (tap, 32 input channels) four tensor-map loads into a shared-memory
+//              ring — A_hi / A_lo as 3-D boxes (32 ch, Lout, mt cutouts) whose row coordinate is shifted by
+//              the tap, so the convolution's zero padding is the TMA's out-of-bounds fill; W_hi / W_lo as
+//              2-D boxes.  128-byte swizzle, completion on an mbarrier (complete_tx).
+//   warp 1     MMA issuer: 12 x tcgen05.mma.kind::tf32 (M = 128, N = BN, K = 8) per k-block into one of two
+//              tensor-memory accumulators; tcgen05.commit releases the ring slot and signals the chain.
+//   warp 2     tensor-memory allocation (512 columns) and release.
+//   warps 4-11 promotion + epilogue: tcgen05.ld the finished chain, add into registers, hand the TMEM
+//              buffer back; after the last chain: + bias, LeakyReLU, max-pool over row pairs (shuffle),
+//              optional hi/lo split for the next layer, 128-bit stores.
+// Every mbarrier wait is bounded: on a timeout the role records an error code and leaves, so a bug
+// surfaces as a status, never as a hung GPU.
+#include <cuda.h>
+
+#include "pof_common.cuh"
+
+namespace pof {
+namespace {
+
+constexpr int kThreads = 384;
+constexpr int kTileM = 128;
+constexpr int kKBlock = 32;                    // fp32 elements per 128-byte swizzled row
+constexpr int kATile = kTileM * 128;           // bytes of one A operand tile (hi or lo)
+constexpr int kTmemCols = 512;
+constexpr long long kWaitLimit = 2000000000LL; // ~1 s of SM clocks
+
+template <int BN>
+struct Cfg {
+    static constexpr int kBTile = BN * 128;
+    static constexpr int kStage = 2 * kATile + 2 * kBTile;
+    static constexpr int kStages = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
+    static constexpr int kSmem = kStages * kStage + 1024 /* alignment slack */ + 256 /* barriers */;
+    static constexpr int kAcc = BN / 2;        // accumulators per epilogue thread
+};
+
+struct Params {
+    long long Mcut;      // cutouts (outer dimension of A)
+    long long tiles_m;
+    int tiles_n;
+    int Lout;            // output rows per cutout (= box height)
+    int mt;              // cutouts per tile, mt * Lout <= 128
+    int Cin, Cout, taps, pad, pool;
+    float slope;
+    const float* bias;   // [Cout] or null
+    float* out_plain;    // [Mcut * Lout / pool, Cout] or null
+    float* out_split;    // [Mcut * Lout / pool, 2 Cout] = [hi | lo] or null
+    int* status;         // device int, 0 = ok
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait; false = timed out (status written).
+__device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity, int* status, int code) {
+    if (mbar_try(bar, parity)) return true;
+    const long long t0 = clock64();
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 256; ++i)
+            if (mbar_try(bar, parity)) return true;
+        if (clock64() - t0 > kWaitLimit) {
+            atomicCAS(status, 0, code);
+            return false;
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ unsigned long long umma_desc(unsigned addr) {
+    return (unsigned long long)((addr >> 4) & 0x3fffu) | (1ull << 16) /* LBO (unused with swizzle) */ |
+           (64ull << 32) /* SBO = 1024 B */ | (1ull << 46) /* descriptor version (sm_100) */ | (2ull << 61) /* SWIZZLE_128B */;
+}
+// Instruction descriptor: D = fp32, A = B = TF32, both K-major, M = 128, N = bn.
+__device__ __forceinline__ unsigned umma_idesc(int bn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(bn >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long a, unsigned long long b, unsigned idesc, unsigned acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"          // same statement: the registers are valid when it returns
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ float tf32_rn(float x) {
+    unsigned u = __float_as_uint(x);
+    u += 0x0fffu + ((u >> 13) & 1u);
+    return __uint_as_float(u & 0xffffe000u);
+}
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Params p) {
+    using C = Cfg<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    const unsigned base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const unsigned bars = base + C::kStages * C::kStage;       // full[S] | empty[S] | tfull[2] | tempty[2] | tmem ptr
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (C::kStages + s); };
+    auto tfull = [&](int b) { return bars + 8u * (2 * C::kStages + b); };
+    auto tempty = [&](int b) { return bars + 8u * (2 * C::kStages + 2 + b); };
+    const unsigned tmem_slot = bars + 8u * (2 * C::kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb_per_tap = p.Cin / kKBlock;
+    const int n_kb = p.taps * kb_per_tap;
+    const long long n_tiles = p.tiles_m * p.tiles_n;
+    const int rows_tile = p.mt * p.Lout;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull(b), 1); mbar_init(tempty(b), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    unsigned tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == 0 && lane == 0) {
+            // ------------------------------------------------------------------ TMA producer
+            const unsigned tx = 2u * (unsigned)rows_tile * 128u + 2u * (unsigned)C::kBTile;
+            long long it = 0;
+            bool ok = true;
+            for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+                const int nt = (int)(tile % p.tiles_n);
+                const long long m0 = (tile / p.tiles_n) * p.mt;
+                for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                    const int s = (int)(it % C::kStages);
+                    const unsigned ph = (unsigned)((it / C::kStages) & 1);
+                    if (!(ok = mbar_wait(empty(s), ph ^ 1u, p.status, 1))) break;
+                    const int tap = kb / kb_per_tap, c0 = (kb - tap * kb_per_tap) * kKBlock;
+                    const unsigned dst = base + (unsigned)s * C::kStage;
+                    mbar_expect_tx(full(s), tx);
+                    tma_load_3d(dst, &map_a, c0, tap - p.pad, (int)m0, full(s));
+                    tma_load_3d(dst + kATile, &map_a, p.Cin + c0, tap - p.pad, (int)m0, full(s));
+                    tma_load_2d(dst + 2 * kATile, &map_w, c0, (tap * 2 + 0) * p.Cout + nt * BN, full(s));
+                    tma_load_2d(dst + 2 * kATile + C::kBTile, &map_w, c0, (tap * 2 + 1) * p.Cout + nt * BN, full(s));
+                }
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ------------------------------------------------------------------ MMA issuer
+            const unsigned idesc = umma_idesc(BN);
+            long long it = 0;
+            bool ok = true;
+            for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+                for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                    const int s = (int)(it % C::kStages);
+                    const unsigned ph = (unsigned)((it / C::kStages) & 1);
+                    const int buf = (int)(it & 1);
+                    const unsigned bph = (unsigned)((it >> 1) & 1);
+                    if (!(ok = mbar_wait(tempty(buf), bph ^ 1u, p.status, 2))) break;      // chain it-2 promoted
+                    if (!(ok = mbar_wait(full(s), ph, p.status, 3))) break;                // operands landed
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned st = base + (unsigned)s * C::kStage;
+                    const unsigned long long a_hi = umma_desc(st), a_lo = umma_desc(st + kATile);
+                    const unsigned long long b_hi = umma_desc(st + 2 * kATile), b_lo = umma_desc(st + 2 * kATile + C::kBTile);
+                    const unsigned d = tmem_base + (unsigned)(buf * BN);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_tf32(d, a_lo + 2 * k, b_hi + 2 * k, idesc, k > 0);   // corrections first
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_tf32(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_tf32(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);       // main product last
+                    umma_commit(empty(s));
+                    umma_commit(tfull(buf));
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------------- promotion + epilogue
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+        const int e = warp - 4, q = e & 3, h = e >> 2;           // TMEM lane quarter (= warp % 4), column half
+        const int row = q * 32 + lane;
+        const unsigned lane_addr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(h * C::kAcc);
+        long long it = 0;
+        bool ok = true;
+        for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+            float acc[C::kAcc];
+#pragma unroll
+            for (int j = 0; j < C::kAcc; ++j) acc[j] = 0.f;
+            for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                const int buf = (int)(it & 1);
+                const unsigned bph = (unsigned)((it >> 1) & 1);
+                if (!(ok = mbar_wait(tfull(buf), bph, p.status, 4))) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < C::kAcc / 32; ++j) {
+                    unsigned v[32];
+                    tmem_ld32(lane_addr + (unsigned)(buf * BN + j * 32), v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[j * 32 + i] = __fadd_rn(acc[j * 32 + i], __uint_as_float(v[i]));
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty(buf));
+            }
+            if (!ok) break;
+            // epilogue for this tile: registers only, the tensor memory is already back with the MMA warp
+            const int nt = (int)(tile % p.tiles_n);
+            const long long r = (tile / p.tiles_n) * p.mt * p.Lout + row;          // global output row before pooling
+            const bool valid = row < rows_tile && r < p.Mcut * p.Lout && (p.pool == 1 || (lane & 1) == 0);
+            const long long orow = p.pool == 2 ? (r >> 1) : r;
+            const int cbase = nt * BN + h * C::kAcc;
+#pragma unroll
+            for (int j = 0; j < C::kAcc; j += 4) {
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float v = acc[j + i];
+                    if (p.pool == 2) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+                    if (p.bias) v += __ldg(p.bias + cbase + j + i);
+                    o[i] = lrelu(v, p.slope);
+                }
+                if (valid) {
+                    if (p.out_plain)
+                        st_stream_f4(reinterpret_cast<float4*>(p.out_plain + orow * p.Cout + cbase + j), make_float4(o[0], o[1], o[2], o[3]));
+                    if (p.out_split) {
+                        float hi[4], lo[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { hi[i] = tf32_rn(o[i]); lo[i] = tf32_rn(o[i] - hi[i]); }
+                        float* dst = p.out_split + orow * 2 * p.Cout + cbase + j;
+                        st_stream_f4(reinterpret_cast<float4*>(dst), make_float4(hi[0], hi[1], hi[2], hi[3]));
+                        st_stream_f4(reinterpret_cast<float4*>(dst + p.Cout), make_float4(lo[0], lo[1], lo[2], lo[3]));
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+template <int BN>
+int launch(const CUtensorMap& ma, const CUtensorMap& mw, const Params& p, cudaStream_t stream) {
+    using C = Cfg<BN>;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    POF_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        POF_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+        attr_set[dev] = true;
+    }
+    const long long tiles = p.tiles_m * p.tiles_n;
+    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    conv_tc_kernel<BN><<<grid, kThreads, C::kSmem, stream>>>(ma, mw, p);
+    POF_CUDA(cudaGetLastError());
+    return POF_OK;
+}
+
+}  // namespace
+}  // namespace pof
+
+extern "C" {
+
+int pof_conv_tc_fwd(const float* a_split, const float* w_split, const float* bias, long long Mcut, int LA, int Lout, int Cin,
+                    int Cout, int taps, int pad, int pool, float slope, float* out_plain, float* out_split, int* status,
+                    void* stream_) {
+    using namespace pof;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (Mcut == 0) return POF_OK;
+    POF_REQUIRE(a_split && w_split && status && (out_plain || out_split), POF_ERR_NULL_POINTER, "pof_conv_tc_fwd: null pointer");
+    POF_REQUIRE(Mcut > 0 && Mcut < (1ll << 31) && LA >= 1 && Lout >= 1 && Lout <= 128 && LA <= 256, POF_ERR_BAD_SHAPE,
+                "pof_conv_tc_fwd: bad shape Mcut=%lld LA=%d Lout=%d", Mcut, LA, Lout);
+    POF_REQUIRE(Cin >= 32 && Cin % 32 == 0, POF_ERR_BAD_SHAPE, "pof_conv_tc_fwd: Cin must be a multiple of 32 (got %d)", Cin);
+    POF_REQUIRE(Cout == 64 || Cout == 128 || (Cout >= 256 && Cout % 256 == 0), POF_ERR_BAD_SHAPE,
+                "pof_conv_tc_fwd: Cout must be 64, 128 or a multiple of 256 (got %d)", Cout);
+    POF_REQUIRE(taps >= 1 && pad >= 0 && pad < taps, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: bad taps/pad %d/%d", taps, pad);
+    POF_REQUIRE(pool == 1 || (pool == 2 && Lout % 2 == 0), POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: pool must be 1, or 2 with even Lout");
+    const uintptr_t al = reinterpret_cast<uintptr_t>(a_split) | reinterpret_cast<uintptr_t>(w_split) |
+                         reinterpret_cast<uintptr_t>(out_plain) | reinterpret_cast<uintptr_t>(out_split) |
+                         reinterpret_cast<uintptr_t>(bias);
+    POF_REQUIRE((al & 15) == 0, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: tensors must be 16-byte aligned");
+    EncodeTiledFn enc = encode_tiled();
+    POF_REQUIRE(enc != nullptr, POF_ERR_UNSUPPORTED, "pof_conv_tc_fwd: the driver does not export cuTensorMapEncodeTiled");
+
+    const int bn = Cout >= 256 ? 256 : Cout;
+    Params p;
+    p.Mcut = Mcut;
+    p.Lout = Lout;
+    p.mt = kTileM / Lout;
+    p.tiles_m = (Mcut + p.mt - 1) / p.mt;
+    p.tiles_n = Cout / bn;
+    p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.pad = pad; p.pool = pool; p.slope = slope;
+    p.bias = bias; p.out_plain = out_plain; p.out_split = out_split; p.status = status;
+
+    alignas(64) CUtensorMap ma, mw;
+    {   // A: [Mcut][LA][2 Cin] fp32, box (32 channels, Lout rows, mt cutouts); out-of-range rows read as zero
+        const cuuint64_t dims[3] = {(cuuint64_t)(2 * Cin), (cuuint64_t)LA, (cuuint64_t)Mcut};
+        const cuuint64_t strides[2] = {(cuuint64_t)(2 * Cin) * 4, (cuuint64_t)LA * (2 * Cin) * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)kKBlock, (cuuint32_t)Lout, (cuuint32_t)p.mt};
+        const cuuint32_t es[3] = {1, 1, 1};
+        const CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a_split), dims, strides, box, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        POF_REQUIRE(r == CUDA_SUCCESS, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+    }
+    {   // W: [taps][2][Cout][Cin] fp32 seen as a [taps * 2 * Cout, Cin] matrix, box (32 channels, bn rows)
+        const cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)taps * 2 * Cout};
+        const cuuint64_t strides[1] = {(cuuint64_t)Cin * 4};
+        const cuuint32_t box[2] = {(cuuint32_t)kKBlock, (cuuint32_t)bn};
+        const cuuint32_t es[2] = {1, 1};
+        const CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w_split), dims, strides, box, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        POF_REQUIRE(r == CUDA_SUCCESS, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+    }
+    if (bn == 256) return launch<256>(ma, mw, p, stream);
+    if (bn == 128) return launch<128>(ma, mw, p, stream);
+    return launch<64>(ma, mw, p, stream);
+}
+
+}  // extern "C"

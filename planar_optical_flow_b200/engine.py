@@ -14,18 +14,19 @@ disjoint set of sequences with no data-path collective.
 
 Numerics (BatchNorm is folded into the convolutions in eval mode in every mode, which
 re-associates one multiply):
-  * `precision="fp32"`   every convolution in IEEE fp32 on cuDNN's SIMT kernels, NCL layout as in the
-                         reference; ~1e-6 relative to the reference's CPU path.  The strict mode.
-  * `precision="tf32x3"` fp32-ACCURATE convolutions on the TF32 tensor cores: activations and weights
-                         are split x = hi + lo (hi exactly TF32) and each convolution runs once over
-                         [hi | lo | hi] x [w_hi | w_hi | w_lo] with fp32 accumulation, i.e. the three
-                         significant partial products of the fp32 product (the dropped lo*lo term is
-                         2^-22 relative).  Activations are channels-last; libpof's glue kernels
-                         (csrc/pof_backbone.cu) fuse bias + LeakyReLU + max-pool + split into one pass
-                         per layer, and the first layer and the avg-pool/heads/sigmoid tail are theirs too.
-  * `precision="tf32"`   the same channels-last pipeline without the split: plain TF32 (what PyTorch's
-                         defaults give the reference on a GPU, ~1e-3).  Throughput mode, reported
-                         separately.
+  * `precision="fp32"`   (default) fp32-ACCURATE convolutions on the tcgen05 tensor cores
+                         (csrc/pof_conv_tc.cu): operands split x = hi + lo (hi exactly TF32), the three
+                         significant partial products lo*w_hi + hi*w_lo + hi*w_hi accumulated in short
+                         chains that are promoted to fp32 registers with rounded adds.  Per layer 2-4e-7
+                         of the fp64 result - tighter than cuDNN's fp32 SIMT kernels (1e-6).  Channels-last
+                         activations; bias + LeakyReLU + max-pool + split are the kernel's epilogue.
+  * `precision="fp32-simt"`  every convolution in IEEE fp32 on cuDNN's SIMT kernels, NCL layout as in the
+                         reference.  The library baseline of the mode above (5x slower).
+  * `precision="tf32x3"` the same split run through cuDNN's TF32 convolutions ([hi | lo | hi] x
+                         [w_hi | w_hi | w_lo] channels): exact products, but the tensor core accumulates
+                         with truncation over the whole 4608-deep reduction -> 1e-4, not parity.
+  * `precision="tf32"`   plain TF32 on cuDNN, channels-last (what PyTorch's defaults give the reference on
+                         a GPU, ~1e-3).  Throughput mode, reported separately.
 """
 import contextlib
 
@@ -75,8 +76,10 @@ class _ChannelsLastBackbone:
     only dense contraction; everything between them is libpof's fused glue.
     """
 
-    def __init__(self, model, split):
+    def __init__(self, model, split, tc=False):
         self.split = bool(split)
+        self.tc = bool(tc)                  # convolutions on libpof's tcgen05 kernel instead of cuDNN
+        self.parts = 2 if tc else 3
         blocks = [model.conv_block_1, model.conv_block_2, model.conv_block_3, model.conv_block_4]
         folded = [[fold_conv_bn(layer) for layer in blk] for blk in blocks]
         w0, b0 = folded[0][0]
@@ -95,10 +98,20 @@ class _ChannelsLastBackbone:
         hi, lo = split_tf32(w)
         return torch.cat([hi, hi, lo], dim=dim)
 
+    @staticmethod
+    def _tc_weight(w):                                               # [Cout, Cin, taps] -> [taps, 2, Cout, Cin]
+        hi, lo = split_tf32(w)
+        lo, _ = split_tf32(lo)
+        return torch.stack([hi, lo], dim=0).permute(3, 0, 1, 2).contiguous()
+
     def _conv_weight(self, w):                                       # [Cout, Cin, 3] -> [Cout, Ceff, 1, 3] NHWC
+        if self.tc:
+            return self._tc_weight(w)
         return self._cat(w, 1).unsqueeze(2).contiguous(memory_format=torch.channels_last)
 
     def _embed_weight(self, w):                                      # [E, C, L] -> [L * Ceff, E]
+        if self.tc:
+            return self._tc_weight(w)
         return self._cat(w, 1).permute(2, 1, 0).reshape(-1, w.shape[0]).contiguous()
 
     def _conv(self, a, M, L, w4, cout):
@@ -108,36 +121,42 @@ class _ChannelsLastBackbone:
             raise RuntimeError("cuDNN returned a non-channels-last convolution output")
         return y.view(M * L, cout)
 
-    def _act(self, y, bias, pool, plain=False):
-        """-> (plain or None, operand for the next convolution)."""
-        p, s = ops.act(y, bias, pool=pool, slope=_SLOPE, want_plain=plain or not self.split, want_split=self.split)
+    def _layer(self, a, M, L, w, b, cout, pool, plain=False):
+        """One conv + bias + LeakyReLU (+ max-pool) layer -> (plain or None, operand for the next convolution)."""
+        if self.tc:
+            return ops.conv_tc(a, w, b, M, L, L, 3, 1, pool=pool, slope=_SLOPE, want_plain=plain, want_split=True)
+        y = self._conv(a, M, L, w, cout)
+        p, s = ops.act(y, b, pool=pool, slope=_SLOPE, want_plain=plain or not self.split, want_split=self.split)
         return p, (s if self.split else p)
 
     def operand(self, plain_rows):
         """The convolution operand of already-activated rows (the attention memory)."""
         if not self.split:
             return plain_rows
-        return ops.act(plain_rows, None, pool=1, slope=1.0, want_plain=False, want_split=True)[1]
+        return ops.act(plain_rows, None, pool=1, slope=1.0, want_plain=False, want_split=True, parts=self.parts)[1]
 
     def features(self, cutouts):
         """cutouts [M, P] -> (features [M * P/4, 256] plain, the same rows as a convolution operand)."""
         M, L = cutouts.shape
         p, s = ops.conv_first(cutouts, self.w_first, self.b_first, slope=_SLOPE, want_plain=not self.split,
-                              want_split=self.split)
+                              want_split=self.split, parts=self.parts)
         a = s if self.split else p
         plain = None
         for bi in (0, 1):
             todo = self.layers[bi][1:] if bi == 0 else self.layers[bi]
             for k, (w4, b, cout) in enumerate(todo):
-                y = self._conv(a, M, L, w4, cout)
                 last = k == len(todo) - 1
-                plain, a = self._act(y, b, 2 if last else 1, plain=last and bi == 1)
+                plain, a = self._layer(a, M, L, w4, b, cout, 2 if last else 1, plain=last and bi == 1)
                 if last:
                     L //= 2
         return plain, a
 
     def embed(self, operand, M):
         """Gate embedding (Conv1d k = L, no padding == one GEMM over whole rows) + BN + LeakyReLU."""
+        if self.tc:
+            L = self.emb_w.shape[0]
+            return ops.conv_tc(operand, self.emb_w, self.emb_b, M, L, 1, L, 0, pool=1, slope=_SLOPE, want_plain=True,
+                               want_split=False)[0]
         return F.leaky_relu_(torch.addmm(self.emb_b, operand.view(M, -1), self.emb_w), _SLOPE)
 
     def votes(self, operand, M, L):
@@ -145,11 +164,14 @@ class _ChannelsLastBackbone:
         a = operand
         for bi in (2, 3):
             for k, (w4, b, cout) in enumerate(self.layers[bi]):
-                y = self._conv(a, M, L, w4, cout)
-                if bi == 3 and k == len(self.layers[bi]) - 1:
-                    return ops.head(y, b, M, L, self.w_head, self.b_head, n_sigmoid=self.n_cls, slope=_SLOPE)
                 last = k == len(self.layers[bi]) - 1
-                _, a = self._act(y, b, 2 if last else 1)
+                if bi == 3 and last:
+                    if self.tc:         # bias + LeakyReLU already applied by the convolution's epilogue
+                        y = ops.conv_tc(a, w4, b, M, L, L, 3, 1, pool=1, slope=_SLOPE, want_plain=True, want_split=False)[0]
+                        return ops.head(y, None, M, L, self.w_head, self.b_head, n_sigmoid=self.n_cls, slope=1.0)
+                    y = self._conv(a, M, L, w4, cout)
+                    return ops.head(y, b, M, L, self.w_head, self.b_head, n_sigmoid=self.n_cls, slope=_SLOPE)
+                _, a = self._layer(a, M, L, w4, b, cout, 2 if last else 1)
                 if last:
                     L //= 2
 
@@ -166,8 +188,8 @@ class StreamingDetector:
                  min_dist=0.5, seq_chunk=None, record_events=False):
         if not torch.cuda.is_available():
             raise RuntimeError("StreamingDetector needs a CUDA device; there is no CPU path")
-        if precision not in ("fp32", "tf32x3", "tf32"):
-            raise ValueError("precision must be 'fp32', 'tf32x3' or 'tf32'")
+        if precision not in ("fp32", "fp32-simt", "tf32x3", "tf32"):
+            raise ValueError("precision must be 'fp32', 'fp32-simt', 'tf32x3' or 'tf32'")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.precision = precision
         self.cutout_kwargs = dict(cutout_kwargs)
@@ -183,12 +205,12 @@ class StreamingDetector:
         model = model.to(self.device).eval()
         self.alpha = float(model.gate._alpha)
         self.window = int(model.gate.window)
-        self.channels_last = precision != "fp32"
+        self.channels_last = precision != "fp32-simt"
         with torch.no_grad():
             if self.channels_last:
                 if self.P % 4:
                     raise ValueError("the channels-last pipeline needs num_cutout_pts to be a multiple of 4")
-                self.net = _ChannelsLastBackbone(model, split=precision == "tf32x3")
+                self.net = _ChannelsLastBackbone(model, split=precision != "tf32", tc=precision == "fp32")
             self.block1 = _FoldedStack(model.conv_block_1, 1)
             self.block2 = _FoldedStack(model.conv_block_2, 1)
             self.block3 = _FoldedStack(model.conv_block_3, 1)
@@ -241,7 +263,7 @@ class StreamingDetector:
     @contextlib.contextmanager
     def _precision(self):
         old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
-        allow = self.precision != "fp32"
+        allow = self.precision in ("tf32x3", "tf32")
         torch.backends.cudnn.allow_tf32 = allow
         torch.backends.cuda.matmul.allow_tf32 = allow
         try:
@@ -284,10 +306,12 @@ class StreamingDetector:
             t_op = self.net.operand(nxt[b0:b1].view(M * L, -1))
             # the embedding of the NEW memory is what the next step's gate needs (dr_spaam.py:180-181)
             self.emb_memory[b0:b1] = self.net.embed(t_op, M).view(nb, N, -1)
-            self.kernel_launches += 1 if self.net.split else 0
+            self.kernel_launches += (1 if self.net.split else 0) + (1 if self.net.tc else 0)
         feat_fused[b0:b1] = ff
         v = self.net.votes(t_op, M, L).view(nb, N, -1)
-        self.kernel_launches += 12       # first layer + 9 activation passes + head + gate
+        # cuDNN modes: first layer + 9 activation passes + head + gate; tcgen05 mode: first layer + 10 convolutions
+        # + embedding + head + gate
+        self.kernel_launches += 14 if self.net.tc else 12
         pred_cls[b0:b1] = v[:, :, 0]
         pred_reg[b0:b1] = v[:, :, 1:]
 
@@ -351,6 +375,12 @@ class StreamingDetector:
         res.update(pred_cls=pred_cls, pred_reg=pred_reg, feat_fused=feat_fused)
         self._last = res
         return res
+
+    def check(self):
+        """Synchronise and raise if a tcgen05 pipeline wait timed out on the device (results would be invalid)."""
+        code = ops.conv_tc_status(self.device)
+        if code:
+            raise RuntimeError("pof_conv_tc_fwd reported pipeline status %d on %s" % (code, self.device))
 
     @property
     def template(self):

@@ -141,22 +141,23 @@ def gate(x, tmpl, emb_x, emb_t, alpha, window):
 
 
 # --------------------------------------------------------------------------- backbone glue
-def act(y, bias=None, pool=1, slope=0.1, want_plain=True, want_split=False):
+def act(y, bias=None, pool=1, slope=0.1, want_plain=True, want_split=False, parts=3):
     """Channels-last activations y [rows, C] -> (+bias) LeakyReLU, max over `pool` consecutive rows.
 
-    Returns (plain [rows/pool, C] or None, split [rows/pool, 3C] = [hi | lo | hi] or None)."""
+    Returns (plain [rows/pool, C] or None, split [rows/pool, parts*C] or None); parts = 3: [hi | lo | hi]
+    (cuDNN operand), parts = 2: [hi | lo] (operand of `conv_tc`)."""
     require_cuda_tensor(y, "y", torch.float32)
     rows, C = y.shape
     dev = y.device
     with torch.cuda.device(dev):
         plain = torch.empty((rows // pool, C), dtype=torch.float32, device=dev) if want_plain else None
-        split = torch.empty((rows // pool, 3 * C), dtype=torch.float32, device=dev) if want_split else None
+        split = torch.empty((rows // pool, parts * C), dtype=torch.float32, device=dev) if want_split else None
         check(_lib.lib().pof_act_fwd(_ptr(y), _ptr(bias), rows, C, int(pool), float(slope), _ptr(plain), _ptr(split),
-                                     current_stream_ptr(dev)), "pof_act_fwd")
+                                     int(parts), current_stream_ptr(dev)), "pof_act_fwd")
     return plain, split
 
 
-def conv_first(cutouts, weight, bias, slope=0.1, want_plain=False, want_split=True):
+def conv_first(cutouts, weight, bias, slope=0.1, want_plain=False, want_split=True, parts=3):
     """cutouts [M, P], weight [C, 3], bias [C] -> first conv layer + LeakyReLU, channels-last [M*P, C] / [M*P, 3C]."""
     require_cuda_tensor(cutouts, "cutouts", torch.float32)
     require_cuda_tensor(weight, "weight", torch.float32)
@@ -166,9 +167,45 @@ def conv_first(cutouts, weight, bias, slope=0.1, want_plain=False, want_split=Tr
     dev = cutouts.device
     with torch.cuda.device(dev):
         plain = torch.empty((M * P, C), dtype=torch.float32, device=dev) if want_plain else None
-        split = torch.empty((M * P, 3 * C), dtype=torch.float32, device=dev) if want_split else None
+        split = torch.empty((M * P, parts * C), dtype=torch.float32, device=dev) if want_split else None
         check(_lib.lib().pof_conv_first_fwd(_ptr(cutouts), _ptr(weight), _ptr(bias), M, P, C, float(slope), _ptr(plain),
-                                            _ptr(split), current_stream_ptr(dev)), "pof_conv_first_fwd")
+                                            _ptr(split), int(parts), current_stream_ptr(dev)), "pof_conv_first_fwd")
+    return plain, split
+
+
+_conv_tc_status = {}
+
+
+def conv_tc_status(device):
+    """The device-side status word of `conv_tc` launches on `device` (0 = every pipeline wait completed)."""
+    t = _conv_tc_status.get(torch.device(device))
+    return 0 if t is None else int(t.item())
+
+
+def conv_tc(a_split, w_split, bias, Mcut, LA, Lout, taps, pad, pool=1, slope=0.1, want_plain=False, want_split=True):
+    """fp32-accurate convolution / whole-row GEMM on tcgen05 (csrc/pof_conv_tc.cu).
+
+    a_split [Mcut*LA, 2*Cin] = [hi | lo] rows, w_split [taps, 2, Cout, Cin]  ->
+    (plain [Mcut*Lout/pool, Cout] or None, split [.., 2*Cout] or None)."""
+    require_cuda_tensor(a_split, "a_split", torch.float32)
+    require_cuda_tensor(w_split, "w_split", torch.float32)
+    Cin = a_split.shape[-1] // 2
+    if w_split.dim() != 4 or w_split.shape[0] != taps or w_split.shape[1] != 2 or w_split.shape[3] != Cin:
+        raise ValueError("w_split must be [taps, 2, Cout, Cin] (got %s for Cin = %d)" % (tuple(w_split.shape), Cin))
+    if a_split.numel() != Mcut * LA * 2 * Cin:
+        raise ValueError("a_split has %d elements, expected %d x %d x %d" % (a_split.numel(), Mcut, LA, 2 * Cin))
+    Cout = w_split.shape[2]
+    dev = a_split.device
+    with torch.cuda.device(dev):
+        status = _conv_tc_status.get(dev)
+        if status is None:
+            status = _conv_tc_status[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+        rows = Mcut * Lout // pool
+        plain = torch.empty((rows, Cout), dtype=torch.float32, device=dev) if want_plain else None
+        split = torch.empty((rows, 2 * Cout), dtype=torch.float32, device=dev) if want_split else None
+        check(_lib.lib().pof_conv_tc_fwd(_ptr(a_split), _ptr(w_split), _ptr(bias), Mcut, int(LA), int(Lout), Cin, Cout,
+                                         int(taps), int(pad), int(pool), float(slope), _ptr(plain), _ptr(split),
+                                         _ptr(status), current_stream_ptr(dev)), "pof_conv_tc_fwd")
     return plain, split
 
 

@@ -23,31 +23,47 @@ def _tf32_round(x):
     return hi
 
 
-def _emit(v, want_plain, want_split):
+def _emit(v, want_plain, want_split, parts=3):
     split = None
     if want_split:
         hi = _tf32_round(v)
-        split = torch.cat([hi, v - hi, hi], dim=1)
+        split = torch.cat([hi, v - hi, hi], dim=1) if parts == 3 else torch.cat([hi, _tf32_round(v - hi)], dim=1)
     return (v if want_plain else None), split
 
 
-def fake_act(y, bias=None, pool=1, slope=0.1, want_plain=True, want_split=False):
+def fake_act(y, bias=None, pool=1, slope=0.1, want_plain=True, want_split=False, parts=3):
     rows, C = y.shape
     v = y.view(rows // pool, pool, C).max(dim=1).values
     if bias is not None:
         v = v + bias
     v = torch.where(v > 0, v, v * slope)
-    return _emit(v, want_plain, want_split)
+    return _emit(v, want_plain, want_split, parts)
 
 
-def fake_conv_first(cutouts, weight, bias, slope=0.1, want_plain=False, want_split=True):
+def fake_conv_first(cutouts, weight, bias, slope=0.1, want_plain=False, want_split=True, parts=3):
     M, P = cutouts.shape
     v = F.conv1d(cutouts.view(M, 1, P), weight.view(-1, 1, 3), bias, padding=1)        # [M, C, P]
     v = F.leaky_relu(v, slope).permute(0, 2, 1).reshape(M * P, -1)
-    return _emit(v, want_plain, want_split)
+    return _emit(v, want_plain, want_split, parts)
+
+
+def fake_conv_tc(a_split, w_split, bias, Mcut, LA, Lout, taps, pad, pool=1, slope=0.1, want_plain=False, want_split=True):
+    """The definition pof_conv_tc_fwd implements, with the three split products in plain fp32."""
+    cin = a_split.shape[1] // 2
+    hi, lo = a_split[:, :cin].view(Mcut, LA, cin).permute(0, 2, 1), a_split[:, cin:].view(Mcut, LA, cin).permute(0, 2, 1)
+    w_hi, w_lo = w_split[:, 0].permute(1, 2, 0), w_split[:, 1].permute(1, 2, 0)          # [Cout, Cin, taps]
+    y = F.conv1d(lo, w_hi, None, padding=pad) + F.conv1d(hi, w_lo, None, padding=pad) + F.conv1d(hi, w_hi, None, padding=pad)
+    if bias is not None:
+        y = y + bias[None, :, None]
+    if pool == 2:
+        y = F.max_pool1d(y, 2)
+    y = torch.where(y > 0, y, y * slope).permute(0, 2, 1).reshape(Mcut * Lout // pool, -1)
+    return _emit(y, want_plain, want_split, 2)
 
 
 def fake_head(y, bias, M, L, w_head, b_head, n_sigmoid, slope=0.1):
+    if bias is None:
+        bias = torch.zeros(y.shape[1])
     v = F.leaky_relu(y + bias, slope).view(M, L, -1).mean(dim=1)
     out = v @ w_head.t() + b_head
     out[:, :n_sigmoid] = torch.sigmoid(out[:, :n_sigmoid])
@@ -59,6 +75,7 @@ def cpu_glue(monkeypatch):
     monkeypatch.setattr(ops, "act", fake_act)
     monkeypatch.setattr(ops, "conv_first", fake_conv_first)
     monkeypatch.setattr(ops, "head", fake_head)
+    monkeypatch.setattr(ops, "conv_tc", fake_conv_tc)
 
 
 def test_split_tf32_is_exact_and_tf32_representable():
@@ -70,14 +87,14 @@ def test_split_tf32_is_exact_and_tf32_representable():
     assert float((lo.abs() / w.abs()).max()) <= 2.0 ** -11
 
 
-@pytest.mark.parametrize("split", [False, True])
-def test_channels_last_backbone_matches_oracle(cpu_glue, split):
+@pytest.mark.parametrize("split,tc", [(False, False), (True, False), (True, True)])
+def test_channels_last_backbone_matches_oracle(cpu_glue, split, tc):
     sd = omodel.randomize_bn_stats(omodel.init_state_dict(56, True, seed=5))
     m = SpatialDROW(num_scans=10, num_pts=56, alpha=0.5, window_size=11, pedestrian_only=True)
     m.load_state_dict(sd, strict=True)
     m.eval()
     with torch.no_grad():
-        net = engine._ChannelsLastBackbone(m, split=split)
+        net = engine._ChannelsLastBackbone(m, split=split, tc=tc)
         b, n = 2, 9
         torch.manual_seed(1)
         cut = torch.randn(b, n, 56).clamp(-1, 1)
