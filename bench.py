@@ -301,7 +301,7 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": world * B * K / (ms_dev / 1e3), "unit": "scans/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "f32 (3xTF32 split products on tcgen05, chains promoted to fp32 registers; 2-4e-7 per layer vs fp64)",
+        "vs_baseline": None, "dtype": {"fp32": "f32 (3xTF32 split products on tcgen05, 64-channel chains promoted to fp32 registers; 5-7e-7 per layer vs fp64, cuDNN fp32: 1-2e-6)",
                                       "fp32-simt": "f32", "tf32x3": "f32 operands, TF32 tensor-core accumulation (1e-4)",
                                       "tf32": "tf32"}[args.precision], "data": "synthetic",
         "impl": "ours",

@@ -212,13 +212,16 @@ POF_API int pof_head_fwd(const float* y, const float* bias, long long M, int L, 
  *                        Conv1d(k=3,p=1): Lout = LA, taps = 3, pad = 1.  Gate embedding (dr_spaam.py:130-133,
  *                        Conv1d(k=LA)): Lout = 1, taps = LA, pad = 0.  Epilogue: + bias, LeakyReLU(slope),
  *                        max over `pool` consecutive rows, -> out_plain [Mcut*Lout/pool, Cout] and/or
- *                        out_split [.., 2 Cout].  Cin % 32 == 0; Cout in {64, 128, 256 k}.
+ *                        out_split [.., 2 Cout].  Cin % 16 == 0; Cout in {64, 128, 256 k}.
  *                        `status` is a device int the caller zeroes: non-zero after the launch means an
- *                        internal pipeline wait timed out (results invalid).                              */
+ *                        internal pipeline wait timed out (results invalid).
+ *                        `chain_channels`: input channels (of one tap) accumulated inside the tensor core
+ *                        before the partial sum is promoted to an fp32 register accumulator; 0 = default (64),
+ *                        multiples of 16.  Longer chains are faster and less accurate (tuning and tests).          */
 POF_API int pof_conv_tc_fwd(const float* a_split, const float* w_split, const float* bias,
                             long long Mcut, int LA, int Lout, int Cin, int Cout, int taps, int pad,
                             int pool, float slope, float* out_plain, float* out_split,
-                            int* status, void* stream);
+                            int* status, int chain_channels, void* stream);
 
 #ifdef __cplusplus
 }

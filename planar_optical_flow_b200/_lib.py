@@ -42,7 +42,7 @@ SIGNATURES = {
     "pof_conv_first_fwd": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_float,
                                    c_void_p, c_void_p, c_int, c_void_p]),
     "pof_conv_tc_fwd": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_int,
-                                c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pof_head_fwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_int,
                              c_void_p, c_void_p]),
     "pof_nms_ws_bytes": (c_size_t, [c_int, c_int]),

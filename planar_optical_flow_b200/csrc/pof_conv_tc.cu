@@ -14,17 +14,20 @@
 // Why not cuDNN with the same split (engine precision "tf32x3")?  The tensor core accumulates with
 // TRUNCATION: every 8-deep k-step loses ~2^-24 of the running sum, always towards zero, and over the
 // 4608-deep reductions of this network that is a coherent 1e-4 bias (profiles/r1_precision_modes.txt).
-// Here a reduction is cut into CHAINS of one 32-channel block of one tap: inside a chain the two small
-// correction products are issued first (they truncate against a tiny accumulator) and the main product
-// last (4 k-steps); each finished chain is read back from tensor memory and added to a register
-// accumulator with a rounded fp32 add.  That brings the result to fp32 SIMT accuracy.
+// Here a reduction is cut into CHAINS of 64 channels of one tap (four 16-channel k-blocks): inside a
+// k-block the two small correction products are issued before the main product, and each finished chain
+// is read back from tensor memory and added to a register accumulator with a rounded fp32 add.  Measured
+// against fp64 (profiles/r1_conv_tc_layers_v3.txt): 5-7e-7 per layer with 64-channel chains, 3e-7 with 32,
+// against 1-2e-6 for cuDNN's fp32 SIMT kernels on the same layers.
 //
 // Structure (one persistent CTA per SM, 384 threads, tiles of 128 rows x BN output channels):
-//   warp 0     TMA producer: per k-block (tap, 32 input channels) four tensor-map loads into a shared-memory
-//              ring — A_hi / A_lo as 3-D boxes (32 ch, Lout, mt cutouts) whose row coordinate is shifted by
+//   warp 0     TMA producer: per k-block (tap, 16 input channels) four tensor-map loads into a shared-memory
+//              ring — A_hi / A_lo as 3-D boxes (16 ch, Lout, mt cutouts) whose row coordinate is shifted by
 //              the tap, so the convolution's zero padding is the TMA's out-of-bounds fill; W_hi / W_lo as
-//              2-D boxes.  128-byte swizzle, completion on an mbarrier (complete_tx).
-//   warp 1     MMA issuer: 12 x tcgen05.mma.kind::tf32 (M = 128, N = BN, K = 8) per k-block into one of two
+//              2-D boxes.  64-byte swizzle, completion on an mbarrier (complete_tx).  The k-block is small
+//              (48 KB at BN = 256) so that FOUR of them fit: the kernel is bound by the latency of these
+//              loads, not by their bandwidth (ncu: L2->SM at 31 %), and depth is what hides it.
+//   warp 1     MMA issuer: 6 x tcgen05.mma.kind::tf32 (M = 128, N = BN, K = 8) per k-block into one of two
 //              tensor-memory accumulators; tcgen05.commit releases the ring slot and signals the chain.
 //   warp 2     tensor-memory allocation (512 columns) and release.
 //   warps 4-11 promotion + epilogue: tcgen05.ld the finished chain, add into registers, hand the TMEM
@@ -41,16 +44,17 @@ namespace {
 
 constexpr int kThreads = 384;
 constexpr int kTileM = 128;
-constexpr int kKBlock = 32;                    // fp32 elements per 128-byte swizzled row
-constexpr int kATile = kTileM * 128;           // bytes of one A operand tile (hi or lo)
+constexpr int kKBlock = 16;                    // fp32 elements per 64-byte swizzled row
+constexpr int kRowBytes = kKBlock * 4;
+constexpr int kATile = kTileM * kRowBytes;     // bytes of one A operand tile (hi or lo)
 constexpr int kTmemCols = 512;
 constexpr long long kWaitLimit = 2000000000LL; // ~1 s of SM clocks
 
 template <int BN>
 struct Cfg {
-    static constexpr int kBTile = BN * 128;
+    static constexpr int kBTile = BN * kRowBytes;
     static constexpr int kStage = 2 * kATile + 2 * kBTile;
-    static constexpr int kStages = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
+    static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
     static constexpr int kSmem = kStages * kStage + 1024 /* alignment slack */ + 256 /* barriers */;
     static constexpr int kAcc = BN / 2;        // accumulators per epilogue thread
 };
@@ -62,6 +66,7 @@ struct Params {
     int Lout;            // output rows per cutout (= box height)
     int mt;              // cutouts per tile, mt * Lout <= 128
     int Cin, Cout, taps, pad, pool;
+    int chain;           // k-blocks accumulated in tensor memory before a promotion to registers
     float slope;
     const float* bias;   // [Cout] or null
     float* out_plain;    // [Mcut * Lout / pool, Cout] or null
@@ -118,10 +123,11 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
         : "memory");
 }
 
-// Shared-memory matrix descriptor, K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart.
+// Shared-memory matrix descriptor, K-major, 64-byte swizzle: rows of 64 B, 8-row groups 512 B apart.
 __device__ __forceinline__ unsigned long long umma_desc(unsigned addr) {
     return (unsigned long long)((addr >> 4) & 0x3fffu) | (1ull << 16) /* LBO (unused with swizzle) */ |
-           (64ull << 32) /* SBO = 1024 B */ | (1ull << 46) /* descriptor version (sm_100) */ | (2ull << 61) /* SWIZZLE_128B */;
+           ((unsigned long long)(8 * kRowBytes >> 4) << 32) /* SBO */ | (1ull << 46) /* descriptor version (sm_100) */ |
+           (4ull << 61) /* SWIZZLE_64B */;
 }
 // Instruction descriptor: D = fp32, A = B = TF32, both K-major, M = 128, N = bn.
 __device__ __forceinline__ unsigned umma_idesc(int bn) {
@@ -148,6 +154,25 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&v)[32]) {
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
           "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld64(unsigned taddr, unsigned (&v)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]),
+          "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]),
+          "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]),
+          "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]),
+          "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
         : "r"(taddr)
         : "memory");
 }
@@ -196,7 +221,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 0 && lane == 0) {
             // ------------------------------------------------------------------ TMA producer
-            const unsigned tx = 2u * (unsigned)rows_tile * 128u + 2u * (unsigned)C::kBTile;
+            const unsigned tx = 2u * (unsigned)rows_tile * kRowBytes + 2u * (unsigned)C::kBTile;
             long long it = 0;
             bool ok = true;
             for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
@@ -218,29 +243,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         } else if (warp == 1 && lane == 0) {
             // ------------------------------------------------------------------ MMA issuer
             const unsigned idesc = umma_idesc(BN);
-            long long it = 0;
+            long long it = 0, ic = 0;                                  // k-blocks, chains issued so far
             bool ok = true;
             for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
                     const int s = (int)(it % C::kStages);
                     const unsigned ph = (unsigned)((it / C::kStages) & 1);
-                    const int buf = (int)(it & 1);
-                    const unsigned bph = (unsigned)((it >> 1) & 1);
-                    if (!(ok = mbar_wait(tempty(buf), bph ^ 1u, p.status, 2))) break;      // chain it-2 promoted
+                    const int buf = (int)(ic & 1);
+                    const bool first = kb % p.chain == 0, last = (kb + 1) % p.chain == 0 || kb + 1 == n_kb;
+                    if (first && !(ok = mbar_wait(tempty(buf), (unsigned)((ic >> 1) & 1) ^ 1u, p.status, 2))) break;   // chain ic-2 promoted
                     if (!(ok = mbar_wait(full(s), ph, p.status, 3))) break;                // operands landed
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const unsigned st = base + (unsigned)s * C::kStage;
                     const unsigned long long a_hi = umma_desc(st), a_lo = umma_desc(st + kATile);
                     const unsigned long long b_hi = umma_desc(st + 2 * kATile), b_lo = umma_desc(st + 2 * kATile + C::kBTile);
                     const unsigned d = tmem_base + (unsigned)(buf * BN);
+                    constexpr int kSteps = kKBlock / 8;                                    // K = 8 per tf32 MMA = 32 B of the row
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_tf32(d, a_lo + 2 * k, b_hi + 2 * k, idesc, k > 0);   // corrections first
+                    for (int k = 0; k < kSteps; ++k) umma_tf32(d, a_lo + 2 * k, b_hi + 2 * k, idesc, k > 0 || !first);   // corrections first
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_tf32(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+                    for (int k = 0; k < kSteps; ++k) umma_tf32(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_tf32(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);       // main product last
+                    for (int k = 0; k < kSteps; ++k) umma_tf32(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);       // main product last
                     umma_commit(empty(s));
-                    umma_commit(tfull(buf));
+                    if (last) { umma_commit(tfull(buf)); ++ic; }
                 }
             }
         }
@@ -256,17 +282,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float acc[C::kAcc];
 #pragma unroll
             for (int j = 0; j < C::kAcc; ++j) acc[j] = 0.f;
-            for (int kb = 0; kb < n_kb; ++kb, ++it) {
+            const int n_chains = (n_kb + p.chain - 1) / p.chain;
+            for (int ch = 0; ch < n_chains; ++ch, ++it) {
                 const int buf = (int)(it & 1);
                 const unsigned bph = (unsigned)((it >> 1) & 1);
                 if (!(ok = mbar_wait(tfull(buf), bph, p.status, 4))) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if constexpr (C::kAcc >= 64) {
 #pragma unroll
-                for (int j = 0; j < C::kAcc / 32; ++j) {
+                    for (int j = 0; j < C::kAcc / 64; ++j) {
+                        unsigned v[64];
+                        tmem_ld64(lane_addr + (unsigned)(buf * BN + j * 64), v);
+#pragma unroll
+                        for (int i = 0; i < 64; ++i) acc[j * 64 + i] = __fadd_rn(acc[j * 64 + i], __uint_as_float(v[i]));
+                    }
+                } else {
                     unsigned v[32];
-                    tmem_ld32(lane_addr + (unsigned)(buf * BN + j * 32), v);
+                    tmem_ld32(lane_addr + (unsigned)(buf * BN), v);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[j * 32 + i] = __fadd_rn(acc[j * 32 + i], __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; ++i) acc[i] = __fadd_rn(acc[i], __uint_as_float(v[i]));
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
@@ -353,14 +387,17 @@ extern "C" {
 
 int pof_conv_tc_fwd(const float* a_split, const float* w_split, const float* bias, long long Mcut, int LA, int Lout, int Cin,
                     int Cout, int taps, int pad, int pool, float slope, float* out_plain, float* out_split, int* status,
-                    void* stream_) {
+                    int chain_channels, void* stream_) {
     using namespace pof;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (Mcut == 0) return POF_OK;
     POF_REQUIRE(a_split && w_split && status && (out_plain || out_split), POF_ERR_NULL_POINTER, "pof_conv_tc_fwd: null pointer");
     POF_REQUIRE(Mcut > 0 && Mcut < (1ll << 31) && LA >= 1 && Lout >= 1 && Lout <= 128 && LA <= 256, POF_ERR_BAD_SHAPE,
                 "pof_conv_tc_fwd: bad shape Mcut=%lld LA=%d Lout=%d", Mcut, LA, Lout);
-    POF_REQUIRE(Cin >= 32 && Cin % 32 == 0, POF_ERR_BAD_SHAPE, "pof_conv_tc_fwd: Cin must be a multiple of 32 (got %d)", Cin);
+    POF_REQUIRE(Cin >= kKBlock && Cin % kKBlock == 0, POF_ERR_BAD_SHAPE, "pof_conv_tc_fwd: Cin must be a multiple of %d (got %d)", kKBlock, Cin);
+    if (chain_channels == 0) chain_channels = 64;
+    POF_REQUIRE(chain_channels > 0 && chain_channels % kKBlock == 0, POF_ERR_BAD_PARAM,
+                "pof_conv_tc_fwd: chain_channels must be a multiple of %d (got %d)", kKBlock, chain_channels);
     POF_REQUIRE(Cout == 64 || Cout == 128 || (Cout >= 256 && Cout % 256 == 0), POF_ERR_BAD_SHAPE,
                 "pof_conv_tc_fwd: Cout must be 64, 128 or a multiple of 256 (got %d)", Cout);
     POF_REQUIRE(taps >= 1 && pad >= 0 && pad < taps, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: bad taps/pad %d/%d", taps, pad);
@@ -380,26 +417,27 @@ int pof_conv_tc_fwd(const float* a_split, const float* w_split, const float* bia
     p.tiles_m = (Mcut + p.mt - 1) / p.mt;
     p.tiles_n = Cout / bn;
     p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.pad = pad; p.pool = pool; p.slope = slope;
+    p.chain = chain_channels / kKBlock;
     p.bias = bias; p.out_plain = out_plain; p.out_split = out_split; p.status = status;
 
     alignas(64) CUtensorMap ma, mw;
-    {   // A: [Mcut][LA][2 Cin] fp32, box (32 channels, Lout rows, mt cutouts); out-of-range rows read as zero
+    {   // A: [Mcut][LA][2 Cin] fp32, box (16 channels, Lout rows, mt cutouts); out-of-range rows read as zero
         const cuuint64_t dims[3] = {(cuuint64_t)(2 * Cin), (cuuint64_t)LA, (cuuint64_t)Mcut};
         const cuuint64_t strides[2] = {(cuuint64_t)(2 * Cin) * 4, (cuuint64_t)LA * (2 * Cin) * 4};
         const cuuint32_t box[3] = {(cuuint32_t)kKBlock, (cuuint32_t)Lout, (cuuint32_t)p.mt};
         const cuuint32_t es[3] = {1, 1, 1};
         const CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a_split), dims, strides, box, es,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         POF_REQUIRE(r == CUDA_SUCCESS, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
     }
-    {   // W: [taps][2][Cout][Cin] fp32 seen as a [taps * 2 * Cout, Cin] matrix, box (32 channels, bn rows)
+    {   // W: [taps][2][Cout][Cin] fp32 seen as a [taps * 2 * Cout, Cin] matrix, box (16 channels, bn rows)
         const cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)taps * 2 * Cout};
         const cuuint64_t strides[1] = {(cuuint64_t)Cin * 4};
         const cuuint32_t box[2] = {(cuuint32_t)kKBlock, (cuuint32_t)bn};
         const cuuint32_t es[2] = {1, 1};
         const CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w_split), dims, strides, box, es,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         POF_REQUIRE(r == CUDA_SUCCESS, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
     }

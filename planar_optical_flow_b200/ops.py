@@ -182,7 +182,7 @@ def conv_tc_status(device):
     return 0 if t is None else int(t.item())
 
 
-def conv_tc(a_split, w_split, bias, Mcut, LA, Lout, taps, pad, pool=1, slope=0.1, want_plain=False, want_split=True):
+def conv_tc(a_split, w_split, bias, Mcut, LA, Lout, taps, pad, pool=1, slope=0.1, want_plain=False, want_split=True, chain_channels=0):
     """fp32-accurate convolution / whole-row GEMM on tcgen05 (csrc/pof_conv_tc.cu).
 
     a_split [Mcut*LA, 2*Cin] = [hi | lo] rows, w_split [taps, 2, Cout, Cin]  ->
@@ -205,7 +205,7 @@ def conv_tc(a_split, w_split, bias, Mcut, LA, Lout, taps, pad, pool=1, slope=0.1
         split = torch.empty((rows, 2 * Cout), dtype=torch.float32, device=dev) if want_split else None
         check(_lib.lib().pof_conv_tc_fwd(_ptr(a_split), _ptr(w_split), _ptr(bias), Mcut, int(LA), int(Lout), Cin, Cout,
                                          int(taps), int(pad), int(pool), float(slope), _ptr(plain), _ptr(split),
-                                         _ptr(status), current_stream_ptr(dev)), "pof_conv_tc_fwd")
+                                         _ptr(status), int(chain_channels), current_stream_ptr(dev)), "pof_conv_tc_fwd")
     return plain, split
 
 

@@ -30,7 +30,7 @@ def reference(x, w, b, pad, pool, slope):
     return y.permute(0, 2, 1).reshape(-1, w.shape[0])
 
 
-def run(M, LA, Cin, Cout, taps, pad, pool, seed=0, time_it=False):
+def run(M, LA, Cin, Cout, taps, pad, pool, seed=0, time_it=False, flags=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     x = (torch.randn(M, LA, Cin, generator=g).abs() * torch.rand(M, LA, Cin, generator=g)).to(dev)
     x = torch.where(torch.rand(M, LA, Cin, generator=g).to(dev) < 0.3, -0.1 * x, x)        # LeakyReLU-like
@@ -39,7 +39,7 @@ def run(M, LA, Cin, Cout, taps, pad, pool, seed=0, time_it=False):
     Lout = LA if pad else LA - taps + 1
     _, a = ops.act(x.view(M * LA, Cin), None, pool=1, slope=1.0, want_plain=False, want_split=True, parts=2)
     ws = w_split(w)
-    plain, split = ops.conv_tc(a, ws, b, M, LA, Lout, taps, pad, pool=pool, slope=0.1, want_plain=True, want_split=True)
+    plain, split = ops.conv_tc(a, ws, b, M, LA, Lout, taps, pad, pool=pool, slope=0.1, want_plain=True, want_split=True, chain_channels=flags)
     torch.cuda.synchronize()
     st = ops.conv_tc_status(dev)
     want = reference(x, w, b, pad, pool, 0.1)
@@ -54,15 +54,15 @@ def run(M, LA, Cin, Cout, taps, pad, pool, seed=0, time_it=False):
     y32 = F.leaky_relu(y32, 0.1).permute(0, 2, 1).reshape(-1, Cout)
     torch.backends.cudnn.allow_tf32 = old
     err32 = float((y32.double() - want).abs().max()) / scale
-    msg = "M=%-6d LA=%-2d %3d->%3d taps=%-2d pool=%d  status=%d  err=%.2e (split %.2e)  cudnn-fp32 err=%.2e" % (
+    msg = "chain=%-3d " % flags + "M=%-6d LA=%-2d %3d->%3d taps=%-2d pool=%d  status=%d  err=%.2e (split %.2e)  cudnn-fp32 err=%.2e" % (
         M, LA, Cin, Cout, taps, pool, st, err, err_split, err32)
     if time_it:
         for _ in range(2):
-            ops.conv_tc(a, ws, b, M, LA, Lout, taps, pad, pool=pool, slope=0.1, want_plain=False, want_split=True)
+            ops.conv_tc(a, ws, b, M, LA, Lout, taps, pad, pool=pool, slope=0.1, want_plain=False, want_split=True, chain_channels=flags)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(5):
-            ops.conv_tc(a, ws, b, M, LA, Lout, taps, pad, pool=pool, slope=0.1, want_plain=False, want_split=True)
+            ops.conv_tc(a, ws, b, M, LA, Lout, taps, pad, pool=pool, slope=0.1, want_plain=False, want_split=True, chain_channels=flags)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
@@ -79,14 +79,63 @@ SMALL = [  # (M, LA, Cin, Cout, taps, pad, pool)
 LAYERS = [(64, 64, 56, 1), (64, 128, 56, 2), (128, 128, 28, 1), (128, 128, 28, 1), (128, 256, 28, 2), (256, 256, 14, 1),
           (256, 256, 14, 1), (256, 512, 14, 2), (512, 256, 7, 1), (256, 128, 7, 1)]
 
+def clocks_under_load(cfg, flags, seconds=3.0):
+    """Loop one layer for a few seconds and sample nvidia-smi: the SM clock the tensor pipe really runs at."""
+    import subprocess
+    import threading
+    import time
+
+    M, LA, Cin, Cout, taps, pad, pool = cfg
+    x = torch.randn(M * LA, Cin, device=dev)
+    _, a = ops.act(x, None, pool=1, slope=1.0, want_plain=False, want_split=True, parts=2)
+    ws = w_split(torch.randn(Cout, Cin, taps, device=dev) * 0.05)
+    b = torch.zeros(Cout, device=dev)
+    samples = []
+    stop = threading.Event()
+
+    def sample():
+        while not stop.is_set():
+            out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap",
+                                  "--format=csv,noheader,nounits", "-i", "0"], capture_output=True, text=True).stdout.strip()
+            samples.append(out)
+            time.sleep(0.1)
+
+    th = threading.Thread(target=sample)
+    th.start()
+    t0 = time.time()
+    n = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    while time.time() - t0 < seconds:
+        for _ in range(20):
+            ops.conv_tc(a, ws, b, M, LA, LA, taps, pad, pool=pool, slope=0.1, want_plain=False, want_split=True, chain_channels=flags)
+        n += 20
+        torch.cuda.synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    stop.set()
+    th.join()
+    print("sustained: %.3f ms per launch over %d launches; nvidia-smi (MHz, W, power cap): %s" % (
+        e0.elapsed_time(e1) / n, n, " | ".join(samples[3::4])), flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "small"
+    if what == "clocks":
+        clocks_under_load((64 * 1091, 14, 256, 512, 3, 1, 2), int(sys.argv[2], 0) if len(sys.argv) > 2 else 32)
+    if what == "one":
+        flags = int(sys.argv[2], 0) if len(sys.argv) > 2 else 32
+        for _ in range(3):
+            run(64 * 1091, 14, 256, 512, 3, 1, 2, time_it=False, flags=flags)
     if what in ("small", "all"):
         for k, c in enumerate(SMALL):
-            if run(*c, seed=k):
-                sys.exit("pipeline wait timed out")
+            for flags in (16, 32, 64):
+                if run(*c, seed=k, flags=flags):
+                    sys.exit("pipeline wait timed out")
     if what in ("layers", "all"):
         M = int(sys.argv[2]) if len(sys.argv) > 2 else 64 * 1091
         for cin, cout, L, pool in LAYERS:
-            run(M, L, cin, cout, 3, 1, pool, time_it=True)
-        run(M, 14, 256, 128, 14, 0, 1, time_it=True)
+            for flags in (16, 32, 64, 96):
+                run(M, L, cin, cout, 3, 1, pool, time_it=True, flags=flags)
+        for flags in (32, 64, 128):
+            run(M, 14, 256, 128, 14, 0, 1, time_it=True, flags=flags)
