@@ -122,14 +122,16 @@ __device__ __forceinline__ float finish(double v, float range, const Consts& c, 
 }
 
 // Range, half-angle, step and start angle of row (b, s, m)   (:274-285)
-template <typename PhiT>
+// FAST_ATAN (float32 arctangent, 1-2 ulp) was measured: it saves 9 % of the FAST kernel's instructions but the
+// extra half-angle ulps against NumPy cost end-to-end parity of the streaming engine, so nothing uses it.
+template <typename PhiT, bool FAST_ATAN = false>
 __device__ __forceinline__ void row_basics(const CutoutArgs& a, int b, int s, int m, RowGeom& g, float& two_ha) {
     const int i = m * a.stride;
     const int ref_scan = a.fixed ? s : a.S - 1;
     g.range = __ldg(a.scans + ((size_t)b * a.S + ref_scan) * a.N + i);
     const size_t ha_slot = ((size_t)b * a.S + s) * a.M + m;
-    const float ha = a.half_alpha_in ? __ldg(a.half_alpha_in + ha_slot)
-                                     : atan_f32(__fdiv_rn(a.half_width, fmaxf(g.range, 1e-2f)));   // :279
+    const float ratio = __fdiv_rn(a.half_width, fmaxf(g.range, 1e-2f));
+    const float ha = a.half_alpha_in ? __ldg(a.half_alpha_in + ha_slot) : (FAST_ATAN ? atanf(ratio) : atan_f32(ratio));   // :279
     if (a.half_alpha_out) a.half_alpha_out[ha_slot] = ha;
     two_ha = 2.0f * ha;
     g.step = __fdiv_rn(two_ha, (float)(a.P - 1));                    // :282
@@ -138,7 +140,7 @@ __device__ __forceinline__ void row_basics(const CutoutArgs& a, int b, int s, in
 }
 
 // One CTA per sample b: max over its S*M rows of idx[P-1] - idx[0]   (:304, :308)
-template <typename PhiT>
+template <typename PhiT, bool FAST_ATAN>
 __global__ void __launch_bounds__(kThreads) cutout_span_kernel(const CutoutArgs a) {
     __shared__ double warp_max[kThreads / 32];
     const Consts c = make_consts<PhiT>(a);
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(kThreads) cutout_span_kernel(const CutoutArgs 
     for (int r = threadIdx.x; r < a.S * a.M; r += kThreads) {
         RowGeom g;
         float two_ha;
-        row_basics<PhiT>(a, b, r / a.M, r % a.M, g, two_ha);
+        row_basics<PhiT, FAST_ATAN>(a, b, r / a.M, r % a.M, g, two_ha);
         const double span = __dsub_rn(sample_index(g.start, g.step, a.P - 1, c), sample_index(g.start, g.step, 0, c));
         if (span > best) best = span;
     }
@@ -349,9 +351,184 @@ __global__ void __launch_bounds__(kThreads) cutout_kernel(const CutoutArgs a) {
     }
 }
 
+// ---- FAST numerics, row-per-thread form ---------------------------------------------------------
+// The piece-per-thread kernel above spends ~39 issue slots per 4-byte sample, most of them on per-piece
+// bookkeeping (row lookup, 80 bytes of geometry from shared memory, 64-bit index set-up) and on address
+// arithmetic for the scattered 16-byte stores.  Here a thread keeps ONE row's geometry in registers and
+// walks its P samples with a running 32.32 fixed-point index (17 slots per sample, branch-free: the
+// in-scan test is one 64-bit compare, the loads are clamped, the fraction becomes a float with one funnel
+// shift); results are parked in a padded shared-memory tile and leave the SM as one TMA bulk store per row
+// (cp.async.bulk.global.shared::cta, SASS UBLKCP), so the LSU never sees the output.  The few area-mode rows
+// of a tile are done afterwards, spread over all threads as before.
+constexpr int kRowPitchPad = 4;        // floats of padding per tile row: 16-byte aligned and conflict-free STS.128
+
+struct AreaRow {
+    long long fx_base, fx_slope, fx_slope_a;
+    float lo_f, hi_f, pad_f, bias;
+    int s_area, row;
+};
+
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                 "r"((unsigned)__cvta_generic_to_shared(src_smem)), "r"(bytes)
+                 : "memory");
+}
+
+template <typename PhiT>
+__global__ void __launch_bounds__(kThreads) cutout_rows_kernel(const CutoutArgs a) {
+    extern __shared__ __align__(16) float smem_f[];          // [N + 1 (+pad)] staged scan | [kTilePts][P + pad] tile
+    __shared__ AreaRow area_rows[kTilePts];
+    __shared__ int warp_area[kTilePts / 32];
+    const Consts c = make_consts<PhiT>(a);
+    const int tid = threadIdx.x;
+    const int bs = blockIdx.x / a.tiles_per_scan;            // b * S + s
+    const int m0 = (blockIdx.x - bs * a.tiles_per_scan) * kTilePts;
+    const int b = bs / a.S, s = bs - b * a.S;
+    const int rows_here = min(kTilePts, a.M - m0);
+    const int nm1 = a.N - 1;
+    // S == 1: the tile's rows are adjacent in the output, so an unpadded tile leaves as ONE bulk store (its
+    // 16-byte stores then have 2-way bank conflicts, which is far cheaper than issuing a store per row)
+    const int pitch = a.S == 1 ? a.P : a.P + kRowPitchPad;
+    float* staged = smem_f;
+    float* tile = smem_f + ((a.N + 1 + 3) & ~3);
+    const float* scan = a.scans + (size_t)bs * a.N;
+
+    for (int i = tid; i < a.N; i += kThreads) staged[i] = __ldg(scan + i);
+    if (tid == 0) staged[a.N] = __ldg(scan + nm1);           // beam N-1 once more: the two-tap load never leaves the array
+
+    // ---- one thread per point: geometry in registers -------------------------------------------
+    const bool valid = tid < rows_here;
+    bool is_area = false;
+    RowGeom g;
+    float scale = a.centered ? (float)c.inv_depth : 1.0f, bias = 0.f;
+    g.fx_base = g.fx_slope = g.fx_slope_a = 0;
+    g.s_area = 0;
+    g.lo_f = g.hi_f = g.pad_f = 0.f;
+    if (valid) {
+        float two_ha;
+        row_basics<PhiT>(a, b, s, m0 + tid, g, two_ha);
+        const double i0 = sample_index(g.start, g.step, 0, c);
+        g.step_a = 0.f;
+        if (a.area_mode) {                                               // :304-310
+            const double span = __dsub_rn(sample_index(g.start, g.step, a.P - 1, c), i0);
+            if (span > (double)a.P) {
+                g.s_area = (int)ceil(__ddiv_rn(a.span_max[b], (double)a.P));
+                g.step_a = __fdiv_rn(two_ha, (float)(g.s_area * a.P - 1));
+                is_area = true;
+            }
+        }
+        g.lo_f = finish((double)(g.range - a.depth_f), g.range, c, a.centered);
+        g.hi_f = finish((double)(g.range + a.depth_f), g.range, c, a.centered);
+        g.pad_f = fminf(fmaxf(finish(a.pad, g.range, c, a.centered), g.lo_f), g.hi_f);
+        g.fx_base = to_fixed(i0);
+        g.fx_slope = to_fixed((double)g.step * c.inv_pitch);
+        g.fx_slope_a = to_fixed((double)g.step_a * c.inv_pitch);
+        bias = a.centered ? -g.range * scale : 0.f;
+    }
+    const unsigned m_area = __ballot_sync(0xffffffffu, valid && is_area);
+    if ((tid & 31) == 0) warp_area[tid >> 5] = __popc(m_area);
+    __syncthreads();                                                     // staged scan + area counts visible
+
+    // ---- two-tap rows: P samples per thread ------------------------------------------------------
+    if (valid && !is_area) {
+        // +2^-24 beam: the 23-bit fraction below is then rounded, not truncated; the in-scan limit moves with it
+        long long fx = g.fx_base + 0x100ll;
+        const unsigned long long limit = ((unsigned long long)(unsigned)nm1 << 32) + 0x100ull;
+        float* dst = tile + tid * pitch;
+        const long long step3 = 3 * g.fx_slope;
+        for (int k = 0; k < a.P; k += 4) {
+            float res[4];
+            // the index grows along the row: if the first and the last sample of the chunk are inside the
+            // scan, all four are, and neither clamping nor the padding select is needed
+            if ((unsigned long long)fx <= limit && (unsigned long long)(fx + step3) <= limit) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u, fx += g.fx_slope) {
+                    const unsigned lo = (unsigned)((unsigned long long)fx >> 32);
+                    const float v0 = staged[lo], v1 = staged[lo + 1];
+                    const float w = __uint_as_float(__funnelshift_r((unsigned)fx, 0x7fu, 9)) - 1.0f;   // fraction of the index
+                    res[u] = fminf(fmaxf(fmaf(fmaf(w, v1 - v0, v0), scale, bias), g.lo_f), g.hi_f);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u, fx += g.fx_slope) {
+                    const unsigned lo = min((unsigned)((unsigned long long)fx >> 32), (unsigned)nm1);
+                    const float v0 = staged[lo], v1 = staged[lo + 1];
+                    const float w = __uint_as_float(__funnelshift_r((unsigned)fx, 0x7fu, 9)) - 1.0f;
+                    const float v = fminf(fmaxf(fmaf(fmaf(w, v1 - v0, v0), scale, bias), g.lo_f), g.hi_f);
+                    res[u] = ((unsigned long long)fx <= limit) ? v : g.pad_f;
+                }
+            }
+            *reinterpret_cast<float4*>(dst + k) = make_float4(res[0], res[1], res[2], res[3]);
+        }
+    }
+
+    // ---- area rows: compact them, then 4-sample pieces over all threads -------------------------
+    int n_area = 0;
+#pragma unroll
+    for (int w = 0; w < kTilePts / 32; ++w) n_area += warp_area[w];
+    if (n_area > 0) {                                                    // CTA-uniform
+        if (valid && is_area) {
+            int pos = __popc(m_area & ((1u << (tid & 31)) - 1u));
+            for (int v = 0; v < (tid >> 5); ++v) pos += warp_area[v];
+            AreaRow r;
+            r.fx_base = g.fx_base; r.fx_slope = g.fx_slope; r.fx_slope_a = g.fx_slope_a;
+            r.lo_f = g.lo_f; r.hi_f = g.hi_f; r.pad_f = g.pad_f; r.bias = bias; r.s_area = g.s_area; r.row = tid;
+            area_rows[pos] = r;
+        }
+        __syncthreads();
+        const unsigned vpr = (unsigned)a.P >> 2;
+        const unsigned pieces = (unsigned)n_area * vpr;
+        for (unsigned q = tid; q < pieces; q += kThreads) {
+            const unsigned li = q / vpr, cq = q - li * vpr;
+            const AreaRow r = area_rows[li];
+            long long fx = r.fx_base + (long long)(cq << 2) * r.fx_slope;
+            float res[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u, fx += r.fx_slope) {
+                const int lo = (int)(fx >> 32);
+                float v = r.pad_f;
+                if ((unsigned)lo < (unsigned)nm1 || (lo == nm1 && (unsigned)fx == 0u)) {
+                    float acc = 0.f;
+                    long long fa = r.fx_base + (long long)(((int)(cq << 2) + u) * r.s_area) * r.fx_slope_a + 0x80000000ll;
+                    for (int t = 0; t < r.s_area; ++t, fa += r.fx_slope_a) acc += staged[min(max((int)(fa >> 32), 0), nm1)];
+                    v = fminf(fmaxf(fmaf(__fdiv_rn(acc, (float)r.s_area), scale, r.bias), r.lo_f), r.hi_f);
+                }
+                res[u] = v;
+            }
+            *reinterpret_cast<float4*>(tile + r.row * pitch + (cq << 2)) = make_float4(res[0], res[1], res[2], res[3]);
+        }
+    }
+
+    // ---- the tile leaves through the TMA: one bulk store per row ---------------------------------
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> async-proxy reads
+    __syncthreads();
+    if (a.S == 1 ? tid == 0 : valid) {
+        float* row_out = a.out + (((size_t)b * a.M + m0 + tid) * a.S + s) * a.P;
+        bulk_s2g(row_out, tile + tid * pitch, (unsigned)(a.S == 1 ? rows_here : 1) * (unsigned)a.P * 4u);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // shared memory may go once it has been read
+    }
+}
+
 template <typename PhiT, bool FAST>
 int launch_cutout(const CutoutArgs& a, cudaStream_t stream) {
     const unsigned grid = (unsigned)a.tiles_per_scan * (unsigned)(a.B * a.S);
+    if (FAST && a.N < kMaxStagedPts) {
+        const size_t smem = ((size_t)((a.N + 1 + 3) & ~3) + (size_t)kTilePts * (a.P + kRowPitchPad)) * sizeof(float);
+        if (smem <= 200 * 1024) {
+            static bool attr_set[2][64] = {{false}};
+            int dev = 0;
+            POF_CUDA(cudaGetDevice(&dev));
+            const int which = sizeof(PhiT) == 8;
+            if (dev < 64 && !attr_set[which][dev]) {
+                POF_CUDA(cudaFuncSetAttribute(cutout_rows_kernel<PhiT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_set[which][dev] = true;
+            }
+            cutout_rows_kernel<PhiT><<<grid, kThreads, smem, stream>>>(a);
+            POF_CUDA(cudaGetLastError());
+            return POF_OK;
+        }
+    }
     if (a.N <= kMaxStagedPts) {
         cutout_kernel<PhiT, FAST, true><<<grid, kThreads, (size_t)a.N * sizeof(float), stream>>>(a);
     } else {
@@ -407,8 +584,8 @@ int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64, int B, i
     POF_REQUIRE((long long)a.tiles_per_scan * B * S < (1ll << 31), POF_ERR_BAD_SHAPE, "pof_cutout_fwd: too many tiles");
 
     if (area_mode || s_area_out) {
-        if (phi_is_f64) cutout_span_kernel<double><<<B, kThreads, 0, stream>>>(a);
-        else cutout_span_kernel<float><<<B, kThreads, 0, stream>>>(a);
+        if (phi_is_f64) cutout_span_kernel<double, false><<<B, kThreads, 0, stream>>>(a);
+        else cutout_span_kernel<float, false><<<B, kThreads, 0, stream>>>(a);
         POF_CUDA(cudaGetLastError());
     }
     if (numerics == POF_CUTOUT_FAST) return phi_is_f64 ? launch_cutout<double, true>(a, stream) : launch_cutout<float, true>(a, stream);

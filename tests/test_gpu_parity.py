@@ -103,6 +103,18 @@ def _check_cutout(scans, phi, kw, stride=1, want=None, ha_ref=None):
         near = ((diag["rint_margin"] < 1e-6) | (diag["edge_margin"] < 1e-6)).transpose(1, 0, 2)
         assert not (bad4 & ~near).any(), "FAST arithmetic: max err %.3g" % err4[bad4 & ~near].max()
         assert bad4.sum() <= 2
+
+    # (5) FAST on its own: the same device arctangent as EXACT (<= 2 ulp from NumPy's), and the oracle evaluated with the
+    # half-angles the kernel reports matches the kernel at every sample but proven flips
+    got_fast_own, ha_fast = _gpu_cutout(scans, phi, kw, stride, fast=True)
+    assert _ulp_distance(ha_fast, ha_ref).max() <= 2
+    want_fast = ocut.scans_to_cutout(scans, phi, stride=stride, half_alpha=ha_fast, **kw)
+    bad5 = np.abs(got_fast_own.astype(np.float64) - want_fast) > REL_TOL * scale
+    if bad5.any():
+        diag = ocut.cutout_diagnostics(scans, phi, stride=stride, half_alpha=ha_fast, **kw)
+        near = ((diag["rint_margin"] < 1e-6) | (diag["edge_margin"] < 1e-6)).transpose(1, 0, 2)
+        assert not (bad5 & ~near).any(), "FAST with device half-angles: %d samples off" % int((bad5 & ~near).sum())
+        assert bad5.sum() <= 2
     return int(bad.sum()), exact_frac
 
 
