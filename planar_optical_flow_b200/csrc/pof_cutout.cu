@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(kThreads) cutout_rows_kernel(const CutoutArgs 
 template <typename PhiT, bool FAST>
 int launch_cutout(const CutoutArgs& a, cudaStream_t stream) {
     const unsigned grid = (unsigned)a.tiles_per_scan * (unsigned)(a.B * a.S);
-    if (FAST && a.N < kMaxStagedPts) {
+    if (FAST && a.S == 1 && a.N < kMaxStagedPts) {      // S > 1: rows are not adjacent, a bulk store per row is slower than pieces
         const size_t smem = ((size_t)((a.N + 1 + 3) & ~3) + (size_t)kTilePts * (a.P + kRowPitchPad)) * sizeof(float);
         if (smem <= 200 * 1024) {
             static bool attr_set[2][64] = {{false}};
