@@ -223,6 +223,20 @@ POF_API int pof_conv_tc_fwd(const float* a_split, const float* w_split, const fl
                             int pool, float slope, float* out_plain, float* out_split,
                             int* status, int chain_channels, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * 5. Windowed patch correlation of the scan-pair flow prototype
+ *    replaces Prototype._fusion, src/depracted/model/prototype.py:118-156 (dense [N, N] patch
+ *    correlation followed by a +-max_displacement gather):
+ *      out[b, d + D, i] = sum_c sum_{k=-h..h} f1[b, c, clamp(i+k)] * f2[b, c, clamp(clamp(i+d)+k)]
+ *    feat1, feat2 [B, C, N]; out / grad_out [B, 2D+1, N]; h = kernel_size / 2 (odd kernel_size),
+ *    2D+1 <= 32.  The backward is deterministic (no atomics).
+ * ------------------------------------------------------------------------- */
+POF_API int pof_patch_corr_fwd(const float* feat1, const float* feat2, int B, int C, int N,
+                               int kernel_size, int max_displacement, float* out, void* stream);
+POF_API int pof_patch_corr_bwd(const float* feat1, const float* feat2, const float* grad_out,
+                               int B, int C, int N, int kernel_size, int max_displacement,
+                               float* grad_feat1, float* grad_feat2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -122,12 +122,35 @@ def model_cases(rm):
          weights_sha256=np.array(weights_digest(sd)))
 
 
+def prototype_cases():
+    """Scan-pair flow prototype (prototype.py:34-156): the fusion alone and the whole forward, eval mode."""
+    from oracle import prototype as oproto
+
+    rp = ref_shim.load_prototype()
+    seed, b, n = 61, 3, 450
+    sd = oproto.init_state_dict(2, 5, seed=seed)
+    m = rp.Prototype(in_channel=2, max_displacement=5)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    scan1 = torch.randn(b, n, 2, generator=g) * 3
+    scan2 = scan1 + 0.05 * torch.randn(b, n, 2, generator=g)
+    f1, f2 = torch.randn(2, 24, 19, generator=g), torch.randn(2, 24, 19, generator=g)
+    with torch.no_grad(), ref_shim.cpu_cuda_noop():
+        flow = m(scan1, scan2)
+        fused = m._fusion(f1, f2, kernel_size=3, max_displacement=5)
+    save("prototype_drow450", scan1=scan1.numpy(), scan2=scan2.numpy(), flow=flow.numpy(), f1=f1.numpy(), f2=f2.numpy(),
+         fused=fused.numpy(), seed=np.array(seed), weights_sha256=np.array(weights_digest(sd)))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ru, rm = ref_shim.load()
-    cutout_cases(ru)
-    nms_cases(ru)
-    model_cases(rm)
+    if "--only-prototype" not in sys.argv:
+        cutout_cases(ru)
+        nms_cases(ru)
+        model_cases(rm)
+    prototype_cases()
 
 
 if __name__ == "__main__":

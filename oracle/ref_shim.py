@@ -56,6 +56,7 @@ def load():
 
         ref_utils = importlib.import_module("src.utils.utils")
         ref_model = importlib.import_module("src.depracted.model.dr_spaam")
+        _cache["prototype"] = importlib.import_module("src.depracted.model.prototype")
     finally:
         sys.path.remove(REFERENCE_ROOT)
         ref_mods = {k: sys.modules.pop(k) for k in list(sys.modules)
@@ -64,3 +65,28 @@ def load():
     _cache["mods"] = (ref_utils, ref_model)
     _cache["all"] = ref_mods
     return _cache["mods"]
+
+
+def load_prototype():
+    """The reference's `src.depracted.model.prototype` module (Prototype, flow_loss)."""
+    load()
+    return _cache["prototype"]
+
+
+class cpu_cuda_noop:
+    """`Prototype._fusion` allocates a scratch tensor with `.cuda()` that it never uses
+    (prototype.py:121); on the GPU-less build container that one call is made a no-op while the
+    reference runs.  Nothing else about the reference is altered."""
+
+    def __enter__(self):
+        import torch
+
+        self._orig = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda t, *a, **k: t
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+
+        torch.Tensor.cuda = self._orig
+        return False

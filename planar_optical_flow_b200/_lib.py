@@ -45,6 +45,8 @@ SIGNATURES = {
                                 c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pof_head_fwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_int,
                              c_void_p, c_void_p]),
+    "pof_patch_corr_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pof_patch_corr_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "pof_nms_ws_bytes": (c_size_t, [c_int, c_int]),
     "pof_nms_centers": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_double,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

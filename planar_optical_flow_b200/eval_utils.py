@@ -54,6 +54,44 @@ def make_model_fn_obj_det(cutout_kwargs):
     return model_fn_obj_det
 
 
+# ------------------------------------------------------------------ scan-pair flow prototype (row N3)
+def model_fn(model, batch):
+    """Training closure of the prototype (eval_utils.py:10-29): scan pair -> flow, mean end-point error.
+
+    The reference reads `batch["flow_target_flow"]` (its datasets emit `flow_target`) and unpacks three values
+    from a loss that returns two; this is the version that runs."""
+    device = next(model.parameters()).device
+    pair = torch.from_numpy(np.ascontiguousarray(batch["scan_pair"], dtype=np.float32)).to(device, non_blocking=True)
+    target = torch.from_numpy(np.ascontiguousarray(batch["flow_target"], dtype=np.float32)).to(device, non_blocking=True)
+    core = model.module if hasattr(model, "module") else model
+    loss, _ = core.loss_fn(model(pair[:, 0], pair[:, 1]), target)
+    return loss
+
+
+def loss_fn_eval(pred_flow, target_flow):
+    """End-point error and average angular error per sample (eval_utils.py:129-134)."""
+    epe = torch.mean(torch.norm(pred_flow - target_flow, dim=-1), dim=1)
+    aae = torch.mean(torch.abs(torch.atan2(pred_flow[..., 0], pred_flow[..., 1]) -
+                               torch.atan2(target_flow[..., 0], target_flow[..., 1])), dim=1) * 180 / np.pi
+    return epe, aae
+
+
+@torch.no_grad()
+def model_fn_eval(model, eval_loader):
+    """(mean EPE, mean AAE) over a loader of scan pairs (eval_utils.py:136-155, for the prototype's batches)."""
+    device = next(model.parameters()).device
+    model.eval()
+    epe_sum = aae_sum = 0.0
+    for batch in eval_loader:
+        pair = torch.from_numpy(np.ascontiguousarray(batch["scan_pair"], dtype=np.float32)).to(device)
+        target = torch.from_numpy(np.ascontiguousarray(batch["flow_target"], dtype=np.float32)).to(device)
+        epe, aae = loss_fn_eval(model(pair[:, 0], pair[:, 1]), target)
+        epe_sum += torch.mean(epe).item()
+        aae_sum += torch.mean(aae).item()
+    n = max(len(eval_loader), 1)
+    return epe_sum / n, aae_sum / n
+
+
 @torch.no_grad()
 def eval_dr_spaam(model, test_loader, cfg, output_dir=None, max_sequences=None):
     """Stream every test sample's scans through the detector (memory carried) and run NMS on each."""

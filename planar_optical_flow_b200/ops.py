@@ -224,6 +224,43 @@ def head(y, bias, M, L, w_head, b_head, n_sigmoid, slope=0.1):
     return out
 
 
+# --------------------------------------------------------------------------- patch correlation (prototype)
+class _PatchCorrFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f1, f2, kernel_size, max_displacement):
+        f1, f2 = f1.contiguous(), f2.contiguous()
+        require_cuda_tensor(f1, "feat1", torch.float32)
+        require_cuda_tensor(f2, "feat2", torch.float32)
+        if f1.shape != f2.shape or f1.dim() != 3:
+            raise ValueError("feat1 and feat2 must both be [B, C, N] (got %s, %s)" % (tuple(f1.shape), tuple(f2.shape)))
+        B, C, N = f1.shape
+        dev = f1.device
+        with torch.cuda.device(dev):
+            out = torch.empty((B, 2 * max_displacement + 1, N), dtype=torch.float32, device=dev)
+            check(_lib.lib().pof_patch_corr_fwd(_ptr(f1), _ptr(f2), B, C, N, int(kernel_size), int(max_displacement), _ptr(out),
+                                                current_stream_ptr(dev)), "pof_patch_corr_fwd")
+        ctx.save_for_backward(f1, f2)
+        ctx.cfg = (int(kernel_size), int(max_displacement))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        f1, f2 = ctx.saved_tensors
+        B, C, N = f1.shape
+        dev = f1.device
+        g = g.contiguous()
+        with torch.cuda.device(dev):
+            g1, g2 = torch.empty_like(f1), torch.empty_like(f2)
+            check(_lib.lib().pof_patch_corr_bwd(_ptr(f1), _ptr(f2), _ptr(g), B, C, N, ctx.cfg[0], ctx.cfg[1], _ptr(g1), _ptr(g2),
+                                                current_stream_ptr(dev)), "pof_patch_corr_bwd")
+        return g1, g2, None, None
+
+
+def patch_corr(feat1, feat2, kernel_size=3, max_displacement=5):
+    """Windowed patch correlation [B, C, N] x [B, C, N] -> [B, 2*max_displacement+1, N] (prototype.py:118-156), differentiable."""
+    return _PatchCorrFn.apply(feat1, feat2, kernel_size, max_displacement)
+
+
 # --------------------------------------------------------------------------- nms
 def nms_centers(scan, phi, cls, reg, min_dist=0.5):
     """Batched `nms_predicted_center` (reference: src/utils/utils.py:535-571).

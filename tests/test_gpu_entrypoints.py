@@ -33,6 +33,16 @@ def test_train_then_eval_scripts(tmp_path):
     assert "detections_per_scan" in log
 
 
+def test_prototype_train_then_eval_scripts(tmp_path):
+    out = str(tmp_path)
+    log = _run(["bin/train_prototype.py", "--out", out, "--epochs", "1", "--batch-size", "20", "--num-samples", "60",
+                "--ckpt-save-interval", "1", "--data", "/nonexistent"], tmp_path)
+    assert "Analysis finished" in log and os.path.isfile(os.path.join(out, "ckpts", "ckpt_e1.pth"))
+    log = _run(["bin/eval_prototype.py", "--ckpt", os.path.join(out, "ckpts", "ckpt_e1.pth"), "--num-samples", "40",
+                "--batch-size", "20", "--data", "/nonexistent"], tmp_path)
+    assert "epe" in log
+
+
 def test_training_step_decreases_loss_on_fixed_batch():
     from planar_optical_flow_b200.dataset_dr_spaam import create_dataloader
     from planar_optical_flow_b200.eval_utils import make_model_fn_obj_det

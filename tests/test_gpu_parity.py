@@ -439,6 +439,63 @@ def test_conv_first_and_head_kernels_match_torch():
         assert_rel(got.cpu(), fake_head(y, bias, 29, L, wh, bh, nsig), tol=2e-6, what="heads")
 
 
+# ------------------------------------------------------------------ scan-pair flow prototype (row N3)
+@pytest.mark.parametrize("b,c,n,k,d", [(2, 256, 57, 3, 5), (1, 8, 7, 3, 5), (3, 40, 137, 5, 2), (1, 3, 1, 3, 5), (2, 300, 64, 3, 15)])
+def test_patch_corr_forward_backward(b, c, n, k, d):
+    from oracle import prototype as oproto
+
+    torch.manual_seed(b + c + n)
+    f1 = torch.randn(b, c, n, dtype=torch.float64, requires_grad=True)
+    f2 = torch.randn(b, c, n, dtype=torch.float64, requires_grad=True)
+    want = oproto.fusion_dense(f1, f2, k, d)
+    w = torch.randn_like(want)
+    (want * w).sum().backward()
+    g1 = f1.detach().float().cuda().requires_grad_(True)
+    g2 = f2.detach().float().cuda().requires_grad_(True)
+    got = ops.patch_corr(g1, g2, kernel_size=k, max_displacement=d)
+    (got * w.float().cuda()).sum().backward()
+    assert_rel(got.detach().cpu(), want.detach(), tol=2e-6, what="patch correlation")
+    assert_rel(g1.grad.cpu(), f1.grad, tol=2e-6, what="grad feat1")
+    assert_rel(g2.grad.cpu(), f2.grad, tol=2e-6, what="grad feat2")
+    # deterministic backward: bit-equal on a second run
+    h1 = g1.detach().clone().requires_grad_(True)
+    h2 = g2.detach().clone().requires_grad_(True)
+    (ops.patch_corr(h1, h2, kernel_size=k, max_displacement=d) * w.float().cuda()).sum().backward()
+    assert torch.equal(h1.grad, g1.grad) and torch.equal(h2.grad, g2.grad)
+
+
+def test_prototype_matches_reference_golden_and_trains(golden_dir):
+    from oracle import prototype as oproto
+    from planar_optical_flow_b200.model.prototype import Prototype
+
+    g = np.load(os.path.join(golden_dir, "prototype_drow450.npz"))
+    sd = oproto.init_state_dict(2, 5, seed=int(g["seed"]))
+    m = Prototype(in_channel=2, max_displacement=5)
+    m.load_state_dict(sd, strict=True)                                    # the reference's checkpoint layout
+    m = m.cuda().eval()
+    with torch.no_grad():
+        flow = m(torch.from_numpy(g["scan1"]).cuda(), torch.from_numpy(g["scan2"]).cuda())
+        fused = m._fusion(torch.from_numpy(g["f1"]).cuda(), torch.from_numpy(g["f2"]).cuda())
+    assert_rel(fused.cpu().numpy(), g["fused"], tol=2e-6, what="fusion vs reference")
+    assert_rel(flow.cpu().numpy(), g["flow"], tol=2e-5, what="flow vs reference")
+    # one training step against the autograd of the oracle (train-mode BN)
+    m.train()
+    s1, s2 = torch.from_numpy(g["scan1"][:2]), torch.from_numpy(g["scan2"][:2])
+    tgt = torch.from_numpy(g["flow"][:2]) * 0.5
+    loss, _ = m.loss_fn(m(s1.cuda(), s2.cuda()), tgt.cuda())
+    loss.backward()
+    sd_o = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    loss_o = torch.mean(torch.mean(torch.norm(oproto.prototype_forward(s1, s2, sd_o, training=True) - tgt, dim=-1), dim=1))
+    loss_o.backward()
+    assert abs(loss.item() - loss_o.item()) <= 1e-4 * abs(loss_o.item())
+    for name, p in m.named_parameters():
+        if name.endswith(".0.bias"):
+            continue                        # a conv bias in front of train-mode BN has zero gradient in exact arithmetic
+        gq, wq = p.grad.cpu().flatten().double(), sd_o[name].grad.flatten().double()
+        cos = float((gq @ wq) / (gq.norm() * wq.norm() + 1e-300))
+        assert cos > 0.999, (name, cos)
+
+
 # ------------------------------------------------------------------ streaming engine
 # tf32x3 on cuDNN: the split products are exact, but the tensor cores ACCUMULATE with truncation, a bias of
 # ~5e-8 per 8-wide k-step that adds up coherently over the 4608-deep reductions (measured 8e-5 on the

@@ -22,6 +22,24 @@ def test_reference_import_paths_resolve():
     assert phi.shape == (450,) and phi.dtype == np.float64 and abs(phi[1] - phi[0] - np.radians(0.5)) < 1e-12
 
 
+def test_prototype_import_paths_and_batches():
+    """Row N3: `from src.depracted.model import Prototype`, FlowDataset batches with the reference's keys."""
+    import numpy as np
+
+    from src.depracted.model import Prototype  # noqa: F401
+    from src.utils.dataset import FlowDataset
+    from src.utils.eval_utils import model_fn, model_fn_eval  # noqa: F401
+
+    ds = FlowDataset(None, split="train", num_samples=6)
+    batch = ds.collate_batch([ds[0], ds[1], ds[2]])
+    assert batch["scan_pair"].shape == (3, 2, 450, 2) and batch["flow_target"].shape == (3, 450, 2)
+    assert batch["scan_pair"].dtype == np.float32
+    m = Prototype(in_channel=2)
+    ref_keys = {"encoder_0", "encoder_1", "encoder_2", "decoder_1", "decoder_0", "flow_reg"}
+    assert {k.split(".")[0] for k in m.state_dict()} == ref_keys
+    assert m.decoder_1[0].weight.shape == (128, 11 + 128, 3) and m.flow_reg[0].weight.shape == (2, 130, 1)
+
+
 def test_config_schema_matches_reference_keys():
     cfg = yaml.safe_load(open(os.path.join(ROOT, "config", "dr_spaam.yaml")))
     for k in ("tag", "epochs", "batch_size", "grad_norm_clip", "num_workers", "num_scans", "use_data_augumentation",

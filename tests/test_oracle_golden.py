@@ -80,3 +80,19 @@ def test_model_stream_golden(golden_dir):
             assert np.array_equal(reg.numpy(), g["reg_%d" % t])
             assert np.array_equal(ff.numpy(), g["feat_fused_%d" % t])
     assert np.array_equal(tmpl.numpy()[:, ::8, ::16], g["template_last_sample"])
+
+
+def test_prototype_oracle_matches_reference_golden(golden_dir):
+    import os
+
+    import torch
+
+    from oracle import prototype as oproto
+
+    g = np.load(os.path.join(golden_dir, "prototype_drow450.npz"))
+    sd = oproto.init_state_dict(2, 5, seed=int(g["seed"]))
+    with torch.no_grad():
+        flow = oproto.prototype_forward(torch.from_numpy(g["scan1"]), torch.from_numpy(g["scan2"]), sd)
+        fused = oproto.fusion_dense(torch.from_numpy(g["f1"]), torch.from_numpy(g["f2"]), 3, 5)
+    assert np.array_equal(fused.numpy(), g["fused"])
+    assert np.abs(flow.numpy() - g["flow"]).max() <= 1e-6 * np.abs(g["flow"]).max()

@@ -158,3 +158,42 @@ def test_drow_forward_matches_reference(ref):
         got = omodel.drow_forward(x, sd_drow)
     for a, b in zip(want, got):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ scan-pair flow prototype (row N3)
+@pytest.mark.reference
+@pytest.mark.parametrize("b,c,n,k,d", [(2, 24, 57, 3, 5), (1, 8, 7, 3, 5), (3, 4, 20, 5, 2), (1, 3, 1, 3, 5)])
+def test_prototype_fusion_bit_equal(b, c, n, k, d):
+    from oracle import prototype as oproto
+    from oracle import ref_shim
+
+    rp = ref_shim.load_prototype()
+    torch.manual_seed(b * 100 + n)
+    f1, f2 = torch.randn(b, c, n), torch.randn(b, c, n)
+    m = rp.Prototype(in_channel=2, max_displacement=d)
+    with ref_shim.cpu_cuda_noop():
+        want = m._fusion(f1, f2, kernel_size=k, max_displacement=d)
+    assert torch.equal(oproto.fusion_dense(f1, f2, k, d), want)
+    got = oproto.fusion_windowed(f1, f2, k, d)
+    assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+@pytest.mark.reference
+def test_prototype_forward_bit_equal():
+    from oracle import prototype as oproto
+    from oracle import ref_shim
+
+    rp = ref_shim.load_prototype()
+    sd = oproto.init_state_dict(2, 5, seed=3)
+    m = rp.Prototype(in_channel=2, max_displacement=5)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    torch.manual_seed(4)
+    s1 = torch.randn(2, 450, 2)
+    s2 = s1 + 0.1 * torch.randn(2, 450, 2)
+    with torch.no_grad(), ref_shim.cpu_cuda_noop():
+        want = m(s1, s2)
+        want_self = m(s1)
+    with torch.no_grad():
+        assert torch.equal(oproto.prototype_forward(s1, s2, sd), want)
+        assert torch.equal(oproto.prototype_forward(s1, s1, sd), want_self)
