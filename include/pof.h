@@ -237,6 +237,22 @@ POF_API int pof_patch_corr_bwd(const float* feat1, const float* feat2, const flo
                                int B, int C, int N, int kernel_size, int max_displacement,
                                float* grad_feat1, float* grad_feat2, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * 6. Legacy preprocessing
+ *    pof_cutout_original_fwd  replaces scans_to_cutout_original, src/utils/utils.py:423-489 (integer beam
+ *        window resampled with cv2.resize: INTER_AREA when shrinking, INTER_LINEAR otherwise); selected by
+ *        configs without `area_mode` (src/utils/dataset_dr_spaam.py:440-443).  scans [B, S, N] -> out
+ *        [B, N, S, P], each b one reference call.  `angle_incre_is_f32`: the reference divides by
+ *        scan_phi[1] - scan_phi[0] in that value's own dtype.
+ *    pof_polar_grid_fwd       replaces scans_to_polar_grid, utils.py:492-531: scans [S, N] -> out
+ *        [S, R, N], R = int((max_range - min_range) / range_bin_size) + 1.
+ * ------------------------------------------------------------------------- */
+POF_API int pof_cutout_original_fwd(const float* scans, int B, int S, int N, double angle_incre,
+                                    int angle_incre_is_f32, int P, double window_width, double window_depth,
+                                    double padding_val, int fixed, int centered, float* out, void* stream);
+POF_API int pof_polar_grid_fwd(const float* scans, int S, int N, double min_range, double max_range,
+                               double range_bin_size, double tsdf_clip, int normalize, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

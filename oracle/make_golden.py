@@ -143,14 +143,33 @@ def prototype_cases():
          fused=fused.numpy(), seed=np.array(seed), weights_sha256=np.array(weights_digest(sd)))
 
 
+def legacy_cases(ru):
+    """scans_to_cutout_original / scans_to_polar_grid (utils.py:423-531) on DROW- and JRDB-shaped scans."""
+    for shape, n in (("drow", 450), ("jrdb", 1091)):
+        phi = synth.phi_for(shape)
+        scans = synth.structured_sequence(2, n, seed=81, phi=phi)
+        adv = synth.adversarial_scans(2, n, seed=82)
+        adv[0, :7] = [0.004, 0.0099, 0.01, 0.02, 0.05, 29.99, 0.3]          # tiny ranges: windows longer than the scan
+        incre = phi[1] - phi[0]
+        kw = dict(fixed=True, centered=True, window_width=1.66, window_depth=1.0, num_cutout_pts=48, padding_val=29.99)
+        save("cutout_original_%s" % shape, scans=scans, adv=adv, incre=np.array(incre),
+             out=ru.scans_to_cutout_original(scans, incre, **kw), out_adv=ru.scans_to_cutout_original(adv, incre, **kw),
+             out_lastref=ru.scans_to_cutout_original(scans, incre, **dict(kw, fixed=False, centered=False, num_cutout_pts=56)),
+             polar=ru.scans_to_polar_grid(scans[:, ::16]), polar_raw=ru.scans_to_polar_grid(adv[:, ::16], 0.5, 20.0, 0.5, 0.0, False))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ru, rm = ref_shim.load()
-    if "--only-prototype" not in sys.argv:
+    only = [a for a in sys.argv[1:] if a.startswith("--only-")]
+    if not only:
         cutout_cases(ru)
         nms_cases(ru)
         model_cases(rm)
-    prototype_cases()
+    if not only or "--only-prototype" in only:
+        prototype_cases()
+    if not only or "--only-legacy" in only:
+        legacy_cases(ru)
 
 
 if __name__ == "__main__":

@@ -47,6 +47,9 @@ SIGNATURES = {
                              c_void_p, c_void_p]),
     "pof_patch_corr_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pof_patch_corr_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "pof_cutout_original_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_double, c_double, c_double,
+                                        c_int, c_int, c_void_p, c_void_p]),
+    "pof_polar_grid_fwd": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_int, c_void_p, c_void_p]),
     "pof_nms_ws_bytes": (c_size_t, [c_int, c_int]),
     "pof_nms_centers": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_double,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

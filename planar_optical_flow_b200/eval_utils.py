@@ -17,6 +17,10 @@ from . import ops
 def batch_cutouts(batch, cutout_kwargs, device, fast=False):
     """Raw ranges [B, S, N] (NumPy) -> device cutouts [B, N, S, P] (dataset_dr_spaam.py:445 on the GPU)."""
     scans = torch.from_numpy(np.ascontiguousarray(batch["scans"], dtype=np.float32)).to(device, non_blocking=True)
+    if "area_mode" not in cutout_kwargs:          # legacy configs (dataset_dr_spaam.py:440-443): integer window + cv2.resize
+        phi_h = np.asarray(batch["scan_phi"])
+        incre = phi_h[1] - phi_h[0]
+        return ops.cutout_original(scans, float(incre), angle_incre_is_f32=phi_h.dtype == np.float32, **cutout_kwargs)
     phi = torch.from_numpy(np.ascontiguousarray(batch["scan_phi"])).to(device)
     return ops.cutout(scans, phi, fast=fast, **cutout_kwargs)
 

@@ -64,6 +64,37 @@ def cutout(scans, phi, stride=1, centered=True, fixed=False, window_width=1.66, 
     return (out, *extra) if extra else out
 
 
+def cutout_original(scans, angle_incre, angle_incre_is_f32=False, fixed=True, centered=True, window_width=1.66, window_depth=1.0,
+                    num_cutout_pts=48, padding_val=29.99):
+    """Batched `scans_to_cutout_original` (utils.py:423-489): scans [B, S, N] float32 CUDA -> [B, N, S, P]."""
+    require_cuda_tensor(scans, "scans", torch.float32)
+    if scans.dim() != 3:
+        raise ValueError("scans must be [B, S, N] (got %s)" % (tuple(scans.shape),))
+    B, S, N = scans.shape
+    dev = scans.device
+    with torch.cuda.device(dev):
+        out = torch.empty((B, N, S, int(num_cutout_pts)), dtype=torch.float32, device=dev)
+        check(_lib.lib().pof_cutout_original_fwd(_ptr(scans), B, S, N, float(angle_incre), int(bool(angle_incre_is_f32)),
+                                                 int(num_cutout_pts), float(window_width), float(window_depth), float(padding_val),
+                                                 int(bool(fixed)), int(bool(centered)), _ptr(out), current_stream_ptr(dev)),
+              "pof_cutout_original_fwd")
+    return out
+
+
+def polar_grid(scans, min_range=0.0, max_range=30.0, range_bin_size=1.0, tsdf_clip=1.0, normalize=True):
+    """`scans_to_polar_grid` (utils.py:492-531): scans [S, N] float32 CUDA -> [S, R, N]."""
+    require_cuda_tensor(scans, "scans", torch.float32)
+    S, N = scans.shape
+    R = int((max_range - min_range) / range_bin_size) + 1
+    dev = scans.device
+    with torch.cuda.device(dev):
+        out = torch.empty((S, R, N), dtype=torch.float32, device=dev)
+        check(_lib.lib().pof_polar_grid_fwd(_ptr(scans), S, N, float(min_range), float(max_range), float(range_bin_size),
+                                            float(tsdf_clip), int(bool(normalize)), _ptr(out), current_stream_ptr(dev)),
+              "pof_polar_grid_fwd")
+    return out
+
+
 # --------------------------------------------------------------------------- gate
 def gate_forward(x, tmpl, emb_x, emb_t, alpha, window, want_weights=False, out=None):
     """Windowed attention memory update (reference: dr_spaam.py:183-215).

@@ -109,6 +109,32 @@ def scans_to_cutout_batch(scans, scan_phi, **cutout_kwargs):
     return ops.cutout(scans.float().contiguous(), phi.to(scans.device), **cutout_kwargs)
 
 
+def scans_to_cutout_original(scans, angle_incre, fixed=True, centered=True, pt_inds=None, window_width=1.66, window_depth=1.0,
+                             num_cutout_pts=48, padding_val=29.99):
+    """The legacy cutout (utils.py:423-489; configs without `area_mode`): `scans [S, N]` -> `[N, S, P]` float32.
+
+    `pt_inds` restricts the reference's loop to some points and leaves the other rows of its np.empty
+    output uninitialised; here every row is computed."""
+    scans = np.asarray(scans)
+    if scans.ndim != 2:
+        raise ValueError("scans must be [num_scans, num_pts]")
+    dev = _device()
+    s = torch.from_numpy(np.ascontiguousarray(scans, dtype=np.float32)).to(dev).unsqueeze(0)
+    is_f32 = isinstance(angle_incre, np.floating) and np.dtype(type(angle_incre)) == np.float32
+    out = ops.cutout_original(s, float(angle_incre), angle_incre_is_f32=is_f32, fixed=fixed, centered=centered,
+                              window_width=window_width, window_depth=window_depth, num_cutout_pts=num_cutout_pts,
+                              padding_val=padding_val)
+    return out[0].cpu().numpy()
+
+
+def scans_to_polar_grid(scans, min_range=0.0, max_range=30.0, range_bin_size=1.0, tsdf_clip=1.0, normalize=True):
+    """utils.py:492-531: `scans [S, N]` -> polar grid `[S, R, N]` float32."""
+    scans = np.asarray(scans)
+    dev = _device()
+    s = torch.from_numpy(np.ascontiguousarray(scans, dtype=np.float32)).to(dev)
+    return ops.polar_grid(s, min_range, max_range, range_bin_size, tsdf_clip, normalize).cpu().numpy()
+
+
 # ------------------------------------------------------------------ NMS
 def nms_predicted_center(scan_grid, phi_grid, pred_cls, pred_reg, min_dist=0.5):
     """Returns `(det_xys [K,2], det_cls [K,1], instance_mask [N] int32)` as utils.py:535-571.

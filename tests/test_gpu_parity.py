@@ -439,6 +439,43 @@ def test_conv_first_and_head_kernels_match_torch():
         assert_rel(got.cpu(), fake_head(y, bias, 29, L, wh, bh, nsig), tol=2e-6, what="heads")
 
 
+# ------------------------------------------------------------------ legacy preprocessing (row N4)
+@pytest.mark.parametrize("shape", ["drow", "jrdb"])
+def test_cutout_original_and_polar_grid_match_reference_golden(golden_dir, shape):
+    from oracle import cutout_legacy as ol
+
+    g = np.load(os.path.join(golden_dir, "cutout_original_%s.npz" % shape))
+    incre = g["incre"][()]
+    kw = dict(fixed=True, centered=True, window_width=1.66, window_depth=1.0, num_cutout_pts=48, padding_val=29.99)
+    cases = ((g["scans"], g["out"], kw), (g["adv"], g["out_adv"], kw),
+             (g["scans"], g["out_lastref"], dict(kw, fixed=False, centered=False, num_cutout_pts=56)))
+    for scans, want, k in cases:
+        got = utils.scans_to_cutout_original(scans, incre, **k)
+        assert got.dtype == np.float32 and got.shape == want.shape
+        bad = np.abs(got.astype(np.float64) - want) > REL_TOL * np.abs(want).max()          # [N, S, P]
+        # a window end that sits within 1e-5 beams of a rounding boundary may move with the device arctangent
+        near = (ol.window_margins(scans, incre, k["fixed"], k["window_width"]) < 1e-5).T[..., None]
+        assert not (bad & ~near).any(), "legacy cutout: %d samples off" % int((bad & ~near).sum())
+        assert bad.any(axis=2).sum() <= 2
+    assert np.array_equal(utils.scans_to_polar_grid(g["scans"][:, ::16]), g["polar"])
+    assert np.array_equal(utils.scans_to_polar_grid(g["adv"][:, ::16], 0.5, 20.0, 0.5, 0.0, False), g["polar_raw"])
+
+
+def test_cutout_original_batched_and_f32_pitch():
+    from oracle import cutout_legacy as ol
+
+    phi32 = synth.phi_for("jrdb")                                              # float32 angles: float32 beam pitch
+    assert phi32.dtype == np.float32
+    scans = np.stack([synth.structured_sequence(2, len(phi32), seed=k, phi=phi32) for k in range(3)])      # [B, S, N]
+    incre = phi32[1] - phi32[0]
+    got = ops.cutout_original(torch.from_numpy(scans).cuda(), float(incre), angle_incre_is_f32=True, num_cutout_pts=32).cpu().numpy()
+    for b in range(3):
+        want = ol.scans_to_cutout_original(scans[b], incre, num_cutout_pts=32)
+        bad = np.abs(got[b] - want) > REL_TOL * np.abs(want).max()
+        near = (ol.window_margins(scans[b], incre, True, 1.66) < 1e-4).T[..., None]
+        assert not (bad & ~near).any()
+
+
 # ------------------------------------------------------------------ scan-pair flow prototype (row N3)
 @pytest.mark.parametrize("b,c,n,k,d", [(2, 256, 57, 3, 5), (1, 8, 7, 3, 5), (3, 40, 137, 5, 2), (1, 3, 1, 3, 5), (2, 300, 64, 3, 15)])
 def test_patch_corr_forward_backward(b, c, n, k, d):

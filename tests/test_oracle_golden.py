@@ -96,3 +96,19 @@ def test_prototype_oracle_matches_reference_golden(golden_dir):
         fused = oproto.fusion_dense(torch.from_numpy(g["f1"]), torch.from_numpy(g["f2"]), 3, 5)
     assert np.array_equal(fused.numpy(), g["fused"])
     assert np.abs(flow.numpy() - g["flow"]).max() <= 1e-6 * np.abs(g["flow"]).max()
+
+
+@pytest.mark.parametrize("shape", ["drow", "jrdb"])
+def test_legacy_oracle_matches_reference_golden(golden_dir, shape):
+    import os
+
+    from oracle import cutout_legacy as ol
+
+    g = np.load(os.path.join(golden_dir, "cutout_original_%s.npz" % shape))
+    kw = dict(fixed=True, centered=True, window_width=1.66, window_depth=1.0, num_cutout_pts=48, padding_val=29.99)
+    incre = g["incre"][()]
+    for scans, want in ((g["scans"], g["out"]), (g["adv"], g["out_adv"])):
+        got = ol.scans_to_cutout_original(scans, incre, **kw)
+        assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+    assert np.array_equal(ol.scans_to_polar_grid(g["scans"][:, ::16]), g["polar"])
+    assert np.array_equal(ol.scans_to_polar_grid(g["adv"][:, ::16], 0.5, 20.0, 0.5, 0.0, False), g["polar_raw"])

@@ -197,3 +197,40 @@ def test_prototype_forward_bit_equal():
     with torch.no_grad():
         assert torch.equal(oproto.prototype_forward(s1, s2, sd), want)
         assert torch.equal(oproto.prototype_forward(s1, s1, sd), want_self)
+
+
+# ------------------------------------------------------------------ legacy preprocessing (row N4)
+@pytest.mark.reference
+def test_resize_column_matches_cv2():
+    import cv2
+
+    from oracle import cutout_legacy as ol
+
+    rs = np.random.RandomState(0)
+    for _ in range(300):
+        n, P = int(rs.randint(1, 600)), int(rs.choice([48, 56, 32, 7]))
+        col = (rs.rand(n) * 30).astype(np.float32)
+        area = P < n
+        want = cv2.resize(col, (1, P), interpolation=cv2.INTER_AREA if area else cv2.INTER_LINEAR).reshape(-1)
+        got = ol.resize_column(col, P, area)
+        assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max(), (n, P)
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("shape", ["drow", "jrdb"])
+@pytest.mark.parametrize("kw", [dict(), dict(fixed=False, centered=False, window_width=1.0, window_depth=0.5, num_cutout_pts=56)])
+def test_cutout_original_and_polar_grid_match_reference(shape, kw):
+    from oracle import cutout_legacy as ol
+    from oracle import ref_shim
+
+    ru, _ = ref_shim.load()
+    phi = synth.phi_for(shape)
+    scans = np.concatenate([synth.structured_sequence(2, len(phi), seed=5, phi=phi), synth.adversarial_scans(1, len(phi), seed=6)])
+    incre = phi[1] - phi[0]
+    want = ru.scans_to_cutout_original(scans, incre, **kw)
+    got = ol.scans_to_cutout_original(scans, incre, **kw)
+    assert got.dtype == want.dtype == np.float32 and got.shape == want.shape
+    assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+    assert (got == want).mean() > 0.999
+    assert np.array_equal(ol.scans_to_polar_grid(scans), ru.scans_to_polar_grid(scans))
+    assert np.array_equal(ol.scans_to_polar_grid(scans, 0.5, 20.0, 0.5, 0.0, False), ru.scans_to_polar_grid(scans, 0.5, 20.0, 0.5, 0.0, False))
