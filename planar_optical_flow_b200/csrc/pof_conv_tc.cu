@@ -50,12 +50,19 @@ constexpr int kATile = kTileM * kRowBytes;     // bytes of one A operand tile (h
 constexpr int kTmemCols = 512;
 constexpr long long kWaitLimit = 2000000000LL; // ~1 s of SM clocks
 
-template <int BN>
+// CG = 1: one CTA computes a 128 x BN tile.  CG = 2: an SM pair (cta_group::2) computes 256 x BN, each CTA
+// holding its 128 rows of A and HALF of the weight tile: the MMA then reads 64 B/clk of operands per SM
+// instead of 96, which is what lets it run at full rate next to the TMA fill (shared memory moves 128 B/clk).
+constexpr int kRingBytes = 184 * 1024;                 // operand ring
+constexpr int kStagePitch = 36;                        // floats per staged output row: 32 columns + 4 (conflict-free 16-byte accesses)
+constexpr int kStagingBytes = 8 * 32 * kStagePitch * 4;   // one 32 x 32 transposition buffer per epilogue warp
+
+template <int BN, int CG>
 struct Cfg {
-    static constexpr int kBTile = BN * kRowBytes;
+    static constexpr int kBTile = (BN / CG) * kRowBytes;       // this CTA's share of one W operand tile (hi or lo)
     static constexpr int kStage = 2 * kATile + 2 * kBTile;
-    static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int kSmem = kStages * kStage + 1024 /* alignment slack */ + 256 /* barriers */;
+    static constexpr int kStages = (kRingBytes / kStage) < 8 ? (kRingBytes / kStage) : 8;
+    static constexpr int kSmem = kStages * kStage + 1024 /* alignment slack */ + 256 /* barriers */ + kStagingBytes;
     static constexpr int kAcc = BN / 2;        // accumulators per epilogue thread
 };
 
@@ -130,8 +137,8 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned addr) {
            (4ull << 61) /* SWIZZLE_64B */;
 }
 // Instruction descriptor: D = fp32, A = B = TF32, both K-major, M = 128, N = bn.
-__device__ __forceinline__ unsigned umma_idesc(int bn) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(bn >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
+__device__ __forceinline__ unsigned umma_idesc(int bn, int m) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(bn >> 3) << 17) | ((unsigned)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long a, unsigned long long b, unsigned idesc, unsigned acc) {
     asm volatile(
@@ -140,6 +147,48 @@ __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long a,
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(a), "l"(b), "r"(idesc), "r"(acc)
         : "memory");
+}
+// ---- cta_group::2 forms: the leader CTA (cluster rank 0) issues for the pair -----------------------
+constexpr unsigned kPeerBitMask = 0xFEFFFFFFu;    // clears the CTA-rank bit of a shared::cluster address -> the leader's copy
+__device__ __forceinline__ void tma_load_3d_pair(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(unsigned tmem_d, unsigned long long a, unsigned long long b, unsigned idesc, unsigned acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(unsigned bar) {      // arrives on the same barrier in both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((unsigned short)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(unsigned bar) {    // arrive on the leader CTA's copy of `bar`
+    asm volatile(
+        "{\n\t.reg .b32 r;\n\t"
+        "mapa.shared::cluster.u32 r, %0, 0;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [r];\n\t}" ::"r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
 __device__ __forceinline__ void umma_commit(unsigned bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -183,10 +232,10 @@ __device__ __forceinline__ float tf32_rn(float x) {
 }
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int CG>
+__global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Params p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, CG>;
     extern __shared__ unsigned char smem_raw[];
     const unsigned base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const unsigned bars = base + C::kStages * C::kStage;       // full[S] | empty[S] | tfull[2] | tempty[2] | tmem ptr
@@ -195,24 +244,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     auto tfull = [&](int b) { return bars + 8u * (2 * C::kStages + b); };
     auto tempty = [&](int b) { return bars + 8u * (2 * C::kStages + 2 + b); };
     const unsigned tmem_slot = bars + 8u * (2 * C::kStages + 4);
+    float* staging = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned rank = CG > 1 ? cluster_rank() : 0u;          // rank 0 of a pair leads: it issues the MMAs
     const int kb_per_tap = p.Cin / kKBlock;
     const int n_kb = p.taps * kb_per_tap;
-    const long long n_tiles = p.tiles_m * p.tiles_n;
+    // work items: (group of CG consecutive row tiles) x (column tile); a CTA takes row tile CG * g + rank
+    const long long n_tiles = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;
+    const long long first_tile = blockIdx.x / CG, tile_stride = gridDim.x / CG;
     const int rows_tile = p.mt * p.Lout;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::kStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tfull(b), 1); mbar_init(tempty(b), 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull(b), 1); mbar_init(tempty(b), 8 * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CG > 1) cluster_sync();          // the peer's barriers and tensor memory exist before anything is sent to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     unsigned tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -221,31 +280,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 0 && lane == 0) {
             // ------------------------------------------------------------------ TMA producer
-            const unsigned tx = 2u * (unsigned)rows_tile * kRowBytes + 2u * (unsigned)C::kBTile;
+            const unsigned tx = CG * (2u * (unsigned)rows_tile * kRowBytes + 2u * (unsigned)C::kBTile);   // both CTAs' loads land on the leader's barrier
             long long it = 0;
             bool ok = true;
-            for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+            for (long long tile = first_tile; tile < n_tiles && ok; tile += tile_stride) {
                 const int nt = (int)(tile % p.tiles_n);
-                const long long m0 = (tile / p.tiles_n) * p.mt;
+                const long long m0 = ((tile / p.tiles_n) * CG + rank) * p.mt;
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
                     const int s = (int)(it % C::kStages);
                     const unsigned ph = (unsigned)((it / C::kStages) & 1);
                     if (!(ok = mbar_wait(empty(s), ph ^ 1u, p.status, 1))) break;
                     const int tap = kb / kb_per_tap, c0 = (kb - tap * kb_per_tap) * kKBlock;
                     const unsigned dst = base + (unsigned)s * C::kStage;
-                    mbar_expect_tx(full(s), tx);
-                    tma_load_3d(dst, &map_a, c0, tap - p.pad, (int)m0, full(s));
-                    tma_load_3d(dst + kATile, &map_a, p.Cin + c0, tap - p.pad, (int)m0, full(s));
-                    tma_load_2d(dst + 2 * kATile, &map_w, c0, (tap * 2 + 0) * p.Cout + nt * BN, full(s));
-                    tma_load_2d(dst + 2 * kATile + C::kBTile, &map_w, c0, (tap * 2 + 1) * p.Cout + nt * BN, full(s));
+                    if (CG == 1) {
+                        mbar_expect_tx(full(s), tx);
+                        tma_load_3d(dst, &map_a, c0, tap - p.pad, (int)m0, full(s));
+                        tma_load_3d(dst + kATile, &map_a, p.Cin + c0, tap - p.pad, (int)m0, full(s));
+                        tma_load_2d(dst + 2 * kATile, &map_w, c0, (tap * 2 + 0) * p.Cout + nt * BN, full(s));
+                        tma_load_2d(dst + 2 * kATile + C::kBTile, &map_w, c0, (tap * 2 + 1) * p.Cout + nt * BN, full(s));
+                    } else {
+                        const int n0 = nt * BN + (int)rank * (BN / CG);          // my half of the weight tile's rows
+                        if (rank == 0) mbar_expect_tx(full(s), tx);
+                        tma_load_3d_pair(dst, &map_a, c0, tap - p.pad, (int)m0, full(s));
+                        tma_load_3d_pair(dst + kATile, &map_a, p.Cin + c0, tap - p.pad, (int)m0, full(s));
+                        tma_load_2d_pair(dst + 2 * kATile, &map_w, c0, (tap * 2 + 0) * p.Cout + n0, full(s));
+                        tma_load_2d_pair(dst + 2 * kATile + C::kBTile, &map_w, c0, (tap * 2 + 1) * p.Cout + n0, full(s));
+                    }
                 }
             }
-        } else if (warp == 1 && lane == 0) {
-            // ------------------------------------------------------------------ MMA issuer
-            const unsigned idesc = umma_idesc(BN);
+        } else if (warp == 1 && lane == 0 && rank == 0) {
+            // ------------------------------------------------------------------ MMA issuer (the pair's leader only)
+            const unsigned idesc = umma_idesc(BN, kTileM * CG);
             long long it = 0, ic = 0;                                  // k-blocks, chains issued so far
             bool ok = true;
-            for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+            for (long long tile = first_tile; tile < n_tiles && ok; tile += tile_stride) {
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
                     const int s = (int)(it % C::kStages);
                     const unsigned ph = (unsigned)((it / C::kStages) & 1);
@@ -259,14 +327,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const unsigned long long b_hi = umma_desc(st + 2 * kATile), b_lo = umma_desc(st + 2 * kATile + C::kBTile);
                     const unsigned d = tmem_base + (unsigned)(buf * BN);
                     constexpr int kSteps = kKBlock / 8;                                    // K = 8 per tf32 MMA = 32 B of the row
+                    if (CG == 1) {
 #pragma unroll
-                    for (int k = 0; k < kSteps; ++k) umma_tf32(d, a_lo + 2 * k, b_hi + 2 * k, idesc, k > 0 || !first);   // corrections first
+                        for (int k = 0; k < kSteps; ++k) umma_tf32(d, a_lo + 2 * k, b_hi + 2 * k, idesc, k > 0 || !first);   // corrections first
 #pragma unroll
-                    for (int k = 0; k < kSteps; ++k) umma_tf32(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+                        for (int k = 0; k < kSteps; ++k) umma_tf32(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
 #pragma unroll
-                    for (int k = 0; k < kSteps; ++k) umma_tf32(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);       // main product last
-                    umma_commit(empty(s));
-                    if (last) { umma_commit(tfull(buf)); ++ic; }
+                        for (int k = 0; k < kSteps; ++k) umma_tf32(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);       // main product last
+                        umma_commit(empty(s));
+                        if (last) { umma_commit(tfull(buf)); ++ic; }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kSteps; ++k) umma_tf32_pair(d, a_lo + 2 * k, b_hi + 2 * k, idesc, k > 0 || !first);
+#pragma unroll
+                        for (int k = 0; k < kSteps; ++k) umma_tf32_pair(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+#pragma unroll
+                        for (int k = 0; k < kSteps; ++k) umma_tf32_pair(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
+                        umma_commit_pair(empty(s));                      // both CTAs' producers may refill their slot
+                        if (last) { umma_commit_pair(tfull(buf)); ++ic; }  // both CTAs' epilogues may read their rows
+                    }
                 }
             }
         }
@@ -278,7 +357,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const unsigned lane_addr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(h * C::kAcc);
         long long it = 0;
         bool ok = true;
-        for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+        for (long long tile = first_tile; tile < n_tiles && ok; tile += tile_stride) {
             float acc[C::kAcc];
 #pragma unroll
             for (int j = 0; j < C::kAcc; ++j) acc[j] = 0.f;
@@ -304,45 +383,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty(buf));
+                if (lane == 0) {
+                    if (CG == 1) mbar_arrive(tempty(buf));
+                    else mbar_arrive_leader(tempty(buf));              // the leader's MMA warp waits for both CTAs' epilogues
+                }
             }
             if (!ok) break;
-            // epilogue for this tile: registers only, the tensor memory is already back with the MMA warp
+            // epilogue for this tile: registers only, the tensor memory is already back with the MMA warp.
+            // A lane holds one output ROW; written as is, every store instruction would touch 32 rows x 16 bytes.
+            // Each warp therefore transposes 32 x 32 blocks through shared memory and stores 4 rows x 128 bytes
+            // per instruction.
             const int nt = (int)(tile % p.tiles_n);
-            const long long r = (tile / p.tiles_n) * p.mt * p.Lout + row;          // global output row before pooling
-            const bool valid = row < rows_tile && r < p.Mcut * p.Lout && (p.pool == 1 || (lane & 1) == 0);
-            const long long orow = p.pool == 2 ? (r >> 1) : r;
+            const long long r0 = ((tile / p.tiles_n) * CG + rank) * p.mt * p.Lout + q * 32;     // output row of lane 0, before pooling
+            const bool valid = row < rows_tile && r0 + lane < p.Mcut * p.Lout;
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
             const int cbase = nt * BN + h * C::kAcc;
+            float* stg = staging + e * (32 * kStagePitch);
+            const int nrows = p.pool == 2 ? 16 : 32;                  // output rows this warp owns
+            const long long orow0 = p.pool == 2 ? (r0 >> 1) : r0;
+            // one transposition pass: lane l's 32 values -> rows of 128 bytes at dst + j * ld
+            auto flush = [&](const float (&o)[32], float* dst, long long ld) {
 #pragma unroll
-            for (int j = 0; j < C::kAcc; j += 4) {
-                float o[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float v = acc[j + i];
-                    if (p.pool == 2) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-                    if (p.bias) v += __ldg(p.bias + cbase + j + i);
-                    o[i] = lrelu(v, p.slope);
+                for (int k = 0; k < 32; k += 4)
+                    *reinterpret_cast<float4*>(stg + lane * kStagePitch + k) = make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]);
+                __syncwarp();
+                for (int j = lane >> 3; j < nrows; j += 4) {
+                    const int src = p.pool == 2 ? 2 * j : j;          // the lane that holds output row j
+                    if ((vmask >> src) & 1u)
+                        st_stream_f4(reinterpret_cast<float4*>(dst + j * ld + (lane & 7) * 4),
+                                     *reinterpret_cast<const float4*>(stg + src * kStagePitch + (lane & 7) * 4));
                 }
-                if (valid) {
-                    if (p.out_plain)
-                        st_stream_f4(reinterpret_cast<float4*>(p.out_plain + orow * p.Cout + cbase + j), make_float4(o[0], o[1], o[2], o[3]));
-                    if (p.out_split) {
-                        float hi[4], lo[4];
+                __syncwarp();
+            };
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) { hi[i] = tf32_rn(o[i]); lo[i] = tf32_rn(o[i] - hi[i]); }
-                        float* dst = p.out_split + orow * 2 * p.Cout + cbase + j;
-                        st_stream_f4(reinterpret_cast<float4*>(dst), make_float4(hi[0], hi[1], hi[2], hi[3]));
-                        st_stream_f4(reinterpret_cast<float4*>(dst + p.Cout), make_float4(lo[0], lo[1], lo[2], lo[3]));
+            for (int g = 0; g < C::kAcc / 32; ++g) {
+                float o[32];
+#pragma unroll
+                for (int k = 0; k < 32; k += 4) {
+                    const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + cbase + g * 32 + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float v = acc[g * 32 + k + i];
+                        if (p.pool == 2) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+                        o[k + i] = lrelu(v + bb[i], p.slope);
                     }
+                }
+                if (p.out_plain) flush(o, p.out_plain + orow0 * p.Cout + cbase + g * 32, p.Cout);
+                if (p.out_split) {
+                    float hi[32];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) hi[k] = tf32_rn(o[k]);
+                    flush(hi, p.out_split + orow0 * 2 * p.Cout + cbase + g * 32, 2 * p.Cout);
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) o[k] = tf32_rn(o[k] - hi[k]);
+                    flush(o, p.out_split + orow0 * 2 * p.Cout + p.Cout + cbase + g * 32, 2 * p.Cout);
                 }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CG > 1) cluster_sync();          // nobody leaves while the peer may still arrive on its barriers or read its operands
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -363,19 +469,20 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-template <int BN>
+template <int BN, int CG>
 int launch(const CUtensorMap& ma, const CUtensorMap& mw, const Params& p, cudaStream_t stream) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, CG>;
     static bool attr_set[64] = {false};
     int dev = 0;
     POF_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !attr_set[dev]) {
-        POF_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+        POF_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
         attr_set[dev] = true;
     }
-    const long long tiles = p.tiles_m * p.tiles_n;
-    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    conv_tc_kernel<BN><<<grid, kThreads, C::kSmem, stream>>>(ma, mw, p);
+    const long long tiles = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;
+    const long long groups = sm_count() / CG;
+    const int grid = CG * (int)(tiles < groups ? tiles : groups);
+    conv_tc_kernel<BN, CG><<<grid, kThreads, C::kSmem, stream>>>(ma, mw, p);
     POF_CUDA(cudaGetLastError());
     return POF_OK;
 }
@@ -395,6 +502,8 @@ int pof_conv_tc_fwd(const float* a_split, const float* w_split, const float* bia
     POF_REQUIRE(Mcut > 0 && Mcut < (1ll << 31) && LA >= 1 && Lout >= 1 && Lout <= 128 && LA <= 256, POF_ERR_BAD_SHAPE,
                 "pof_conv_tc_fwd: bad shape Mcut=%lld LA=%d Lout=%d", Mcut, LA, Lout);
     POF_REQUIRE(Cin >= kKBlock && Cin % kKBlock == 0, POF_ERR_BAD_SHAPE, "pof_conv_tc_fwd: Cin must be a multiple of %d (got %d)", kKBlock, Cin);
+    const int cg = (chain_channels & POF_CONV_TC_SINGLE_CTA) ? 1 : 2;      // high flag bit: tuning / tests only
+    chain_channels &= ~POF_CONV_TC_SINGLE_CTA;
     if (chain_channels == 0) chain_channels = 64;
     POF_REQUIRE(chain_channels > 0 && chain_channels % kKBlock == 0, POF_ERR_BAD_PARAM,
                 "pof_conv_tc_fwd: chain_channels must be a multiple of %d (got %d)", kKBlock, chain_channels);
@@ -434,16 +543,21 @@ int pof_conv_tc_fwd(const float* a_split, const float* w_split, const float* bia
     {   // W: [taps][2][Cout][Cin] fp32 seen as a [taps * 2 * Cout, Cin] matrix, box (16 channels, bn rows)
         const cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)taps * 2 * Cout};
         const cuuint64_t strides[1] = {(cuuint64_t)Cin * 4};
-        const cuuint32_t box[2] = {(cuuint32_t)kKBlock, (cuuint32_t)bn};
+        const cuuint32_t box[2] = {(cuuint32_t)kKBlock, (cuuint32_t)(bn / cg)};            // each CTA of a pair loads its half
         const cuuint32_t es[2] = {1, 1};
         const CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w_split), dims, strides, box, es,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         POF_REQUIRE(r == CUDA_SUCCESS, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
     }
-    if (bn == 256) return launch<256>(ma, mw, p, stream);
-    if (bn == 128) return launch<128>(ma, mw, p, stream);
-    return launch<64>(ma, mw, p, stream);
+    if (cg == 2) {
+        if (bn == 256) return launch<256, 2>(ma, mw, p, stream);
+        if (bn == 128) return launch<128, 2>(ma, mw, p, stream);
+        return launch<64, 2>(ma, mw, p, stream);
+    }
+    if (bn == 256) return launch<256, 1>(ma, mw, p, stream);
+    if (bn == 128) return launch<128, 1>(ma, mw, p, stream);
+    return launch<64, 1>(ma, mw, p, stream);
 }
 
 }  // extern "C"

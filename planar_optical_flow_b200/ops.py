@@ -6,6 +6,7 @@ hot-path stages happens in libpof.so.  There is no CPU implementation: every
 function raises if handed a CPU tensor.
 """
 import ctypes
+import os
 
 import torch
 
@@ -227,6 +228,8 @@ def conv_tc(a_split, w_split, bias, Mcut, LA, Lout, taps, pad, pool=1, slope=0.1
         raise ValueError("a_split has %d elements, expected %d x %d x %d" % (a_split.numel(), Mcut, LA, 2 * Cin))
     Cout = w_split.shape[2]
     dev = a_split.device
+    if not chain_channels:
+        chain_channels = int(os.environ.get("POF_CONV_TC_CHAIN", "0"), 0)      # tuning aid; 0 = the library default
     with torch.cuda.device(dev):
         status = _conv_tc_status.get(dev)
         if status is None:

@@ -54,7 +54,7 @@ def run(M, LA, Cin, Cout, taps, pad, pool, seed=0, time_it=False, flags=0):
     y32 = F.leaky_relu(y32, 0.1).permute(0, 2, 1).reshape(-1, Cout)
     torch.backends.cudnn.allow_tf32 = old
     err32 = float((y32.double() - want).abs().max()) / scale
-    msg = "chain=%-3d " % flags + "M=%-6d LA=%-2d %3d->%3d taps=%-2d pool=%d  status=%d  err=%.2e (split %.2e)  cudnn-fp32 err=%.2e" % (
+    msg = "chain=%-3d %s " % (flags & 0xffff, "1cta" if flags & 0x10000 else "pair") + "M=%-6d LA=%-2d %3d->%3d taps=%-2d pool=%d  status=%d  err=%.2e (split %.2e)  cudnn-fp32 err=%.2e" % (
         M, LA, Cin, Cout, taps, pool, st, err, err_split, err32)
     if time_it:
         for _ in range(2):
@@ -123,19 +123,23 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "small"
     if what == "clocks":
         clocks_under_load((64 * 1091, 14, 256, 512, 3, 1, 2), int(sys.argv[2], 0) if len(sys.argv) > 2 else 32)
+    if what == "chains":
+        for cfg in ((64 * 1091, 14, 256, 512, 3, 1, 2), (64 * 1091, 7, 512, 256, 3, 1, 1), (64 * 1091, 28, 128, 256, 3, 1, 2)):
+            for flags in (64, 128, 256, 1024, 8192, 8192 | 0x10000):
+                run(*cfg, time_it=True, flags=flags)
     if what == "one":
         flags = int(sys.argv[2], 0) if len(sys.argv) > 2 else 32
         for _ in range(3):
             run(64 * 1091, 14, 256, 512, 3, 1, 2, time_it=False, flags=flags)
     if what in ("small", "all"):
         for k, c in enumerate(SMALL):
-            for flags in (16, 32, 64):
+            for flags in (64, 64 | 0x10000, 32):
                 if run(*c, seed=k, flags=flags):
                     sys.exit("pipeline wait timed out")
     if what in ("layers", "all"):
         M = int(sys.argv[2]) if len(sys.argv) > 2 else 64 * 1091
         for cin, cout, L, pool in LAYERS:
-            for flags in (16, 32, 64, 96):
+            for flags in (64, 64 | 0x10000, 32, 128):
                 run(M, L, cin, cout, 3, 1, pool, time_it=True, flags=flags)
-        for flags in (32, 64, 128):
+        for flags in (64, 64 | 0x10000):
             run(M, 14, 256, 128, 14, 0, 1, time_it=True, flags=flags)
