@@ -13,9 +13,12 @@ One JSON line on stdout (rank 0):
   value      scans/s, whole job, ranges already resident in HBM when the timed region starts
   e2e        the same through StreamingDetector.step(host buffers): H2D of the ranges and D2H
              of the detections inside the timed region
-  roofline   the attention-memory kernel (dominant libpof kernel by bytes): algorithmic bytes
-             (N*44,076 B per sequence-step) / mean launch time from CUDA events
-             recorded around every launch inside the timed steps, against MEASURED_PEAKS.json
+  roofline   the dominant kernel of the step, the tcgen05 convolution (conv_tc_kernel<256,2>): algorithmic
+             fp32 FLOPs (45.9 MFLOP per point) / CUDA-event time around every launch
+             inside the timed steps, against the measured bf16 peak / 2 (TF32 rate)
+  roofline_gate / roofline_cutout   the two HBM-bound hot-path kernels: algorithmic bytes (SURVEY.md
+             §8d: N*44,076 B per sequence-step, N*228 B per scan row) / CUDA-event launch time,
+             against the measured copy bandwidth (MEASURED_PEAKS.json)
   cpu_baseline  the oracle (CPU restatement of the reference, NumPy + torch CPU) timed on this
              box's host cores on a bounded sample of the same workload
 `--impl reference` times that CPU path alone, as the reference arm.
@@ -179,6 +182,16 @@ def measured_hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    """Dense bf16 TFLOP/s sustained inside a long step (MEASURED_PEAKS.json), else the recipe's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+            return float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured bf16 sustained (MEASURED_PEAKS.json)"
+    except Exception:      # noqa: BLE001
+        return 1400.0, "fallback bf16 sustained (B200_PROFILING.md)"
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args):
     import numpy as np
@@ -211,6 +224,7 @@ def run_ours(args):
         for t in range(W):
             run(t)
         det.events = {k: [] for k in det.events}
+        det.event_work = {}
         launches0 = det.kernel_launches
         torch.cuda.synchronize(dev)
         if world > 1:
@@ -240,6 +254,8 @@ def run_ours(args):
     gate_ms = det.event_ms("gate")
     cut_ms = det.event_ms("cutout")
     nms_ms = det.event_ms("nms")
+    conv_ms = {k: det.event_ms(k) for k in ("conv64", "conv128", "conv256")}
+    conv_flops = {k: list(det.event_work.get(k, [])) for k in conv_ms}
     chunk_seqs = det.seq_chunk
     h2d, d2h = det.h2d_bytes_per_step, det.d2h_bytes_per_step
     del det
@@ -298,6 +314,25 @@ def run_ours(args):
     cut_gbs = N * 228 * B / (cut_avg_ms * 1e-3) / 1e9
     sweep_bytes = N * 228 * cut_sweep["batch"]
     sweep_gbs = {k: sweep_bytes / (cut_sweep[k] * 1e-3) / 1e9 for k in ("fast", "exact")}
+    # the dominant kernel of the step: the tcgen05 convolution, BN = 256 instantiation (layers with >= 256 output channels)
+    conv_roof = None
+    if conv_ms["conv256"]:
+        t_ms, fl = sum(conv_ms["conv256"]), sum(conv_flops["conv256"])
+        tpeak, tsrc = measured_tensor_peak()
+        all_ms = sum(sum(v) for v in conv_ms.values())
+        all_fl = sum(sum(v) for v in conv_flops.values())
+        ach = fl / (t_ms * 1e-3) / 1e12
+        conv_roof = {"kernel": "conv_tc_kernel<256,2> (tcgen05 3xTF32 convolution, SM pairs; layers with >= 256 output channels)",
+                     "bound": "tensor", "achieved": ach, "peak": tpeak / 2.0, "unit": "TFLOP/s", "frac": ach / (tpeak / 2.0),
+                     "traffic": None, "peak_source": tsrc + " / 2 (TF32 runs at half the bf16 rate)",
+                     "avg_launch_ms": t_ms / len(conv_ms["conv256"]), "launches_timed": len(conv_ms["conv256"]),
+                     "algorithmic_flops_per_launch": fl / len(conv_ms["conv256"]),
+                     "note": "achieved = fp32 convolution FLOPs (2*rows*Cin*Cout*taps) / CUDA-event time; the kernel issues THREE "
+                             "TF32 MMAs per algorithmic product (hi*hi, lo*hi, hi*lo) to stay fp32-accurate",
+                     "mma_tflops": 3 * ach, "mma_frac_of_tf32_peak": 3 * ach / (tpeak / 2.0),
+                     "share_of_step": t_ms / K / (ms_dev / K),
+                     "all_conv_tc_launches": {"achieved": all_fl / (all_ms * 1e-3) / 1e12, "ms_per_step": all_ms / K,
+                                              "share_of_step": all_ms / ms_dev}}
     out = {
         "metric": METRIC, "value": world * B * K / (ms_dev / 1e3), "unit": "scans/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
@@ -315,7 +350,8 @@ def run_ours(args):
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K, "detections_in_timed_region": n_det,
                 "api": "StreamingDetector.step(host ranges) -> host detections"},
         "gpu_launches": launches,
-        "roofline": {"kernel": "gate_stream_kernel<11,0> (attention memory update)", "bound": "hbm",
+        "roofline": conv_roof,
+        "roofline_gate": {"kernel": "gate_stream_kernel<11,0> (attention memory update)", "bound": "hbm",
                      "achieved": gate_gbs, "peak": peak, "unit": "GB/s", "frac": gate_gbs / peak, "traffic": None,
                      "peak_source": peak_src, "avg_launch_ms": gate_avg_ms, "launches_timed": len(gate_ms),
                      "algorithmic_bytes_per_launch": gate_bytes_per_seq * seqs_per_launch,
@@ -331,11 +367,14 @@ def run_ours(args):
                                                   "note": "one launch pair per step over %d sequences (64 MB): "
                                                           "launch-latency bound at this size" % B}},
         "stage_ms_per_step": {"cutout": sum(cut_ms) / K, "gate": sum(gate_ms) / K, "nms": sum(nms_ms) / K,
-                              "backbone_cudnn_and_rest": ms_dev / K - (sum(cut_ms) + sum(gate_ms) + sum(nms_ms)) / K},
+                              "convolutions_tcgen05": sum(sum(v) for v in conv_ms.values()) / K,
+                              "rest": ms_dev / K - (sum(cut_ms) + sum(gate_ms) + sum(nms_ms) + sum(sum(v) for v in conv_ms.values())) / K},
         "clocks": clocks,
     }
     if extra:
         out["other_precisions"] = extra
+    if out["roofline"] is None:          # library-convolution modes: the attention kernel is the dominant libpof kernel
+        out["roofline"] = out["roofline_gate"]
     if not args.no_cpu_baseline and world == 1:
         v, cores, n, stage = cpu_reference_scans_per_s(args.shape, args.cpu_scans)
         out["cpu_baseline"] = {"value": v, "unit": "scans/s", "cores": cores, "kind": "port",

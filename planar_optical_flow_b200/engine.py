@@ -80,6 +80,7 @@ class _ChannelsLastBackbone:
         self.split = bool(split)
         self.tc = bool(tc)                  # convolutions on libpof's tcgen05 kernel instead of cuDNN
         self.parts = 2 if tc else 3
+        self.timer = None                   # optional: callable(name, flops) -> context manager around each tcgen05 launch
         blocks = [model.conv_block_1, model.conv_block_2, model.conv_block_3, model.conv_block_4]
         folded = [[fold_conv_bn(layer) for layer in blk] for blk in blocks]
         w0, b0 = folded[0][0]
@@ -121,10 +122,18 @@ class _ChannelsLastBackbone:
             raise RuntimeError("cuDNN returned a non-channels-last convolution output")
         return y.view(M * L, cout)
 
+    def _conv_tc(self, a, w, b, M, LA, Lout, taps, pad, **kw):
+        """ops.conv_tc, optionally bracketed by the owner's event timer (algorithmic FLOPs: 2 * rows * Cin * Cout * taps)."""
+        if self.timer is None:
+            return ops.conv_tc(a, w, b, M, LA, Lout, taps, pad, **kw)
+        cin, cout = a.shape[1] // 2, w.shape[2]
+        with self.timer("conv%d" % min(cout, 256), 2.0 * M * Lout * cin * cout * taps):
+            return ops.conv_tc(a, w, b, M, LA, Lout, taps, pad, **kw)
+
     def _layer(self, a, M, L, w, b, cout, pool, plain=False):
         """One conv + bias + LeakyReLU (+ max-pool) layer -> (plain or None, operand for the next convolution)."""
         if self.tc:
-            return ops.conv_tc(a, w, b, M, L, L, 3, 1, pool=pool, slope=_SLOPE, want_plain=plain, want_split=True)
+            return self._conv_tc(a, w, b, M, L, L, 3, 1, pool=pool, slope=_SLOPE, want_plain=plain, want_split=True)
         y = self._conv(a, M, L, w, cout)
         p, s = ops.act(y, b, pool=pool, slope=_SLOPE, want_plain=plain or not self.split, want_split=self.split)
         return p, (s if self.split else p)
@@ -155,8 +164,8 @@ class _ChannelsLastBackbone:
         """Gate embedding (Conv1d k = L, no padding == one GEMM over whole rows) + BN + LeakyReLU."""
         if self.tc:
             L = self.emb_w.shape[0]
-            return ops.conv_tc(operand, self.emb_w, self.emb_b, M, L, 1, L, 0, pool=1, slope=_SLOPE, want_plain=True,
-                               want_split=False)[0]
+            return self._conv_tc(operand, self.emb_w, self.emb_b, M, L, 1, L, 0, pool=1, slope=_SLOPE, want_plain=True,
+                                 want_split=False)[0]
         return F.leaky_relu_(torch.addmm(self.emb_b, operand.view(M, -1), self.emb_w), _SLOPE)
 
     def votes(self, operand, M, L):
@@ -167,7 +176,7 @@ class _ChannelsLastBackbone:
                 last = k == len(self.layers[bi]) - 1
                 if bi == 3 and last:
                     if self.tc:         # bias + LeakyReLU already applied by the convolution's epilogue
-                        y = ops.conv_tc(a, w4, b, M, L, L, 3, 1, pool=1, slope=_SLOPE, want_plain=True, want_split=False)[0]
+                        y = self._conv_tc(a, w4, b, M, L, L, 3, 1, pool=1, slope=_SLOPE, want_plain=True, want_split=False)[0]
                         return ops.head(y, None, M, L, self.w_head, self.b_head, n_sigmoid=self.n_cls, slope=1.0)
                     y = self._conv(a, M, L, w4, cout)
                     return ops.head(y, b, M, L, self.w_head, self.b_head, n_sigmoid=self.n_cls, slope=_SLOPE)
@@ -253,6 +262,9 @@ class StreamingDetector:
         self.d2h_bytes_per_step = sum(t.numel() * t.element_size() for t in self.h_out.values())
         self.record_events = record_events
         self.events = {"cutout": [], "gate": [], "nms": []}
+        self.event_work = {}               # stage -> algorithmic FLOPs of each recorded launch (tcgen05 convolutions)
+        if self.channels_last and record_events:
+            self.net.timer = self._timed
         self.kernel_launches = 0           # launches of libpof kernels (not cuDNN / torch)
 
     # ------------------------------------------------------------------ helpers
@@ -272,7 +284,7 @@ class StreamingDetector:
             torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
     @contextlib.contextmanager
-    def _timed(self, name):
+    def _timed(self, name, work=None):
         if not self.record_events:
             yield
             return
@@ -280,11 +292,13 @@ class StreamingDetector:
         s.record()
         yield
         e.record()
-        self.events[name].append((s, e))
+        self.events.setdefault(name, []).append((s, e))
+        if work is not None:
+            self.event_work.setdefault(name, []).append(work)
 
     def event_ms(self, name):
         """Durations (ms) of the recorded launches of one stage; call after a synchronize."""
-        return [s.elapsed_time(e) for s, e in self.events[name]]
+        return [s.elapsed_time(e) for s, e in self.events.get(name, [])]
 
     # ------------------------------------------------------------------ one chunk of sequences
     def _chunk_channels_last(self, cutouts, b0, b1, first, prev, nxt, pred_cls, pred_reg, feat_fused):
