@@ -31,6 +31,7 @@
 // Area mode needs `s_area = ceil(max_span / P)` over a whole reference call (utils.py:308) =
 // over one sample b here: cutout_span_kernel (one CTA per b) reduces it into `ws` first.
 #include <math.h>
+#include <stdlib.h>
 
 #include "pof_common.cuh"
 
@@ -510,6 +511,298 @@ __global__ void __launch_bounds__(kThreads) cutout_rows_kernel(const CutoutArgs 
     }
 }
 
+// ---- FAST numerics, one CTA per scan (S == 1) -----------------------------------------------------
+// The rows kernel above still spends half of its issue slots outside the sample loop: every 128-point
+// tile re-stages the whole scan, the half-angles are computed twice (span kernel + tile kernel), and the
+// loop itself carries an in-scan test per chunk, two 32-bit gathers, a fraction conversion and a
+// separate scale step.  Here ONE CTA owns ONE scan and its warps work independently:
+//   stage     the scan once, as (C, D) float2 pairs: D = (v[i+1]-v[i])*scale, C = v[i]*scale - D, so a
+//             two-tap sample is ONE LDS.64 and ONE fma on w' = 1.fraction in [1, 2) (the fraction bits
+//             dropped into a float's mantissa with one funnel shift; no int->float conversion);
+//   s_area    = ceil(max span / P) (utils.py:308) needs the scan's maximal index span.  The half-angle is
+//             a monotone function of the range, so the maximum is attained by a row whose range is within
+//             0.1 % of the scan's minimum: only those few rows pay a second arctangent, and no span kernel
+//             runs.  (Caller-supplied half-angles are not monotone: then every row is examined.)
+//   groups    a warp takes 32 consecutive rows at a time: a lane derives its row's geometry once (the double
+//             arctangent included) and walks its P samples with a running 32.32 index, 9 issue slots per
+//             sample (2 index adds, address, LDS.64, funnel shift, fma, bias add, max, min); rows that leave
+//             the scan take a clamped loop.  Chunks are visited in an order rotated by one for every other
+//             group of 4 lanes, which makes the unpadded tile's 16-byte stores bank-conflict free.  The
+//             group's area rows are then resampled by the whole warp, two rows at a time.  The 32 rows are
+//             adjacent in the output, so they leave as ONE TMA bulk store issued by lane 0.  No CTA-wide
+//             barrier after the set-up.
+constexpr int kScanWarpsMax = 12;
+
+__device__ __forceinline__ unsigned hi32(long long v) {
+    unsigned lo, hi;
+    asm("mov.b64 {%0,%1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+    return hi;
+}
+__device__ __forceinline__ float frac_one_two(long long fx) {        // 1.fraction of a 32.32 index, 23 bits
+    return __uint_as_float(__funnelshift_r((unsigned)fx, 0x7fu, 9));
+}
+__device__ __forceinline__ long long shfl_ll(long long v, int src) {
+    return __shfl_sync(0xffffffffu, v, src);
+}
+
+// Four consecutive two-tap samples of a row, in two halves so that the loads of the next chunk are in flight while
+// this one is finished.  INSIDE: every sample is known to lie in the scan.
+struct ChunkTaps {
+    float2 cd[4];
+    float w[4];
+    bool ok[4];
+};
+template <bool INSIDE>
+__device__ __forceinline__ void chunk_load(ChunkTaps& t, long long& fx, long long slope, const float2* pairs, int nm1,
+                                           unsigned long long limit) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u, fx += slope) {
+        t.cd[u] = pairs[INSIDE ? hi32(fx) : min(hi32(fx), (unsigned)nm1)];
+        t.w[u] = frac_one_two(fx);
+        t.ok[u] = INSIDE || (unsigned long long)fx <= limit;
+    }
+}
+template <bool INSIDE>
+__device__ __forceinline__ void chunk_finish(const ChunkTaps& t, float bias, float lo_f, float hi_f, float pad_f, float* dst) {
+    float res[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float v = fminf(fmaxf(fmaf(t.w[u], t.cd[u].y, t.cd[u].x) + bias, lo_f), hi_f);
+        res[u] = t.ok[u] ? v : pad_f;
+    }
+    *reinterpret_cast<float4*>(dst) = make_float4(res[0], res[1], res[2], res[3]);
+}
+// One two-tap row of P = 4*nchunks samples into `dst`; chunks in the order rot, rot+1, ..., nchunks-1, (0 if rot).
+template <bool INSIDE>
+__device__ __forceinline__ void scan_row(long long fx0, long long slope, unsigned rot, int nchunks, const float2* pairs, int nm1,
+                                         unsigned long long limit, float bias, float lo_f, float hi_f, float pad_f, float* dst) {
+    long long fx = fx0 + (rot ? 4 * slope : 0);
+    float* p = dst + 4 * rot;
+    ChunkTaps t0, t1;
+    chunk_load<INSIDE>(t0, fx, slope, pairs, nm1, limit);
+#pragma unroll(INSIDE ? 2 : 1)
+    for (int j = 0; j < nchunks - 2; ++j, p += 4) {
+        chunk_load<INSIDE>(t1, fx, slope, pairs, nm1, limit);
+        chunk_finish<INSIDE>(t0, bias, lo_f, hi_f, pad_f, p);
+        t0 = t1;
+    }
+    if (nchunks > 1) {
+        if (rot) fx = fx0;                                    // the rotated order ends with chunk 0
+        chunk_load<INSIDE>(t1, fx, slope, pairs, nm1, limit);
+        chunk_finish<INSIDE>(t0, bias, lo_f, hi_f, pad_f, p);
+        p = rot ? dst : p + 4;
+        chunk_finish<INSIDE>(t1, bias, lo_f, hi_f, pad_f, p);
+    } else {
+        chunk_finish<INSIDE>(t0, bias, lo_f, hi_f, pad_f, dst);
+    }
+}
+
+// with a single chunk per row there is nothing to rotate
+__device__ __forceinline__ unsigned nchunks_rot(int P, int lane) { return P >= 8 ? ((unsigned)lane >> 2) & 1u : 0u; }
+
+template <typename PhiT>
+__global__ void __launch_bounds__(kScanWarpsMax * 32, 2) cutout_scan_kernel(const CutoutArgs a) {
+    extern __shared__ __align__(16) float smem_f[];          // pairs [N+1] float2 | ranges [N] | per-warp tiles [32][P]
+    __shared__ double warp_span[kScanWarpsMax];
+    __shared__ float warp_min[kScanWarpsMax];
+    const Consts c = make_consts<PhiT>(a);
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const int b = blockIdx.x;                                // S == 1: scan == sample
+    const int nm1 = a.N - 1;
+    const int P = a.P;
+    float2* pairs = reinterpret_cast<float2*>(smem_f);
+    float* vals = smem_f + 2 * ((a.N + 2) & ~1);
+    float* tile = vals + ((a.N + 3) & ~3) + (size_t)warp * 32 * P;
+    const float* scan = a.scans + (size_t)b * a.N;
+    const float scale = a.centered ? (float)c.inv_depth : 1.0f;
+    const PhiT* phi = reinterpret_cast<const PhiT*>(a.phi);
+
+    // ---- stage the scan as (C, D) pairs; entry N repeats beam N-1 so index N-1 + 0 reads in bounds ---
+    float dmin = 3.0e38f;
+    for (int i = tid; i <= a.N; i += T) {
+        const float r0 = __ldg(scan + min(i, nm1));
+        const float v0 = fminf(r0, 1e6f), v1 = fminf(__ldg(scan + min(i + 1, nm1)), 1e6f);     // finite pairs: inf - inf has no blend
+        const float D = (v1 - v0) * scale;
+        pairs[i] = make_float2(fmaf(v0, scale, -D), D);
+        if (i < a.N) vals[i] = r0;
+    }
+    for (int m = tid; m < a.M; m += T) dmin = fminf(dmin, fmaxf(__ldg(scan + m * a.stride), 1e-2f));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    if (lane == 0) warp_min[warp] = dmin;
+    __syncthreads();
+
+    // ---- the scan's maximal index span, from the rows nearest to the sensor -----------------------------
+    int s_area = 0;
+    if (a.area_mode || a.s_area_out) {
+        dmin = warp_min[0];
+        for (int w = 1; w < nwarps; ++w) dmin = fminf(dmin, warp_min[w]);
+        const float near = a.half_alpha_in ? 3.0e38f : dmin * 1.001f;
+        double best = 0.0;
+        for (int m = tid; m < a.M; m += T) {
+            if (fmaxf(vals[m * a.stride], 1e-2f) <= near) {
+                RowGeom g;
+                float two_ha;
+                row_basics<PhiT>(a, b, 0, m, g, two_ha);
+                const double span = __dsub_rn(sample_index(g.start, g.step, P - 1, c), sample_index(g.start, g.step, 0, c));
+                if (span > best) best = span;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double other = __shfl_xor_sync(0xffffffffu, best, o);
+            if (other > best) best = other;
+        }
+        if (lane == 0) warp_span[warp] = best;
+        __syncthreads();
+        best = lane < nwarps ? warp_span[lane] : 0.0;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            const double other = __shfl_xor_sync(0xffffffffu, best, o);
+            if (other > best) best = other;
+        }
+        best = __shfl_sync(0xffffffffu, best, 0);
+        if (a.area_mode && best > (double)P) s_area = (int)ceil(__ddiv_rn(best, (double)P));
+        if (tid == 0) {
+            a.span_max[b] = best;
+            if (a.s_area_out) a.s_area_out[b] = s_area;
+        }
+    }
+
+    const unsigned rot = nchunks_rot(P, lane);
+    const int nchunks = P >> 2;
+    const unsigned long long limit = ((unsigned long long)(unsigned)nm1 << 32) + 0x100ull;
+    const double span_unit = (double)(P - 1) * c.inv_pitch;
+    const float* ha_in = a.half_alpha_in ? a.half_alpha_in + (size_t)b * a.M : nullptr;
+    float* ha_out = a.half_alpha_out ? a.half_alpha_out + (size_t)b * a.M : nullptr;
+    float* out_b = a.out + (size_t)b * a.M * P;
+    const float taps_f = (float)s_area;
+    bool store_pending = false;
+
+    for (int m0 = warp * 32; m0 < a.M; m0 += T) {
+        const int rows_here = min(32, a.M - m0);
+        const bool valid = lane < rows_here;
+        bool is_area = false;
+        long long fx_base = 0, fx_slope = 0, fx_slope_a = 0;
+        float lo_f = 0.f, hi_f = 0.f, pad_f = 0.f, bias = 0.f;
+        if (valid) {                                          // :274-285, from the staged scan
+            const int m = m0 + lane, i = m * a.stride;
+            const float d = vals[i];
+            const float ratio = __fdiv_rn(a.half_width, fmaxf(d, 1e-2f));
+            const float ha = ha_in ? __ldg(ha_in + m) : atan_f32(ratio);                       // :279
+            if (ha_out) ha_out[m] = ha;
+            const float two_ha = 2.0f * ha;
+            const float step = __fdiv_rn(two_ha, (float)(P - 1));                              // :282
+            const double start = (double)(phi[i] - (PhiT)ha);                                  // :284-285
+            fx_base = to_fixed(__dsub_rn(start, c.origin) * c.inv_pitch);
+            fx_slope = to_fixed((double)step * c.inv_pitch);
+            if (s_area > 0) {                                 // :304-310; the exact span only where the decision is close
+                double span = (double)step * span_unit;
+                if (fabs(span - (double)P) < 1e-6 * (double)P)
+                    span = __dsub_rn(sample_index(start, step, P - 1, c), sample_index(start, step, 0, c));
+                if (span > (double)P) {
+                    is_area = true;
+                    fx_slope_a = to_fixed((double)__fdiv_rn(two_ha, (float)(s_area * P - 1)) * c.inv_pitch);
+                }
+            }
+            // float32 forms of the final clip values (EXACT rounds them through double; <= 1 ulp apart)
+            if (a.centered) {
+                lo_f = ((d - a.depth_f) - d) * scale;
+                hi_f = ((d + a.depth_f) - d) * scale;
+                pad_f = fminf(fmaxf(((float)a.pad - d) * scale, lo_f), hi_f);
+                bias = -d * scale;
+            } else {
+                lo_f = d - a.depth_f;
+                hi_f = d + a.depth_f;
+                pad_f = fminf(fmaxf((float)a.pad, lo_f), hi_f);
+            }
+        }
+        if (store_pending) {                                  // the previous group's tile must have been read by the TMA
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+        }
+        const long long fx0 = fx_base + 0x100ll;              // +2^-24 beam: the 23-bit fraction is rounded, not truncated
+        const long long fx_last = fx0 + (long long)(P - 1) * fx_slope;
+        const bool inside = (unsigned long long)fx0 <= limit && (unsigned long long)fx_last <= limit;
+
+        // ---- two-tap rows ---------------------------------------------------------------------------
+        if (valid && !is_area) {
+            float* dst = tile + lane * P;
+            if (inside) scan_row<true>(fx0, fx_slope, rot, nchunks, pairs, nm1, limit, bias, lo_f, hi_f, pad_f, dst);
+            else scan_row<false>(fx0, fx_slope, rot, nchunks, pairs, nm1, limit, bias, lo_f, hi_f, pad_f, dst);
+        }
+
+        // ---- area rows of the group: one at a time, the lanes along its samples (:310-323) --------------
+        unsigned m_area = __ballot_sync(0xffffffffu, valid && is_area);      // 0 when s_area == 0
+        while (m_area) {
+            const int src = __ffs(m_area) - 1;
+            m_area &= m_area - 1;
+            const long long rb = shfl_ll(fx_base, src), rs = shfl_ll(fx_slope, src), rsa = shfl_ll(fx_slope_a, src);
+            const float r_lo = __shfl_sync(0xffffffffu, lo_f, src), r_hi = __shfl_sync(0xffffffffu, hi_f, src);
+            const float r_pad = __shfl_sync(0xffffffffu, pad_f, src), r_bias = __shfl_sync(0xffffffffu, bias, src);
+            const bool r_inside = __shfl_sync(0xffffffffu, (int)inside, src) != 0;
+            float* row = tile + src * P;
+            for (int k = lane; k < P; k += 32) {
+                const long long fx = rb + (long long)k * rs;
+                long long fa = rb + (long long)(k * s_area) * rsa + 0x80000000ll;              // +0.5: nearest tap
+                const int lo = (int)hi32(fx);
+                float v = r_pad;
+                if (r_inside) {
+                    float acc = 0.f;
+                    for (int t = 0; t < s_area; ++t, fa += rsa) acc += vals[hi32(fa)];
+                    v = fminf(fmaxf(fmaf(__fdiv_rn(acc, taps_f), scale, r_bias), r_lo), r_hi);
+                } else if ((unsigned)lo < (unsigned)nm1 || (lo == nm1 && (unsigned)fx == 0u)) {
+                    float acc = 0.f;
+                    for (int t = 0; t < s_area; ++t, fa += rsa) acc += vals[min(max((int)hi32(fa), 0), nm1)];
+                    v = fminf(fmaxf(fmaf(__fdiv_rn(acc, taps_f), scale, r_bias), r_lo), r_hi);
+                }
+                row[k] = v;
+            }
+        }
+
+        // ---- the group's rows are adjacent in the output (S == 1): one bulk store ------------------------
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g(out_b + (unsigned)(m0 * P), tile, (unsigned)(rows_here * P) * 4u);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        store_pending = true;
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+int scan_warps_for(int M) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("POF_SCAN_WARPS");           // tuning aid
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced > 0 && forced <= kScanWarpsMax) return forced;
+    const int groups = (M + 31) / 32;
+    const int rounds = (groups + kScanWarpsMax - 1) / kScanWarpsMax;
+    return (groups + rounds - 1) / rounds;
+}
+
+template <typename PhiT>
+bool launch_cutout_scan(const CutoutArgs& a, cudaStream_t stream, int* status) {
+    const int warps = scan_warps_for(a.M);
+    const size_t smem = ((size_t)2 * ((a.N + 2) & ~1) + (size_t)((a.N + 3) & ~3) + (size_t)warps * 32 * a.P) * sizeof(float);
+    if (smem > 110 * 1024) return false;
+    static bool attr_set[2][64] = {{false}};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    const int which = sizeof(PhiT) == 8;
+    if (dev < 64 && !attr_set[which][dev]) {
+        if (cudaFuncSetAttribute(cutout_scan_kernel<PhiT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess) return false;
+        attr_set[which][dev] = true;
+    }
+    cutout_scan_kernel<PhiT><<<a.B, warps * 32, smem, stream>>>(a);
+    const cudaError_t e = cudaGetLastError();
+    *status = e == cudaSuccess ? POF_OK : cuda_fail(e, "cutout_scan_kernel launch");
+    return true;
+}
+
 template <typename PhiT, bool FAST>
 int launch_cutout(const CutoutArgs& a, cudaStream_t stream) {
     const unsigned grid = (unsigned)a.tiles_per_scan * (unsigned)(a.B * a.S);
@@ -583,6 +876,10 @@ int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64, int B, i
     a.fixed = fixed; a.centered = centered; a.area_mode = area_mode;
     POF_REQUIRE((long long)a.tiles_per_scan * B * S < (1ll << 31), POF_ERR_BAD_SHAPE, "pof_cutout_fwd: too many tiles");
 
+    if (numerics == POF_CUTOUT_FAST && S == 1) {        // one CTA per scan: span reduction, half-angles and samples in one launch
+        int status = POF_OK;
+        if (phi_is_f64 ? launch_cutout_scan<double>(a, stream, &status) : launch_cutout_scan<float>(a, stream, &status)) return status;
+    }
     if (area_mode || s_area_out) {
         if (phi_is_f64) cutout_span_kernel<double, false><<<B, kThreads, 0, stream>>>(a);
         else cutout_span_kernel<float, false><<<B, kThreads, 0, stream>>>(a);
