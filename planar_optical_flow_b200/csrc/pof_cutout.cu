@@ -597,12 +597,70 @@ __device__ __forceinline__ void scan_row(long long fx0, long long slope, unsigne
     }
 }
 
+// Arctangent for the scan kernel: degree-7 Taylor expansions around j/32, j = 0..32 (|h| <= 1/64: truncation
+// 4e-16), coefficient k of interval j at [k][j] so that the lanes of a warp read one bank-conflict-free row per
+// coefficient; a_0 = atan(c), a_k = cos^k(t) sin(k (t + pi/2)) / k with t = atan(c).  19 dependent DFMAs of the
+// library arctangent become 7; the double result rounds to the same float32 (2e6 random ratios: no mismatch).
+constexpr int kAtanDeg = 8, kAtanCells = 33;
+__device__ const double kAtanTab[kAtanDeg][kAtanCells] = {
+    {0.0, 0.031239833430268277, 0.06241880999595735, 0.09347678115858947, 0.12435499454676144, 0.15499674192394097, 0.18534794999569476, 0.21535769969773805, 0.24497866312686414, 0.2741674511196588, 0.3028848683749714, 0.3310960767041321, 0.35877067027057225, 0.38588266939807375, 0.4124104415973873, 0.43833655985795783, 0.4636476090008061, 0.48833395105640554, 0.5123894603107377, 0.5358112379604637, 0.5585993153435624, 0.5807563535676704, 0.6022873461349642, 0.6231993299340659, 0.6435011087932844, 0.6632029927060933, 0.6823165548747481, 0.7008544078844502, 0.7188299996216245, 0.7362574289814281, 0.7531512809621944, 0.7695264804056583, 0.7853981633974483},
+    {1.0, 0.9990243902439024, 0.9961089494163423, 0.9912875121006776, 0.9846153846153846, 0.9761677788369877, 0.9660377358490566, 0.9543336439888164, 0.9411764705882353, 0.9266968325791856, 0.911032028469751, 0.8943231441048035, 0.8767123287671234, 0.8583403185247277, 0.839344262295082, 0.8198558847077663, 0.7999999999999999, 0.7798933739527799, 0.7596439169139466, 0.7393501805054151, 0.7191011235955057, 0.6989761092150172, 0.6790450928381964, 0.6593689632968449, 0.6400000000000001, 0.6209824135839903, 0.6023529411764706, 0.5841414717626925, 0.5663716814159292, 0.5490616621983913, 0.5322245322245323, 0.5158690176322418, 0.5000000000000001},
+    {6.123233995736766e-17, -0.031189054134443818, -0.06201456494420795, -0.09212352484188287, -0.12118343195266268, -0.14889117694367784, -0.17498042007831957, -0.1992271540107127, -0.22145328719723184, -0.24152822423783293, -0.259368549030534, -0.27493602334051587, -0.2882341902796021, -0.2993039166020844, -0.3082182209083579, -0.31507672110466595, -0.31999999999999995, -0.3231241397032081, -0.3245956202837042, -0.3245667218392002, -0.3231915162226992, -0.32062248832251977, -0.3170077886989988, -0.31248909013939336, -0.30720000000000003, -0.3012649671723422, -0.29479861591695505, -0.28790543730916507, -0.28067977132116845, -0.2732060174370548, -0.2655590181577707, -0.2578045669980775, -0.25000000000000006},
+    {-0.3333333333333333, -0.3313849680261942, -0.3255965744411859, -0.3161351980806101, -0.3032693066302534, -0.2873547671703596, -0.26881688015386307, -0.24812989172132635, -0.22579550851482458, -0.20232188302838702, -0.1782043459056766, -0.15390887298395117, -0.12985893504225618, -0.1064260321160807, -0.08392389965092538, -0.06260611727242969, -0.04266666666666668, -0.024242875586053887, -0.00742014386405217, 0.007762137828011928, 0.021304010058125548, 0.03323815990324352, 0.043623288662702764, 0.05253789717845137, 0.06007466666666659, 0.0663355373845743, 0.07142752588370986, 0.07545927443534463, 0.07853829252307457, 0.08076882835302857, 0.08225029603740784, 0.08307617931032006, 0.08333333333333333},
+    {-6.123233995736766e-17, 0.03109782847033422, 0.0612925373519341, 0.0897296352784626, 0.11564771541612685, 0.13841508743188694, 0.1575558835513322, 0.172764162601911, 0.18390584403922366, 0.19100950613396706, 0.1942480277031656, 0.1939136496819828, 0.19038925685573274, 0.1841185660860868, 0.1755775325168041, 0.16524874751139976, 0.1536, 0.14106759025610235, 0.12804448210964214, 0.11487299052889793, 0.10184143725436906, 0.089184060640724, 0.07708341842577798, 0.06567454968857642, 0.05505024000000008, 0.04526683949711949, 0.03635019943918298, 0.02830140572395086, 0.021102089472027713, 0.014719180622174942, 0.009109038982802103, 0.004220948861087882, 2.2962127484012877e-17},
+    {0.2, 0.19708362491474402, 0.18849239252123212, 0.17468634435813643, 0.15638847103500478, 0.13452479177016757, 0.11015087145241911, 0.08437309375308281, 0.05827291058184042, 0.03284107195122972, 0.008926832687212512, -0.012795245362054977, -0.03184060763886972, -0.047913800045917374, -0.06089436996927585, -0.07081332236715301, -0.07782400000000005, -0.082170912261112, -0.08415939044671553, -0.08412816077114978, -0.08242613450013074, -0.07939401190816328, -0.07535073678326323, -0.0705844389824263, -0.06534725632000002, -0.05985331032467883, -0.0542790925861128, -0.04876556844601561, -0.04342139512902429, -0.03832676006858236, -0.03353745621775853, -0.02908891415646316, -0.025000000000000043},
+    {6.123233995736766e-17, -0.03096641713613131, -0.060260921564058025, -0.08635551414720784, -0.10799203289571492, -0.12427516125727307, -0.13472304594573917, -0.13927271513270162, -0.13824402393905807, -0.13227107456173015, -0.12221319485042205, -0.10905837633522088, -0.09383083087154981, -0.07751162873674149, -0.06097797755826145, -0.04496329362748313, -0.030037333333333343, -0.016603590630686293, -0.004910003678043123, 0.004931341550207509, 0.01291956154107462, 0.019138776750677104, 0.023732924964874693, 0.026883292056905875, 0.028789702655999977, 0.029655701234811937, 0.029677611118976936, 0.0290370748743366, 0.02789652856550813, 0.026397012476140822, 0.024657740472706552, 0.022776911998077104, 0.020833333333333343},
+    {-0.14285714285714285, -0.13897938054121464, -0.12768213756913727, -0.10993120326594874, -0.08720236389717116, -0.06130445652312329, -0.0341739304551756, -0.00767210514433281, 0.016587229433004867, 0.03736038077505396, 0.05383747901208601, 0.06564868844587586, 0.07282245349402097, 0.07571029899280447, 0.07489423672083208, 0.07109147681735407, 0.0650678857142857, 0.05756754546991764, 0.04926176605657244, 0.04071759826693892, 0.03238358507275448, 0.02458919992709272, 0.01755399983204303, 0.011402731316661785, 0.0061832189893486125, 0.0018846241885264662, -0.001545572720249459, -0.004186837409626081, -0.006133528134935132, -0.007485570232337259, -0.008341653876645061, -0.008794611007126214, -0.008928571428571435},
+};
+__device__ __forceinline__ double atan_unit(float x, const double* tab) {          // 0 <= x <= 1
+    const int j = __float2int_rn(x * 32.0f);
+    const double h = fma((double)j, -0.03125, (double)x);
+    double r = tab[(kAtanDeg - 1) * kAtanCells + j];
+#pragma unroll
+    for (int k = kAtanDeg - 2; k >= 0; --k) r = fma(r, h, tab[k * kAtanCells + j]);
+    return r;
+}
+__device__ __forceinline__ float atan_f32_tab(float x, const double* tab) {         // x >= 0 (or NaN)
+    if (x <= 1.0f) return (float)atan_unit(x, tab);
+    if (!(x <= 3.0e38f)) return x == x ? 1.57079637050628662109375f : x;            // +inf -> pi/2, NaN stays
+    const double inv = __drcp_rn((double)x);
+    // the reciprocal is not a float: expand around the nearest cell of its float rounding, with the exact offset
+    const float invf = (float)inv;
+    const int j = __float2int_rn(invf * 32.0f);
+    const double h = fma((double)j, -0.03125, inv);
+    double r = tab[(kAtanDeg - 1) * kAtanCells + j];
+#pragma unroll
+    for (int k = kAtanDeg - 2; k >= 0; --k) r = fma(r, h, tab[k * kAtanCells + j]);
+    return (float)(1.5707963267948966 - r);
+}
+
+// Sum of the s_area nearest-beam taps of an area sample, accumulated in tap order (:318-321).  TAPS > 0: unrolled.
+template <int TAPS, bool CLAMP>
+__device__ __forceinline__ float tap_sum(const float* vals, long long fa, long long rsa, int nm1, int s_area) {
+    float acc = 0.f;
+    if (TAPS > 0) {
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t, fa += rsa) acc += vals[CLAMP ? min(max((int)hi32(fa), 0), nm1) : hi32(fa)];
+    } else {
+#pragma unroll 1
+        for (int t = 0; t < s_area; ++t, fa += rsa) acc += vals[CLAMP ? min(max((int)hi32(fa), 0), nm1) : hi32(fa)];
+    }
+    return acc;
+}
+// acc / s_area, correctly rounded: Markstein's three-operation form for a small integer divisor (checked against
+// float division on 9e7 operands for every divisor 2..32), the plain division otherwise.
+__device__ __forceinline__ float div_taps(float acc, float taps_f, float taps_rcp, int s_area) {
+    if (s_area > 32) return __fdiv_rn(acc, taps_f);
+    const float q0 = __fmul_rn(acc, taps_rcp);
+    const float q = fmaf(fmaf(-q0, taps_f, acc), taps_rcp, q0);
+    return q == q ? q : q0;                                   // an infinite sum stays infinite
+}
 // with a single chunk per row there is nothing to rotate
 __device__ __forceinline__ unsigned nchunks_rot(int P, int lane) { return P >= 8 ? ((unsigned)lane >> 2) & 1u : 0u; }
 
 template <typename PhiT>
 __global__ void __launch_bounds__(kScanWarpsMax * 32, 2) cutout_scan_kernel(const CutoutArgs a) {
-    extern __shared__ __align__(16) float smem_f[];          // pairs [N+1] float2 | ranges [N] | per-warp tiles [32][P]
+    extern __shared__ __align__(16) float smem_f[];          // pairs [N+1] float2 | arctangent table | ranges [N] | per-warp tiles [32][P]
     __shared__ double warp_span[kScanWarpsMax];
     __shared__ float warp_min[kScanWarpsMax];
     const Consts c = make_consts<PhiT>(a);
@@ -611,14 +669,18 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 2) cutout_scan_kernel(cons
     const int nm1 = a.N - 1;
     const int P = a.P;
     float2* pairs = reinterpret_cast<float2*>(smem_f);
-    float* vals = smem_f + 2 * ((a.N + 2) & ~1);
+    double* atab = reinterpret_cast<double*>(smem_f + 2 * ((a.N + 2) & ~1));
+    float* vals = reinterpret_cast<float*>(atab + kAtanDeg * kAtanCells);
     float* tile = vals + ((a.N + 3) & ~3) + (size_t)warp * 32 * P;
     const float* scan = a.scans + (size_t)b * a.N;
     const float scale = a.centered ? (float)c.inv_depth : 1.0f;
     const PhiT* phi = reinterpret_cast<const PhiT*>(a.phi);
+    const float* ha_in = a.half_alpha_in ? a.half_alpha_in + (size_t)b * a.M : nullptr;
+    float* ha_out = a.half_alpha_out ? a.half_alpha_out + (size_t)b * a.M : nullptr;
 
     // ---- stage the scan as (C, D) pairs; entry N repeats beam N-1 so index N-1 + 0 reads in bounds ---
     float dmin = 3.0e38f;
+    for (int i = tid; i < kAtanDeg * kAtanCells; i += T) atab[i] = (&kAtanTab[0][0])[i];
     for (int i = tid; i <= a.N; i += T) {
         const float r0 = __ldg(scan + min(i, nm1));
         const float v0 = fminf(r0, 1e6f), v1 = fminf(__ldg(scan + min(i + 1, nm1)), 1e6f);     // finite pairs: inf - inf has no blend
@@ -640,11 +702,13 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 2) cutout_scan_kernel(cons
         const float near = a.half_alpha_in ? 3.0e38f : dmin * 1.001f;
         double best = 0.0;
         for (int m = tid; m < a.M; m += T) {
-            if (fmaxf(vals[m * a.stride], 1e-2f) <= near) {
-                RowGeom g;
-                float two_ha;
-                row_basics<PhiT>(a, b, 0, m, g, two_ha);
-                const double span = __dsub_rn(sample_index(g.start, g.step, P - 1, c), sample_index(g.start, g.step, 0, c));
+            const int i = m * a.stride;
+            const float dc = fmaxf(vals[i], 1e-2f);
+            if (dc <= near) {
+                const float ha = ha_in ? __ldg(ha_in + m) : atan_f32_tab(__fdiv_rn(a.half_width, dc), atab);
+                const float step = __fdiv_rn(2.0f * ha, (float)(P - 1));
+                const double start = (double)(phi[i] - (PhiT)ha);
+                const double span = __dsub_rn(sample_index(start, step, P - 1, c), sample_index(start, step, 0, c));
                 if (span > best) best = span;
             }
         }
@@ -673,10 +737,8 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 2) cutout_scan_kernel(cons
     const int nchunks = P >> 2;
     const unsigned long long limit = ((unsigned long long)(unsigned)nm1 << 32) + 0x100ull;
     const double span_unit = (double)(P - 1) * c.inv_pitch;
-    const float* ha_in = a.half_alpha_in ? a.half_alpha_in + (size_t)b * a.M : nullptr;
-    float* ha_out = a.half_alpha_out ? a.half_alpha_out + (size_t)b * a.M : nullptr;
     float* out_b = a.out + (size_t)b * a.M * P;
-    const float taps_f = (float)s_area;
+    const float taps_f = (float)s_area, taps_rcp = s_area > 0 ? 1.0f / (float)s_area : 0.f;
     bool store_pending = false;
 
     for (int m0 = warp * 32; m0 < a.M; m0 += T) {
@@ -689,7 +751,7 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 2) cutout_scan_kernel(cons
             const int m = m0 + lane, i = m * a.stride;
             const float d = vals[i];
             const float ratio = __fdiv_rn(a.half_width, fmaxf(d, 1e-2f));
-            const float ha = ha_in ? __ldg(ha_in + m) : atan_f32(ratio);                       // :279
+            const float ha = ha_in ? __ldg(ha_in + m) : atan_f32_tab(ratio, atab);             // :279
             if (ha_out) ha_out[m] = ha;
             const float two_ha = 2.0f * ha;
             const float step = __fdiv_rn(two_ha, (float)(P - 1));                              // :282
@@ -744,17 +806,23 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 2) cutout_scan_kernel(cons
             float* row = tile + src * P;
             for (int k = lane; k < P; k += 32) {
                 const long long fx = rb + (long long)k * rs;
-                long long fa = rb + (long long)(k * s_area) * rsa + 0x80000000ll;              // +0.5: nearest tap
+                const long long fa = rb + (long long)(k * s_area) * rsa + 0x80000000ll;        // +0.5: nearest tap
                 const int lo = (int)hi32(fx);
                 float v = r_pad;
-                if (r_inside) {
-                    float acc = 0.f;
-                    for (int t = 0; t < s_area; ++t, fa += rsa) acc += vals[hi32(fa)];
-                    v = fminf(fmaxf(fmaf(__fdiv_rn(acc, taps_f), scale, r_bias), r_lo), r_hi);
-                } else if ((unsigned)lo < (unsigned)nm1 || (lo == nm1 && (unsigned)fx == 0u)) {
-                    float acc = 0.f;
-                    for (int t = 0; t < s_area; ++t, fa += rsa) acc += vals[min(max((int)hi32(fa), 0), nm1)];
-                    v = fminf(fmaxf(fmaf(__fdiv_rn(acc, taps_f), scale, r_bias), r_lo), r_hi);
+                if (r_inside || (unsigned)lo < (unsigned)nm1 || (lo == nm1 && (unsigned)fx == 0u)) {
+                    float acc;
+                    if (!r_inside) acc = tap_sum<0, true>(vals, fa, rsa, nm1, s_area);
+                    else switch (s_area) {                                                    // warp-uniform
+                        case 2: acc = tap_sum<2, false>(vals, fa, rsa, nm1, s_area); break;
+                        case 3: acc = tap_sum<3, false>(vals, fa, rsa, nm1, s_area); break;
+                        case 4: acc = tap_sum<4, false>(vals, fa, rsa, nm1, s_area); break;
+                        case 5: acc = tap_sum<5, false>(vals, fa, rsa, nm1, s_area); break;
+                        case 6: acc = tap_sum<6, false>(vals, fa, rsa, nm1, s_area); break;
+                        case 7: acc = tap_sum<7, false>(vals, fa, rsa, nm1, s_area); break;
+                        case 8: acc = tap_sum<8, false>(vals, fa, rsa, nm1, s_area); break;
+                        default: acc = tap_sum<0, false>(vals, fa, rsa, nm1, s_area); break;
+                    }
+                    v = fminf(fmaxf(fmaf(div_taps(acc, taps_f, taps_rcp, s_area), scale, r_bias), r_lo), r_hi);
                 }
                 row[k] = v;
             }
@@ -779,15 +847,17 @@ int scan_warps_for(int M) {
         forced = e ? atoi(e) : 0;
     }
     if (forced > 0 && forced <= kScanWarpsMax) return forced;
-    const int groups = (M + 31) / 32;
-    const int rounds = (groups + kScanWarpsMax - 1) / kScanWarpsMax;
-    return (groups + rounds - 1) / rounds;
+    // small CTAs: five 4-warp CTAs fit an SM (43 KB each), and their set-up phases overlap the others' sample loops
+    // (measured on JRDB- and DROW-shaped scans: 4 warps > 5 > 6 > 8 > 12)
+    (void)M;
+    return 4;
 }
 
 template <typename PhiT>
 bool launch_cutout_scan(const CutoutArgs& a, cudaStream_t stream, int* status) {
     const int warps = scan_warps_for(a.M);
-    const size_t smem = ((size_t)2 * ((a.N + 2) & ~1) + (size_t)((a.N + 3) & ~3) + (size_t)warps * 32 * a.P) * sizeof(float);
+    const size_t smem = ((size_t)2 * ((a.N + 2) & ~1) + (size_t)((a.N + 3) & ~3) + (size_t)warps * 32 * a.P) * sizeof(float) +
+                        sizeof(double) * kAtanDeg * kAtanCells;
     if (smem > 110 * 1024) return false;
     static bool attr_set[2][64] = {{false}};
     int dev = 0;
