@@ -180,7 +180,7 @@ POF_API int pof_nms_centers(const void* scan, int scan_is_f64, const void* phi, 
  *
  *    split_parts = 3: out_split rows are [hi | lo | hi], lo = x - hi exact (operand of a cuDNN TF32
  *    convolution against [w_hi | w_hi | w_lo]); split_parts = 2: [hi | lo], lo rounded to TF32 (operand
- *    of pof_conv_tc_fwd).
+ *    of pof_conv_tc_fwd); split_parts = POF_SPLIT_F16: [hi | lo] as binary16 (operand of pof_conv_tc_f16_fwd).
  *
  *    pof_act_fwd         y [rows_in, C] -> out_plain [rows_in/pool, C] and/or
  *                        out_split [rows_in/pool, split_parts*C]; bias [C] or NULL; pool in {1,2}
@@ -189,12 +189,13 @@ POF_API int pof_nms_centers(const void* scan, int scan_is_f64, const void* phi, 
  *    pof_conv_first_fwd  cutouts [M, P] (x) weight [C, 3], bias [C] -> [M*P, C] / [M*P, 3C]:
  *                        the 1 -> C, k = 3, zero-padded first layer + LeakyReLU (+ split).
  * ------------------------------------------------------------------------- */
+#define POF_SPLIT_F16 16   /* split_parts: out_split rows are [hi | lo] in binary16 (operand of pof_conv_tc_f16_fwd) */
 POF_API int pof_act_fwd(const float* y, const float* bias, long long rows_in, int C, int pool,
-                        float slope, float* out_plain, float* out_split, int split_parts, void* stream);
+                        float slope, float* out_plain, void* out_split, int split_parts, void* stream);
 
 POF_API int pof_conv_first_fwd(const float* cutouts, const float* weight, const float* bias,
                                long long M, int P, int C, float slope,
-                               float* out_plain, float* out_split, int split_parts, void* stream);
+                               float* out_plain, void* out_split, int split_parts, void* stream);
 
 /*    pof_head_fwd        the tail of DROW._forward_fused_cutout (dr_spaam.py:110-114): y [M, L, C] raw
  *                        output of the last convolution -> +bias, LeakyReLU -> avg_pool1d over L ->
@@ -223,6 +224,19 @@ POF_API int pof_conv_tc_fwd(const float* a_split, const float* w_split, const fl
                             long long Mcut, int LA, int Lout, int Cin, int Cout, int taps, int pad,
                             int pool, float slope, float* out_plain, float* out_split,
                             int* status, int chain_channels, void* stream);
+
+/*    pof_conv_tc_f16_fwd the same convolution with binary16 hi / lo parts (tcgen05 kind::f16: twice the
+ *                        tensor-core rate, half the operand bytes, the same 22 significant bits).
+ *                        a_split [Mcut, LA, 2 Cin] and w_split [taps, 2, Cout, Cin] are binary16
+ *                        (pof_act_fwd / pof_conv_first_fwd with split_parts = POF_SPLIT_F16); the caller
+ *                        multiplies a layer's weights by a power of two before splitting them (so that hi
+ *                        and lo are normal binary16 numbers) and passes the inverse power as `out_scale`,
+ *                        which the epilogue applies to the sum before the bias.  out_split is binary16
+ *                        [.., 2 Cout]; an activation beyond 65504 sets *status = 16.  Cin % 32 == 0.        */
+POF_API int pof_conv_tc_f16_fwd(const void* a_split, const void* w_split, const float* bias,
+                                long long Mcut, int LA, int Lout, int Cin, int Cout, int taps, int pad,
+                                int pool, float slope, float out_scale, float* out_plain, void* out_split,
+                                int* status, int chain_channels, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * 5. Windowed patch correlation of the scan-pair flow prototype

@@ -43,6 +43,8 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_int, c_void_p]),
     "pof_conv_tc_fwd": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "pof_conv_tc_f16_fwd": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pof_head_fwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_int,
                              c_void_p, c_void_p]),
     "pof_patch_corr_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -19,6 +19,8 @@
 //   pof_conv_first_fwd   the 1 -> C first layer (k = 3, zero padding) straight from the cutouts, fused
 //                        with bias + LeakyReLU + split: cuDNN needs 2.4 ms for these 3 GFLOP.
 // Both are pure streaming kernels (HBM bound): 128-bit accesses, grid-stride.
+#include <cuda_fp16.h>
+
 #include "pof_common.cuh"
 
 namespace pof {
@@ -34,8 +36,19 @@ __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? 
 
 // parts = 3: [hi | lo | hi] with the exact remainder (operand of a cuDNN TF32 convolution against
 //            [w_hi | w_hi | w_lo]);  parts = 2: [hi | lo] with lo rounded to TF32 (operand of pof_conv_tc_fwd).
-__device__ __forceinline__ void emit(float4 v, size_t row, int c, int C, float* plain, float* split, int parts) {
+//            parts = POF_SPLIT_F16: [hi | lo] in binary16 (operand of pof_conv_tc_f16_fwd).
+__device__ __forceinline__ void emit(float4 v, size_t row, int c, int C, float* plain, void* split_, int parts) {
     if (plain) *reinterpret_cast<float4*>(plain + row * C + c) = v;
+    if (split_ && parts == POF_SPLIT_F16) {
+        const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+        __half* base = reinterpret_cast<__half*>(split_) + row * 2 * (size_t)C + c;
+        *reinterpret_cast<uint2*>(base) = make_uint2(*reinterpret_cast<const unsigned*>(&h01), *reinterpret_cast<const unsigned*>(&h23));
+        *reinterpret_cast<uint2*>(base + C) = make_uint2(*reinterpret_cast<const unsigned*>(&l01), *reinterpret_cast<const unsigned*>(&l23));
+        return;
+    }
+    float* split = reinterpret_cast<float*>(split_);
     if (split) {
         const float4 hi = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
         float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
@@ -52,7 +65,7 @@ __device__ __forceinline__ void emit(float4 v, size_t row, int c, int C, float* 
 
 template <int POOL>
 __global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ y, const float* __restrict__ bias, float slope,
-                                                  int C, long long rows_out, float* plain, float* split, int parts) {
+                                                  int C, long long rows_out, float* plain, void* split, int parts) {
     const int c4n = C >> 2;
     const long long total = rows_out * c4n;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -72,7 +85,7 @@ __global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ y, c
 // out[m, l, c] = lrelu(b[c] + sum_k w[c, k] * x[m, l + k - 1]),  x = cutouts [M, P], zero padded
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float slope, int P, int C,
-                                                         long long rows /* M*P */, float* plain, float* split, int parts) {
+                                                         long long rows /* M*P */, float* plain, void* split, int parts) {
     extern __shared__ float wsm[];                 // [C][4]: w0, w1, w2, bias
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         wsm[4 * i] = w[3 * i]; wsm[4 * i + 1] = w[3 * i + 1]; wsm[4 * i + 2] = w[3 * i + 2]; wsm[4 * i + 3] = bias[i];
@@ -150,14 +163,15 @@ unsigned stream_grid(long long items, int threads) {
 extern "C" {
 
 int pof_act_fwd(const float* y, const float* bias, long long rows_in, int C, int pool, float slope, float* out_plain,
-                float* out_split, int split_parts, void* stream_) {
+                void* out_split, int split_parts, void* stream_) {
     using namespace pof;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (rows_in == 0) return POF_OK;
     POF_REQUIRE(y && (out_plain || out_split), POF_ERR_NULL_POINTER, "pof_act_fwd: null input or no output");
     POF_REQUIRE(C >= 4 && (C % 4) == 0, POF_ERR_BAD_SHAPE, "pof_act_fwd: C must be a multiple of 4 (got %d)", C);
     POF_REQUIRE(pool == 1 || pool == 2, POF_ERR_UNSUPPORTED, "pof_act_fwd: pool must be 1 or 2 (got %d)", pool);
-    POF_REQUIRE(split_parts == 2 || split_parts == 3, POF_ERR_BAD_PARAM, "pof_act_fwd: split_parts must be 2 or 3");
+    POF_REQUIRE(split_parts == 2 || split_parts == 3 || split_parts == POF_SPLIT_F16, POF_ERR_BAD_PARAM,
+                "pof_act_fwd: split_parts must be 2, 3 or POF_SPLIT_F16");
     POF_REQUIRE(rows_in > 0 && rows_in % pool == 0, POF_ERR_BAD_SHAPE, "pof_act_fwd: rows_in must be a positive multiple of pool");
     const uintptr_t al = reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias) |
                          reinterpret_cast<uintptr_t>(out_plain) | reinterpret_cast<uintptr_t>(out_split);
@@ -171,7 +185,7 @@ int pof_act_fwd(const float* y, const float* bias, long long rows_in, int C, int
 }
 
 int pof_conv_first_fwd(const float* cutouts, const float* weight, const float* bias, long long M, int P, int C, float slope,
-                       float* out_plain, float* out_split, int split_parts, void* stream_) {
+                       float* out_plain, void* out_split, int split_parts, void* stream_) {
     using namespace pof;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (M == 0) return POF_OK;
@@ -180,7 +194,8 @@ int pof_conv_first_fwd(const float* cutouts, const float* weight, const float* b
                 "pof_conv_first_fwd: bad shape M=%lld P=%d C=%d", M, P, C);
     const uintptr_t al = reinterpret_cast<uintptr_t>(out_plain) | reinterpret_cast<uintptr_t>(out_split);
     POF_REQUIRE((al & 15) == 0, POF_ERR_BAD_PARAM, "pof_conv_first_fwd: outputs must be 16-byte aligned");
-    POF_REQUIRE(split_parts == 2 || split_parts == 3, POF_ERR_BAD_PARAM, "pof_conv_first_fwd: split_parts must be 2 or 3");
+    POF_REQUIRE(split_parts == 2 || split_parts == 3 || split_parts == POF_SPLIT_F16, POF_ERR_BAD_PARAM,
+                "pof_conv_first_fwd: split_parts must be 2, 3 or POF_SPLIT_F16");
     const long long rows = M * P;
     const unsigned grid = stream_grid(rows * (C >> 2), 256);
     conv_first_kernel<<<grid, 256, (size_t)C * 4 * sizeof(float), stream>>>(cutouts, weight, bias, slope, P, C, rows, out_plain,

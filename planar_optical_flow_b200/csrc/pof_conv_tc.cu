@@ -35,7 +35,17 @@
 //              optional hi/lo split for the next layer, 128-bit stores.
 // Every mbarrier wait is bounded: on a timeout the role records an error code and leaves, so a bug
 // surfaces as a status, never as a hung GPU.
+//
+// F16 = true is the same pipeline on kind::f16: x = hi + lo with BOTH parts binary16 (11-bit significands like
+// TF32, so the three products carry the same 22 bits), at twice the tensor-core rate and half the operand
+// bytes - a 64-byte swizzled row now holds 32 channels instead of 16, which halves the shared-memory traffic
+// that bounds the narrow layers and the HBM traffic of the split activations.  binary16's range is handled by
+// scaling, not by a second accumulator: the weights of a layer are multiplied by a power of two that brings
+// their largest magnitude to 2^13 (hi and lo are then both normal numbers) and the epilogue multiplies the
+// sum by the inverse power (exact); activations are stored unscaled - below 2^-3 their lo part is subnormal,
+// i.e. an ABSOLUTE error of 2^-25 on an O(1) activation - and an activation beyond 65504 raises status 16.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "pof_common.cuh"
 
@@ -44,8 +54,8 @@ namespace {
 
 constexpr int kThreads = 384;
 constexpr int kTileM = 128;
-constexpr int kKBlock = 16;                    // fp32 elements per 64-byte swizzled row
-constexpr int kRowBytes = kKBlock * 4;
+constexpr int kRowBytes = 64;                  // one swizzled operand row: 16 fp32 or 32 binary16 channels
+template <bool F16> struct KBlock { static constexpr int value = F16 ? 32 : 16; };
 constexpr int kATile = kTileM * kRowBytes;     // bytes of one A operand tile (hi or lo)
 constexpr int kTmemCols = 512;
 constexpr long long kWaitLimit = 2000000000LL; // ~1 s of SM clocks
@@ -55,6 +65,7 @@ constexpr long long kWaitLimit = 2000000000LL; // ~1 s of SM clocks
 // instead of 96, which is what lets it run at full rate next to the TMA fill (shared memory moves 128 B/clk).
 constexpr int kRingBytes = 184 * 1024;                 // operand ring
 constexpr int kStagePitch = 36;                        // floats per staged output row: 32 columns + 4 (conflict-free 16-byte accesses)
+constexpr int kStagePitchH = 20;                       // words per staged binary16 row: 16 + 4
 constexpr int kStagingBytes = 8 * 32 * kStagePitch * 4;   // one 32 x 32 transposition buffer per epilogue warp
 
 template <int BN, int CG>
@@ -75,9 +86,10 @@ struct Params {
     int Cin, Cout, taps, pad, pool;
     int chain;           // k-blocks accumulated in tensor memory before a promotion to registers
     float slope;
+    float out_scale;     // multiplies the accumulated sum before the bias (F16: the inverse of the weights' power of two)
     const float* bias;   // [Cout] or null
     float* out_plain;    // [Mcut * Lout / pool, Cout] or null
-    float* out_split;    // [Mcut * Lout / pool, 2 Cout] = [hi | lo] or null
+    void* out_split;     // [Mcut * Lout / pool, 2 Cout] = [hi | lo] (fp32, or binary16 when F16) or null
     int* status;         // device int, 0 = ok
 };
 
@@ -136,9 +148,26 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned addr) {
            ((unsigned long long)(8 * kRowBytes >> 4) << 32) /* SBO */ | (1ull << 46) /* descriptor version (sm_100) */ |
            (4ull << 61) /* SWIZZLE_64B */;
 }
-// Instruction descriptor: D = fp32, A = B = TF32, both K-major, M = 128, N = bn.
-__device__ __forceinline__ unsigned umma_idesc(int bn, int m) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(bn >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+// Instruction descriptor: D = fp32, A = B = TF32 (format 2) or binary16 (format 0), both K-major, M = m, N = bn.
+__device__ __forceinline__ unsigned umma_idesc(int bn, int m, bool f16) {
+    const unsigned fmt = f16 ? 0u : 2u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(bn >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(unsigned tmem_d, unsigned long long a, unsigned long long b, unsigned idesc, unsigned acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(unsigned tmem_d, unsigned long long a, unsigned long long b, unsigned idesc, unsigned acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
 }
 __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long a, unsigned long long b, unsigned idesc, unsigned acc) {
     asm volatile(
@@ -232,10 +261,11 @@ __device__ __forceinline__ float tf32_rn(float x) {
 }
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
-template <int BN, int CG>
+template <int BN, int CG, bool F16>
 __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Params p) {
     using C = Cfg<BN, CG>;
+    constexpr int kKBlock = KBlock<F16>::value;
     extern __shared__ unsigned char smem_raw[];
     const unsigned base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const unsigned bars = base + C::kStages * C::kStage;       // full[S] | empty[S] | tfull[2] | tempty[2] | tmem ptr
@@ -310,7 +340,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         } else if (warp == 1 && lane == 0 && rank == 0) {
             // ------------------------------------------------------------------ MMA issuer (the pair's leader only)
-            const unsigned idesc = umma_idesc(BN, kTileM * CG);
+            const unsigned idesc = umma_idesc(BN, kTileM * CG, F16);
             long long it = 0, ic = 0;                                  // k-blocks, chains issued so far
             bool ok = true;
             for (long long tile = first_tile; tile < n_tiles && ok; tile += tile_stride) {
@@ -326,23 +356,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const unsigned long long a_hi = umma_desc(st), a_lo = umma_desc(st + kATile);
                     const unsigned long long b_hi = umma_desc(st + 2 * kATile), b_lo = umma_desc(st + 2 * kATile + C::kBTile);
                     const unsigned d = tmem_base + (unsigned)(buf * BN);
-                    constexpr int kSteps = kKBlock / 8;                                    // K = 8 per tf32 MMA = 32 B of the row
+                    constexpr int kSteps = 2;                                              // one MMA consumes 32 B of the row: K = 8 (tf32) or 16 (f16)
+                    auto mma = [&](unsigned long long a, unsigned long long b, unsigned acc) {
+                        if (CG == 1) { if (F16) umma_f16(d, a, b, idesc, acc); else umma_tf32(d, a, b, idesc, acc); }
+                        else { if (F16) umma_f16_pair(d, a, b, idesc, acc); else umma_tf32_pair(d, a, b, idesc, acc); }
+                    };
+#pragma unroll
+                    for (int k = 0; k < kSteps; ++k) mma(a_lo + 2 * k, b_hi + 2 * k, k > 0 || !first);   // corrections first
+#pragma unroll
+                    for (int k = 0; k < kSteps; ++k) mma(a_hi + 2 * k, b_lo + 2 * k, 1);
+#pragma unroll
+                    for (int k = 0; k < kSteps; ++k) mma(a_hi + 2 * k, b_hi + 2 * k, 1);                 // main product last
                     if (CG == 1) {
-#pragma unroll
-                        for (int k = 0; k < kSteps; ++k) umma_tf32(d, a_lo + 2 * k, b_hi + 2 * k, idesc, k > 0 || !first);   // corrections first
-#pragma unroll
-                        for (int k = 0; k < kSteps; ++k) umma_tf32(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
-#pragma unroll
-                        for (int k = 0; k < kSteps; ++k) umma_tf32(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);       // main product last
                         umma_commit(empty(s));
                         if (last) { umma_commit(tfull(buf)); ++ic; }
                     } else {
-#pragma unroll
-                        for (int k = 0; k < kSteps; ++k) umma_tf32_pair(d, a_lo + 2 * k, b_hi + 2 * k, idesc, k > 0 || !first);
-#pragma unroll
-                        for (int k = 0; k < kSteps; ++k) umma_tf32_pair(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
-#pragma unroll
-                        for (int k = 0; k < kSteps; ++k) umma_tf32_pair(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
                         umma_commit_pair(empty(s));                      // both CTAs' producers may refill their slot
                         if (last) { umma_commit_pair(tfull(buf)); ++ic; }  // both CTAs' epilogues may read their rows
                     }
@@ -415,6 +443,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 __syncwarp();
             };
+            // binary16 rows: lane l's 16 packed words -> rows of 64 bytes at dst + j * ld (in halves)
+            auto flush_h = [&](const unsigned (&w)[16], __half* dst, long long ld) {
+                unsigned* stw = reinterpret_cast<unsigned*>(stg);
+#pragma unroll
+                for (int k = 0; k < 16; k += 4)
+                    *reinterpret_cast<uint4*>(stw + lane * kStagePitchH + k) = make_uint4(w[k], w[k + 1], w[k + 2], w[k + 3]);
+                __syncwarp();
+                for (int j = lane >> 2; j < nrows; j += 8) {
+                    const int src = p.pool == 2 ? 2 * j : j;
+                    if ((vmask >> src) & 1u)
+                        st_stream_f4(reinterpret_cast<float4*>(dst + j * ld + (lane & 3) * 8),
+                                     *reinterpret_cast<const float4*>(stw + src * kStagePitchH + (lane & 3) * 4));
+                }
+                __syncwarp();
+            };
+            bool overflow = false;
 #pragma unroll
             for (int g = 0; g < C::kAcc / 32; ++g) {
                 float o[32];
@@ -425,21 +469,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         float v = acc[g * 32 + k + i];
+                        if (F16) v *= p.out_scale;                      // a power of two: exact
                         if (p.pool == 2) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
                         o[k + i] = lrelu(v + bb[i], p.slope);
                     }
                 }
                 if (p.out_plain) flush(o, p.out_plain + orow0 * p.Cout + cbase + g * 32, p.Cout);
                 if (p.out_split) {
-                    float hi[32];
+                    if (F16) {
+                        __half* os = reinterpret_cast<__half*>(p.out_split) + orow0 * 2 * p.Cout + cbase + g * 32;
+                        unsigned hi[16], lo[16];
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) hi[k] = tf32_rn(o[k]);
-                    flush(hi, p.out_split + orow0 * 2 * p.Cout + cbase + g * 32, 2 * p.Cout);
+                        for (int k = 0; k < 16; ++k) {
+                            const __half2 h2 = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
+                            const float2 hf = __half22float2(h2);
+                            const __half2 l2 = __floats2half2_rn(o[2 * k] - hf.x, o[2 * k + 1] - hf.y);
+                            overflow |= !(fabsf(o[2 * k]) <= 65504.f) || !(fabsf(o[2 * k + 1]) <= 65504.f);
+                            hi[k] = *reinterpret_cast<const unsigned*>(&h2);
+                            lo[k] = *reinterpret_cast<const unsigned*>(&l2);
+                        }
+                        flush_h(hi, os, 2 * p.Cout);
+                        flush_h(lo, os + p.Cout, 2 * p.Cout);
+                    } else {
+                        float* os = reinterpret_cast<float*>(p.out_split);
+                        float hi[32];
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) o[k] = tf32_rn(o[k] - hi[k]);
-                    flush(o, p.out_split + orow0 * 2 * p.Cout + p.Cout + cbase + g * 32, 2 * p.Cout);
+                        for (int k = 0; k < 32; ++k) hi[k] = tf32_rn(o[k]);
+                        flush(hi, os + orow0 * 2 * p.Cout + cbase + g * 32, 2 * p.Cout);
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) o[k] = tf32_rn(o[k] - hi[k]);
+                        flush(o, os + orow0 * 2 * p.Cout + p.Cout + cbase + g * 32, 2 * p.Cout);
+                    }
                 }
             }
+            if (F16 && __any_sync(0xffffffffu, overflow && valid) && lane == 0) atomicCAS(p.status, 0, 16);   // beyond binary16
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -469,48 +532,57 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-template <int BN, int CG>
+template <int BN, int CG, bool F16>
 int launch(const CUtensorMap& ma, const CUtensorMap& mw, const Params& p, cudaStream_t stream) {
     using C = Cfg<BN, CG>;
     static bool attr_set[64] = {false};
     int dev = 0;
     POF_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && !attr_set[dev]) {
-        POF_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+        POF_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, CG, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
         attr_set[dev] = true;
     }
     const long long tiles = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;
     const long long groups = sm_count() / CG;
     const int grid = CG * (int)(tiles < groups ? tiles : groups);
-    conv_tc_kernel<BN, CG><<<grid, kThreads, C::kSmem, stream>>>(ma, mw, p);
+    conv_tc_kernel<BN, CG, F16><<<grid, kThreads, C::kSmem, stream>>>(ma, mw, p);
     POF_CUDA(cudaGetLastError());
     return POF_OK;
 }
 
-}  // namespace
-}  // namespace pof
+template <bool F16>
+int launch_any(int bn, int cg, const CUtensorMap& ma, const CUtensorMap& mw, const Params& p, cudaStream_t stream) {
+    if (cg == 2) {
+        if (bn == 256) return launch<256, 2, F16>(ma, mw, p, stream);
+        if (bn == 128) return launch<128, 2, F16>(ma, mw, p, stream);
+        return launch<64, 2, F16>(ma, mw, p, stream);
+    }
+    if (bn == 256) return launch<256, 1, F16>(ma, mw, p, stream);
+    if (bn == 128) return launch<128, 1, F16>(ma, mw, p, stream);
+    return launch<64, 1, F16>(ma, mw, p, stream);
+}
 
-extern "C" {
-
-int pof_conv_tc_fwd(const float* a_split, const float* w_split, const float* bias, long long Mcut, int LA, int Lout, int Cin,
-                    int Cout, int taps, int pad, int pool, float slope, float* out_plain, float* out_split, int* status,
-                    int chain_channels, void* stream_) {
-    using namespace pof;
-    cudaStream_t stream = (cudaStream_t)stream_;
+// f16 = false: fp32 containers holding TF32 hi / lo parts; f16 = true: binary16 hi / lo parts.
+int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float* bias, long long Mcut, int LA, int Lout, int Cin,
+                int Cout, int taps, int pad, int pool, float slope, float out_scale, float* out_plain, void* out_split, int* status,
+                int chain_channels, cudaStream_t stream) {
     if (Mcut == 0) return POF_OK;
+    const int kb = f16 ? KBlock<true>::value : KBlock<false>::value;
+    const int esize = f16 ? 2 : 4;
     POF_REQUIRE(a_split && w_split && status && (out_plain || out_split), POF_ERR_NULL_POINTER, "pof_conv_tc_fwd: null pointer");
     POF_REQUIRE(Mcut > 0 && Mcut < (1ll << 31) && LA >= 1 && Lout >= 1 && Lout <= 128 && LA <= 256, POF_ERR_BAD_SHAPE,
                 "pof_conv_tc_fwd: bad shape Mcut=%lld LA=%d Lout=%d", Mcut, LA, Lout);
-    POF_REQUIRE(Cin >= kKBlock && Cin % kKBlock == 0, POF_ERR_BAD_SHAPE, "pof_conv_tc_fwd: Cin must be a multiple of %d (got %d)", kKBlock, Cin);
+    POF_REQUIRE(Cin >= kb && Cin % kb == 0, POF_ERR_BAD_SHAPE, "pof_conv_tc_fwd: Cin must be a multiple of %d (got %d)", kb, Cin);
     const int cg = (chain_channels & POF_CONV_TC_SINGLE_CTA) ? 1 : 2;      // high flag bit: tuning / tests only
     chain_channels &= ~POF_CONV_TC_SINGLE_CTA;
     if (chain_channels == 0) chain_channels = 64;
-    POF_REQUIRE(chain_channels > 0 && chain_channels % kKBlock == 0, POF_ERR_BAD_PARAM,
-                "pof_conv_tc_fwd: chain_channels must be a multiple of %d (got %d)", kKBlock, chain_channels);
+    POF_REQUIRE(chain_channels > 0 && chain_channels % kb == 0, POF_ERR_BAD_PARAM,
+                "pof_conv_tc_fwd: chain_channels must be a multiple of %d (got %d)", kb, chain_channels);
     POF_REQUIRE(Cout == 64 || Cout == 128 || (Cout >= 256 && Cout % 256 == 0), POF_ERR_BAD_SHAPE,
                 "pof_conv_tc_fwd: Cout must be 64, 128 or a multiple of 256 (got %d)", Cout);
     POF_REQUIRE(taps >= 1 && pad >= 0 && pad < taps, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: bad taps/pad %d/%d", taps, pad);
     POF_REQUIRE(pool == 1 || (pool == 2 && Lout % 2 == 0), POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: pool must be 1, or 2 with even Lout");
+    POF_REQUIRE(out_scale > 0.f, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: out_scale must be positive");
     const uintptr_t al = reinterpret_cast<uintptr_t>(a_split) | reinterpret_cast<uintptr_t>(w_split) |
                          reinterpret_cast<uintptr_t>(out_plain) | reinterpret_cast<uintptr_t>(out_split) |
                          reinterpret_cast<uintptr_t>(bias);
@@ -526,38 +598,52 @@ int pof_conv_tc_fwd(const float* a_split, const float* w_split, const float* bia
     p.tiles_m = (Mcut + p.mt - 1) / p.mt;
     p.tiles_n = Cout / bn;
     p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.pad = pad; p.pool = pool; p.slope = slope;
-    p.chain = chain_channels / kKBlock;
+    p.chain = chain_channels / kb;
+    p.out_scale = out_scale;
     p.bias = bias; p.out_plain = out_plain; p.out_split = out_split; p.status = status;
+    const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
 
     alignas(64) CUtensorMap ma, mw;
-    {   // A: [Mcut][LA][2 Cin] fp32, box (16 channels, Lout rows, mt cutouts); out-of-range rows read as zero
+    {   // A: [Mcut][LA][2 Cin], box (one 64-byte row of channels, Lout rows, mt cutouts); out-of-range rows read as zero
         const cuuint64_t dims[3] = {(cuuint64_t)(2 * Cin), (cuuint64_t)LA, (cuuint64_t)Mcut};
-        const cuuint64_t strides[2] = {(cuuint64_t)(2 * Cin) * 4, (cuuint64_t)LA * (2 * Cin) * 4};
-        const cuuint32_t box[3] = {(cuuint32_t)kKBlock, (cuuint32_t)Lout, (cuuint32_t)p.mt};
+        const cuuint64_t strides[2] = {(cuuint64_t)(2 * Cin) * esize, (cuuint64_t)LA * (2 * Cin) * esize};
+        const cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)Lout, (cuuint32_t)p.mt};
         const cuuint32_t es[3] = {1, 1, 1};
-        const CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a_split), dims, strides, box, es,
+        const CUresult r = enc(&ma, dt, 3, const_cast<void*>(a_split), dims, strides, box, es,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         POF_REQUIRE(r == CUDA_SUCCESS, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
     }
-    {   // W: [taps][2][Cout][Cin] fp32 seen as a [taps * 2 * Cout, Cin] matrix, box (16 channels, bn rows)
+    {   // W: [taps][2][Cout][Cin] seen as a [taps * 2 * Cout, Cin] matrix, box (one 64-byte row of channels, bn rows)
         const cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)taps * 2 * Cout};
-        const cuuint64_t strides[1] = {(cuuint64_t)Cin * 4};
-        const cuuint32_t box[2] = {(cuuint32_t)kKBlock, (cuuint32_t)(bn / cg)};            // each CTA of a pair loads its half
+        const cuuint64_t strides[1] = {(cuuint64_t)Cin * esize};
+        const cuuint32_t box[2] = {(cuuint32_t)kb, (cuuint32_t)(bn / cg)};            // each CTA of a pair loads its half
         const cuuint32_t es[2] = {1, 1};
-        const CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w_split), dims, strides, box, es,
+        const CUresult r = enc(&mw, dt, 2, const_cast<void*>(w_split), dims, strides, box, es,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         POF_REQUIRE(r == CUDA_SUCCESS, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
     }
-    if (cg == 2) {
-        if (bn == 256) return launch<256, 2>(ma, mw, p, stream);
-        if (bn == 128) return launch<128, 2>(ma, mw, p, stream);
-        return launch<64, 2>(ma, mw, p, stream);
-    }
-    if (bn == 256) return launch<256, 1>(ma, mw, p, stream);
-    if (bn == 128) return launch<128, 1>(ma, mw, p, stream);
-    return launch<64, 1>(ma, mw, p, stream);
+    return f16 ? launch_any<true>(bn, cg, ma, mw, p, stream) : launch_any<false>(bn, cg, ma, mw, p, stream);
+}
+
+}  // namespace
+}  // namespace pof
+
+extern "C" {
+
+int pof_conv_tc_fwd(const float* a_split, const float* w_split, const float* bias, long long Mcut, int LA, int Lout, int Cin,
+                    int Cout, int taps, int pad, int pool, float slope, float* out_plain, float* out_split, int* status,
+                    int chain_channels, void* stream_) {
+    return pof::conv_tc_any(false, a_split, w_split, bias, Mcut, LA, Lout, Cin, Cout, taps, pad, pool, slope, 1.0f, out_plain,
+                            out_split, status, chain_channels, (cudaStream_t)stream_);
+}
+
+int pof_conv_tc_f16_fwd(const void* a_split, const void* w_split, const float* bias, long long Mcut, int LA, int Lout, int Cin,
+                        int Cout, int taps, int pad, int pool, float slope, float out_scale, float* out_plain, void* out_split,
+                        int* status, int chain_channels, void* stream_) {
+    return pof::conv_tc_any(true, a_split, w_split, bias, Mcut, LA, Lout, Cin, Cout, taps, pad, pool, slope, out_scale, out_plain,
+                            out_split, status, chain_channels, (cudaStream_t)stream_);
 }
 
 }  // extern "C"

@@ -15,11 +15,15 @@ disjoint set of sequences with no data-path collective.
 Numerics (BatchNorm is folded into the convolutions in eval mode in every mode, which
 re-associates one multiply):
   * `precision="fp32"`   (default) fp32-ACCURATE convolutions on the tcgen05 tensor cores
-                         (csrc/pof_conv_tc.cu): operands split x = hi + lo (hi exactly TF32), the three
-                         significant partial products lo*w_hi + hi*w_lo + hi*w_hi accumulated in short
-                         chains that are promoted to fp32 registers with rounded adds.  Per layer 2-4e-7
-                         of the fp64 result - tighter than cuDNN's fp32 SIMT kernels (1e-6).  Channels-last
+                         (csrc/pof_conv_tc.cu): operands split x = hi + lo into two 11-bit-significand parts,
+                         the three significant partial products lo*w_hi + hi*w_lo + hi*w_hi accumulated in
+                         short chains that are promoted to fp32 registers with rounded adds.  The parts are
+                         float16 (kind::f16: twice the TF32 rate, half the operand bytes); each layer's weights
+                         are pre-scaled by a power of two so both parts are normal numbers.  Channels-last
                          activations; bias + LeakyReLU + max-pool + split are the kernel's epilogue.
+  * `precision="fp32-tf32"`  the same kernel with TF32 parts in fp32 containers (kind::tf32): no range limit
+                         on the activations (float16 parts need |x| <= 65504, checked on the device), half
+                         the speed.  Per layer 5-7e-7 of the fp64 result; cuDNN's fp32 SIMT kernels: 1-2e-6.
   * `precision="fp32-simt"`  every convolution in IEEE fp32 on cuDNN's SIMT kernels, NCL layout as in the
                          reference.  The library baseline of the mode above (5x slower).
   * `precision="tf32x3"` the same split run through cuDNN's TF32 convolutions ([hi | lo | hi] x
@@ -76,10 +80,11 @@ class _ChannelsLastBackbone:
     only dense contraction; everything between them is libpof's fused glue.
     """
 
-    def __init__(self, model, split, tc=False):
+    def __init__(self, model, split, tc=False, f16=False):
         self.split = bool(split)
         self.tc = bool(tc)                  # convolutions on libpof's tcgen05 kernel instead of cuDNN
-        self.parts = 2 if tc else 3
+        self.f16 = bool(f16) and self.tc    # ... with float16 hi / lo parts (kind::f16) instead of TF32 parts
+        self.parts = ops.SPLIT_F16 if self.f16 else (2 if tc else 3)
         self.timer = None                   # optional: callable(name, flops) -> context manager around each tcgen05 launch
         blocks = [model.conv_block_1, model.conv_block_2, model.conv_block_3, model.conv_block_4]
         folded = [[fold_conv_bn(layer) for layer in blk] for blk in blocks]
@@ -99,11 +104,19 @@ class _ChannelsLastBackbone:
         hi, lo = split_tf32(w)
         return torch.cat([hi, hi, lo], dim=dim)
 
-    @staticmethod
-    def _tc_weight(w):                                               # [Cout, Cin, taps] -> [taps, 2, Cout, Cin]
+    def _tc_weight(self, w):                                         # [Cout, Cin, taps] -> ([taps, 2, Cout, Cin], out_scale)
+        if self.f16:
+            # a power of two brings the largest weight to [2^12, 2^13): hi and lo are then normal float16 numbers
+            # (lo ~ 2^-11 hi), and the epilogue undoes it exactly
+            top = float(w.abs().max())
+            s = 13 - int(np.ceil(np.log2(top))) if top > 0 else 0
+            ws = w * (2.0 ** s)
+            hi = ws.to(torch.float16)
+            lo = (ws - hi.float()).to(torch.float16)
+            return torch.stack([hi, lo], dim=0).permute(3, 0, 1, 2).contiguous(), 2.0 ** -s
         hi, lo = split_tf32(w)
         lo, _ = split_tf32(lo)
-        return torch.stack([hi, lo], dim=0).permute(3, 0, 1, 2).contiguous()
+        return torch.stack([hi, lo], dim=0).permute(3, 0, 1, 2).contiguous(), 1.0
 
     def _conv_weight(self, w):                                       # [Cout, Cin, 3] -> [Cout, Ceff, 1, 3] NHWC
         if self.tc:
@@ -124,11 +137,12 @@ class _ChannelsLastBackbone:
 
     def _conv_tc(self, a, w, b, M, LA, Lout, taps, pad, **kw):
         """ops.conv_tc, optionally bracketed by the owner's event timer (algorithmic FLOPs: 2 * rows * Cin * Cout * taps)."""
+        w, out_scale = w
         if self.timer is None:
-            return ops.conv_tc(a, w, b, M, LA, Lout, taps, pad, **kw)
+            return ops.conv_tc(a, w, b, M, LA, Lout, taps, pad, out_scale=out_scale, **kw)
         cin, cout = a.shape[1] // 2, w.shape[2]
         with self.timer("conv%d" % min(cout, 256), 2.0 * M * Lout * cin * cout * taps):
-            return ops.conv_tc(a, w, b, M, LA, Lout, taps, pad, **kw)
+            return ops.conv_tc(a, w, b, M, LA, Lout, taps, pad, out_scale=out_scale, **kw)
 
     def _layer(self, a, M, L, w, b, cout, pool, plain=False):
         """One conv + bias + LeakyReLU (+ max-pool) layer -> (plain or None, operand for the next convolution)."""
@@ -163,7 +177,7 @@ class _ChannelsLastBackbone:
     def embed(self, operand, M):
         """Gate embedding (Conv1d k = L, no padding == one GEMM over whole rows) + BN + LeakyReLU."""
         if self.tc:
-            L = self.emb_w.shape[0]
+            L = self.emb_w[0].shape[0]
             return self._conv_tc(operand, self.emb_w, self.emb_b, M, L, 1, L, 0, pool=1, slope=_SLOPE, want_plain=True,
                                  want_split=False)[0]
         return F.leaky_relu_(torch.addmm(self.emb_b, operand.view(M, -1), self.emb_w), _SLOPE)
@@ -197,8 +211,8 @@ class StreamingDetector:
                  min_dist=0.5, seq_chunk=None, record_events=False):
         if not torch.cuda.is_available():
             raise RuntimeError("StreamingDetector needs a CUDA device; there is no CPU path")
-        if precision not in ("fp32", "fp32-simt", "tf32x3", "tf32"):
-            raise ValueError("precision must be 'fp32', 'fp32-simt', 'tf32x3' or 'tf32'")
+        if precision not in ("fp32", "fp32-tf32", "fp32-simt", "tf32x3", "tf32"):
+            raise ValueError("precision must be 'fp32', 'fp32-tf32', 'fp32-simt', 'tf32x3' or 'tf32'")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.precision = precision
         self.cutout_kwargs = dict(cutout_kwargs)
@@ -219,7 +233,8 @@ class StreamingDetector:
             if self.channels_last:
                 if self.P % 4:
                     raise ValueError("the channels-last pipeline needs num_cutout_pts to be a multiple of 4")
-                self.net = _ChannelsLastBackbone(model, split=precision != "tf32", tc=precision == "fp32")
+                self.net = _ChannelsLastBackbone(model, split=precision != "tf32", tc=precision in ("fp32", "fp32-tf32"),
+                                                 f16=precision == "fp32")
             self.block1 = _FoldedStack(model.conv_block_1, 1)
             self.block2 = _FoldedStack(model.conv_block_2, 1)
             self.block3 = _FoldedStack(model.conv_block_3, 1)
@@ -393,6 +408,9 @@ class StreamingDetector:
     def check(self):
         """Synchronise and raise if a tcgen05 pipeline wait timed out on the device (results would be invalid)."""
         code = ops.conv_tc_status(self.device)
+        if code == 16:
+            raise RuntimeError("an activation left the float16 range of precision='fp32' (|x| > 65504) on %s: "
+                               "use precision='fp32-tf32' for this checkpoint" % self.device)
         if code:
             raise RuntimeError("pof_conv_tc_fwd reported pipeline status %d on %s" % (code, self.device))
 

@@ -173,17 +173,27 @@ def gate(x, tmpl, emb_x, emb_t, alpha, window):
 
 
 # --------------------------------------------------------------------------- backbone glue
+SPLIT_F16 = 16          # include/pof.h POF_SPLIT_F16
+
+
+def _split_buffer(rows, C, parts, dev):
+    if parts == SPLIT_F16:
+        return torch.empty((rows, 2 * C), dtype=torch.float16, device=dev)
+    return torch.empty((rows, parts * C), dtype=torch.float32, device=dev)
+
+
 def act(y, bias=None, pool=1, slope=0.1, want_plain=True, want_split=False, parts=3):
     """Channels-last activations y [rows, C] -> (+bias) LeakyReLU, max over `pool` consecutive rows.
 
     Returns (plain [rows/pool, C] or None, split [rows/pool, parts*C] or None); parts = 3: [hi | lo | hi]
-    (cuDNN operand), parts = 2: [hi | lo] (operand of `conv_tc`)."""
+    (cuDNN operand), parts = 2: [hi | lo] (operand of `conv_tc`), parts = SPLIT_F16: [hi | lo] in float16
+    (operand of `conv_tc` on float16 operands)."""
     require_cuda_tensor(y, "y", torch.float32)
     rows, C = y.shape
     dev = y.device
     with torch.cuda.device(dev):
         plain = torch.empty((rows // pool, C), dtype=torch.float32, device=dev) if want_plain else None
-        split = torch.empty((rows // pool, parts * C), dtype=torch.float32, device=dev) if want_split else None
+        split = _split_buffer(rows // pool, C, parts, dev) if want_split else None
         check(_lib.lib().pof_act_fwd(_ptr(y), _ptr(bias), rows, C, int(pool), float(slope), _ptr(plain), _ptr(split),
                                      int(parts), current_stream_ptr(dev)), "pof_act_fwd")
     return plain, split
@@ -199,7 +209,7 @@ def conv_first(cutouts, weight, bias, slope=0.1, want_plain=False, want_split=Tr
     dev = cutouts.device
     with torch.cuda.device(dev):
         plain = torch.empty((M * P, C), dtype=torch.float32, device=dev) if want_plain else None
-        split = torch.empty((M * P, parts * C), dtype=torch.float32, device=dev) if want_split else None
+        split = _split_buffer(M * P, C, parts, dev) if want_split else None
         check(_lib.lib().pof_conv_first_fwd(_ptr(cutouts), _ptr(weight), _ptr(bias), M, P, C, float(slope), _ptr(plain),
                                             _ptr(split), int(parts), current_stream_ptr(dev)), "pof_conv_first_fwd")
     return plain, split
@@ -214,18 +224,25 @@ def conv_tc_status(device):
     return 0 if t is None else int(t.item())
 
 
-def conv_tc(a_split, w_split, bias, Mcut, LA, Lout, taps, pad, pool=1, slope=0.1, want_plain=False, want_split=True, chain_channels=0):
+def conv_tc(a_split, w_split, bias, Mcut, LA, Lout, taps, pad, pool=1, slope=0.1, want_plain=False, want_split=True, chain_channels=0,
+            out_scale=1.0):
     """fp32-accurate convolution / whole-row GEMM on tcgen05 (csrc/pof_conv_tc.cu).
 
     a_split [Mcut*LA, 2*Cin] = [hi | lo] rows, w_split [taps, 2, Cout, Cin]  ->
-    (plain [Mcut*Lout/pool, Cout] or None, split [.., 2*Cout] or None)."""
-    require_cuda_tensor(a_split, "a_split", torch.float32)
-    require_cuda_tensor(w_split, "w_split", torch.float32)
+    (plain [Mcut*Lout/pool, Cout] or None, split [.., 2*Cout] or None).
+    float32 operands hold TF32 parts (kind::tf32); float16 operands run on kind::f16 at twice the rate:
+    `w_split` then holds the parts of weight * 2^s and `out_scale` = 2^-s, and `split` is float16."""
+    f16 = a_split.dtype == torch.float16
+    dt = torch.float16 if f16 else torch.float32
+    require_cuda_tensor(a_split, "a_split", dt)
+    require_cuda_tensor(w_split, "w_split", dt)
     Cin = a_split.shape[-1] // 2
     if w_split.dim() != 4 or w_split.shape[0] != taps or w_split.shape[1] != 2 or w_split.shape[3] != Cin:
         raise ValueError("w_split must be [taps, 2, Cout, Cin] (got %s for Cin = %d)" % (tuple(w_split.shape), Cin))
     if a_split.numel() != Mcut * LA * 2 * Cin:
         raise ValueError("a_split has %d elements, expected %d x %d x %d" % (a_split.numel(), Mcut, LA, 2 * Cin))
+    if not f16 and out_scale != 1.0:
+        raise ValueError("out_scale belongs to the float16 operand form")
     Cout = w_split.shape[2]
     dev = a_split.device
     if not chain_channels:
@@ -236,10 +253,16 @@ def conv_tc(a_split, w_split, bias, Mcut, LA, Lout, taps, pad, pool=1, slope=0.1
             status = _conv_tc_status[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
         rows = Mcut * Lout // pool
         plain = torch.empty((rows, Cout), dtype=torch.float32, device=dev) if want_plain else None
-        split = torch.empty((rows, 2 * Cout), dtype=torch.float32, device=dev) if want_split else None
-        check(_lib.lib().pof_conv_tc_fwd(_ptr(a_split), _ptr(w_split), _ptr(bias), Mcut, int(LA), int(Lout), Cin, Cout,
-                                         int(taps), int(pad), int(pool), float(slope), _ptr(plain), _ptr(split),
-                                         _ptr(status), int(chain_channels), current_stream_ptr(dev)), "pof_conv_tc_fwd")
+        split = torch.empty((rows, 2 * Cout), dtype=dt, device=dev) if want_split else None
+        if f16:
+            check(_lib.lib().pof_conv_tc_f16_fwd(_ptr(a_split), _ptr(w_split), _ptr(bias), Mcut, int(LA), int(Lout), Cin, Cout,
+                                                 int(taps), int(pad), int(pool), float(slope), float(out_scale), _ptr(plain),
+                                                 _ptr(split), _ptr(status), int(chain_channels), current_stream_ptr(dev)),
+                  "pof_conv_tc_f16_fwd")
+        else:
+            check(_lib.lib().pof_conv_tc_fwd(_ptr(a_split), _ptr(w_split), _ptr(bias), Mcut, int(LA), int(Lout), Cin, Cout,
+                                             int(taps), int(pad), int(pool), float(slope), _ptr(plain), _ptr(split),
+                                             _ptr(status), int(chain_channels), current_stream_ptr(dev)), "pof_conv_tc_fwd")
     return plain, split
 
 

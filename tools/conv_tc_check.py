@@ -13,10 +13,22 @@ from planar_optical_flow_b200 import ops                      # noqa: E402
 from planar_optical_flow_b200.engine import split_tf32        # noqa: E402
 
 dev = torch.device("cuda")
+F16 = os.environ.get("POF_CHECK_F16", "1") == "1"        # float16 parts (kind::f16, the engine's default) or TF32 parts
+PARTS = ops.SPLIT_F16 if F16 else 2
+OUT_SCALE = [1.0]
 
 
 def w_split(w):
-    """[Cout, Cin, taps] -> [taps, 2, Cout, Cin] (hi, lo rounded to TF32)."""
+    """[Cout, Cin, taps] -> [taps, 2, Cout, Cin] (hi, lo): TF32 parts, or float16 parts of w * 2^s (as the engine does)."""
+    if F16:
+        import numpy as np
+        s = 13 - int(np.ceil(np.log2(float(w.abs().max()))))
+        OUT_SCALE[0] = 2.0 ** -s
+        ws = w * 2.0 ** s
+        hi = ws.half()
+        lo = (ws - hi.float()).half()
+        return torch.stack([hi, lo], dim=0).permute(3, 0, 1, 2).contiguous()
+    OUT_SCALE[0] = 1.0
     hi, lo = split_tf32(w)
     lo, _ = split_tf32(lo)
     return torch.stack([hi, lo], dim=0).permute(3, 0, 1, 2).contiguous()
@@ -37,9 +49,9 @@ def run(M, LA, Cin, Cout, taps, pad, pool, seed=0, time_it=False, flags=0):
     w = (torch.randn(Cout, Cin, taps, generator=g) * (2.0 / (Cin * taps)) ** 0.5).to(dev)
     b = (torch.randn(Cout, generator=g) * 0.1).to(dev)
     Lout = LA if pad else LA - taps + 1
-    _, a = ops.act(x.view(M * LA, Cin), None, pool=1, slope=1.0, want_plain=False, want_split=True, parts=2)
+    _, a = ops.act(x.view(M * LA, Cin), None, pool=1, slope=1.0, want_plain=False, want_split=True, parts=PARTS)
     ws = w_split(w)
-    plain, split = ops.conv_tc(a, ws, b, M, LA, Lout, taps, pad, pool=pool, slope=0.1, want_plain=True, want_split=True, chain_channels=flags)
+    plain, split = ops.conv_tc(a, ws, b, M, LA, Lout, taps, pad, pool=pool, slope=0.1, want_plain=True, want_split=True, chain_channels=flags, out_scale=OUT_SCALE[0])
     torch.cuda.synchronize()
     st = ops.conv_tc_status(dev)
     want = reference(x, w, b, pad, pool, 0.1)
@@ -54,20 +66,20 @@ def run(M, LA, Cin, Cout, taps, pad, pool, seed=0, time_it=False, flags=0):
     y32 = F.leaky_relu(y32, 0.1).permute(0, 2, 1).reshape(-1, Cout)
     torch.backends.cudnn.allow_tf32 = old
     err32 = float((y32.double() - want).abs().max()) / scale
-    msg = "chain=%-3d %s " % (flags & 0xffff, "1cta" if flags & 0x10000 else "pair") + "M=%-6d LA=%-2d %3d->%3d taps=%-2d pool=%d  status=%d  err=%.2e (split %.2e)  cudnn-fp32 err=%.2e" % (
+    msg = "%s chain=%-3d %s " % ("f16 " if F16 else "tf32", flags & 0xffff, "1cta" if flags & 0x10000 else "pair") + "M=%-6d LA=%-2d %3d->%3d taps=%-2d pool=%d  status=%d  err=%.2e (split %.2e)  cudnn-fp32 err=%.2e" % (
         M, LA, Cin, Cout, taps, pool, st, err, err_split, err32)
     if time_it:
         for _ in range(2):
-            ops.conv_tc(a, ws, b, M, LA, Lout, taps, pad, pool=pool, slope=0.1, want_plain=False, want_split=True, chain_channels=flags)
+            ops.conv_tc(a, ws, b, M, LA, Lout, taps, pad, pool=pool, slope=0.1, want_plain=False, want_split=True, chain_channels=flags, out_scale=OUT_SCALE[0])
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(5):
-            ops.conv_tc(a, ws, b, M, LA, Lout, taps, pad, pool=pool, slope=0.1, want_plain=False, want_split=True, chain_channels=flags)
+            ops.conv_tc(a, ws, b, M, LA, Lout, taps, pad, pool=pool, slope=0.1, want_plain=False, want_split=True, chain_channels=flags, out_scale=OUT_SCALE[0])
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
         flops = 2.0 * M * Lout * Cin * Cout * taps
-        msg += "  %.2f ms  %.1f TF/s fp32-equivalent (x3 TF32 products)" % (ms, flops / ms / 1e9)
+        msg += "  %.2f ms  %.1f TF/s fp32-equivalent (x3 split products)" % (ms, flops / ms / 1e9)
     print(msg, flush=True)
     return st
 
@@ -87,7 +99,7 @@ def clocks_under_load(cfg, flags, seconds=3.0):
 
     M, LA, Cin, Cout, taps, pad, pool = cfg
     x = torch.randn(M * LA, Cin, device=dev)
-    _, a = ops.act(x, None, pool=1, slope=1.0, want_plain=False, want_split=True, parts=2)
+    _, a = ops.act(x, None, pool=1, slope=1.0, want_plain=False, want_split=True, parts=PARTS)
     ws = w_split(torch.randn(Cout, Cin, taps, device=dev) * 0.05)
     b = torch.zeros(Cout, device=dev)
     samples = []
@@ -108,7 +120,7 @@ def clocks_under_load(cfg, flags, seconds=3.0):
     e0.record()
     while time.time() - t0 < seconds:
         for _ in range(20):
-            ops.conv_tc(a, ws, b, M, LA, LA, taps, pad, pool=pool, slope=0.1, want_plain=False, want_split=True, chain_channels=flags)
+            ops.conv_tc(a, ws, b, M, LA, LA, taps, pad, pool=pool, slope=0.1, want_plain=False, want_split=True, chain_channels=flags, out_scale=OUT_SCALE[0])
         n += 20
         torch.cuda.synchronize()
     e1.record()
