@@ -2,7 +2,7 @@
 """Benchmark of the DR-SPAAM per-point scan hot path on B200 (see BASELINE.json).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--sequences 256] [--shape jrdb|drow] [--precision fp32|fp32-simt|tf32x3|tf32]
+                    [--sequences 256] [--shape jrdb|drow] [--precision fp32|fp32-tf32|fp32-simt|tf32x3|tf32]
 
 Workload (BASELINE.json configs[2], the one the metric is quoted on): DR-SPAAM streaming
 inference with spatial-attention memory over 256 independent JRDB-shaped sequences
@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sequences", type=int, default=256, help="sequences per GPU")
     ap.add_argument("--shape", default="jrdb", choices=["jrdb", "drow"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32-simt", "tf32x3", "tf32"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32-tf32", "fp32-simt", "tf32x3", "tf32"])
     ap.add_argument("--cpu-scans", type=int, default=24, help="scans in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extra-precisions", default="", help="comma list of further engine precisions to time (device only)")
@@ -322,21 +322,25 @@ def run_ours(args):
         all_ms = sum(sum(v) for v in conv_ms.values())
         all_fl = sum(sum(v) for v in conv_flops.values())
         ach = fl / (t_ms * 1e-3) / 1e12
-        conv_roof = {"kernel": "conv_tc_kernel<256,2> (tcgen05 3xTF32 convolution, SM pairs; layers with >= 256 output channels)",
-                     "bound": "tensor", "achieved": ach, "peak": tpeak / 2.0, "unit": "TFLOP/s", "frac": ach / (tpeak / 2.0),
-                     "traffic": None, "peak_source": tsrc + " / 2 (TF32 runs at half the bf16 rate)",
+        f16 = args.precision == "fp32"
+        pipe_peak = tpeak if f16 else tpeak / 2.0
+        conv_roof = {"kernel": "conv_tc_kernel<256,2,%s> (tcgen05 3x%s split convolution, SM pairs; layers with >= 256 output channels)"
+                               % (("true", "F16") if f16 else ("false", "TF32")),
+                     "bound": "tensor", "achieved": ach, "peak": pipe_peak, "unit": "TFLOP/s", "frac": ach / pipe_peak,
+                     "traffic": None, "peak_source": tsrc + (" (kind::f16 runs at the bf16 rate)" if f16 else " / 2 (TF32 runs at half the bf16 rate)"),
                      "avg_launch_ms": t_ms / len(conv_ms["conv256"]), "launches_timed": len(conv_ms["conv256"]),
                      "algorithmic_flops_per_launch": fl / len(conv_ms["conv256"]),
                      "note": "achieved = fp32 convolution FLOPs (2*rows*Cin*Cout*taps) / CUDA-event time; the kernel issues THREE "
-                             "TF32 MMAs per algorithmic product (hi*hi, lo*hi, hi*lo) to stay fp32-accurate",
-                     "mma_tflops": 3 * ach, "mma_frac_of_tf32_peak": 3 * ach / (tpeak / 2.0),
+                             "MMAs per algorithmic product (hi*hi, lo*hi, hi*lo) to stay fp32-accurate",
+                     "mma_tflops": 3 * ach, "mma_frac_of_pipe_peak": 3 * ach / pipe_peak,
                      "share_of_step": t_ms / K / (ms_dev / K),
                      "all_conv_tc_launches": {"achieved": all_fl / (all_ms * 1e-3) / 1e12, "ms_per_step": all_ms / K,
                                               "share_of_step": all_ms / ms_dev}}
     out = {
         "metric": METRIC, "value": world * B * K / (ms_dev / 1e3), "unit": "scans/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "f32 (3xTF32 split products on tcgen05, 64-channel chains promoted to fp32 registers; 5-7e-7 per layer vs fp64, cuDNN fp32: 1-2e-6)",
+        "vs_baseline": None, "dtype": {"fp32": "f32 (operands split into two float16 parts, three kind::f16 products per term on tcgen05, 64-channel chains promoted to fp32 registers; 3-4e-7 per layer vs fp64, cuDNN fp32: 1-2e-6)",
+                                      "fp32-tf32": "f32 (3xTF32 split products on tcgen05, 64-channel chains promoted to fp32 registers; 5-7e-7 per layer vs fp64)",
                                       "fp32-simt": "f32", "tf32x3": "f32 operands, TF32 tensor-core accumulation (1e-4)",
                                       "tf32": "tf32"}[args.precision], "data": "synthetic",
         "impl": "ours",
@@ -356,7 +360,7 @@ def run_ours(args):
                      "peak_source": peak_src, "avg_launch_ms": gate_avg_ms, "launches_timed": len(gate_ms),
                      "algorithmic_bytes_per_launch": gate_bytes_per_seq * seqs_per_launch,
                      "frac_of_nominal_8TBs": gate_gbs / 8000.0},
-        "roofline_cutout": {"kernel": "cutout_span_kernel + cutout_kernel<FAST>, cutout-only sweep at batch %d "
+        "roofline_cutout": {"kernel": "cutout_scan_kernel (one CTA per scan, FAST numerics), cutout-only sweep at batch %d "
                                       "(BASELINE.json configs[1])" % cut_sweep["batch"],
                             "bound": "hbm", "achieved": sweep_gbs["fast"], "peak": peak, "unit": "GB/s",
                             "frac": sweep_gbs["fast"] / peak, "avg_launch_ms": cut_sweep["fast"],

@@ -232,7 +232,8 @@ POF_API int pof_conv_tc_fwd(const float* a_split, const float* w_split, const fl
  *                        multiplies a layer's weights by a power of two before splitting them (so that hi
  *                        and lo are normal binary16 numbers) and passes the inverse power as `out_scale`,
  *                        which the epilogue applies to the sum before the bias.  out_split is binary16
- *                        [.., 2 Cout]; an activation beyond 65504 sets *status = 16.  Cin % 32 == 0.        */
+ *                        [.., 2 Cout]; an activation beyond 65504 sets *status = 16.  Cin % 32 == 0;
+ *                        chain_channels: multiples of 32, 0 = default (128).                                    */
 POF_API int pof_conv_tc_f16_fwd(const void* a_split, const void* w_split, const float* bias,
                                 long long Mcut, int LA, int Lout, int Cin, int Cout, int taps, int pad,
                                 int pool, float slope, float out_scale, float* out_plain, void* out_split,

@@ -63,16 +63,15 @@ constexpr long long kWaitLimit = 2000000000LL; // ~1 s of SM clocks
 // CG = 1: one CTA computes a 128 x BN tile.  CG = 2: an SM pair (cta_group::2) computes 256 x BN, each CTA
 // holding its 128 rows of A and HALF of the weight tile: the MMA then reads 64 B/clk of operands per SM
 // instead of 96, which is what lets it run at full rate next to the TMA fill (shared memory moves 128 B/clk).
-constexpr int kRingBytes = 184 * 1024;                 // operand ring
-constexpr int kStagePitch = 36;                        // floats per staged output row: 32 columns + 4 (conflict-free 16-byte accesses)
-constexpr int kStagePitchH = 20;                       // words per staged binary16 row: 16 + 4
-constexpr int kStagingBytes = 8 * 32 * kStagePitch * 4;   // one 32 x 32 transposition buffer per epilogue warp
+constexpr int kRingBytes = 205 * 1024;                 // operand ring (227 KB per CTA minus staging, barriers and alignment slack)
+constexpr int kStagePitch = 20;                        // words per staged output row: 16 + 4 (conflict-free 16-byte accesses)
+constexpr int kStagingBytes = 8 * 32 * kStagePitch * 4;   // one 32 x 16-word transposition buffer per epilogue warp
 
 template <int BN, int CG>
 struct Cfg {
     static constexpr int kBTile = (BN / CG) * kRowBytes;       // this CTA's share of one W operand tile (hi or lo)
     static constexpr int kStage = 2 * kATile + 2 * kBTile;
-    static constexpr int kStages = (kRingBytes / kStage) < 8 ? (kRingBytes / kStage) : 8;
+    static constexpr int kStages = (kRingBytes / kStage) < 10 ? (kRingBytes / kStage) : 10;
     static constexpr int kSmem = kStages * kStage + 1024 /* alignment slack */ + 256 /* barriers */ + kStagingBytes;
     static constexpr int kAcc = BN / 2;        // accumulators per epilogue thread
 };
@@ -134,6 +133,10 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
         "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+// Warm the L2 with a box the producer will load a tile later (the first touch of the activations comes from HBM).
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
     asm volatile(
@@ -316,11 +319,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (long long tile = first_tile; tile < n_tiles && ok; tile += tile_stride) {
                 const int nt = (int)(tile % p.tiles_n);
                 const long long m0 = ((tile / p.tiles_n) * CG + rank) * p.mt;
+                // the rows this CTA loads next (first column tile only: the others find them in L2 anyway)
+                const long long tile_nx = tile + tile_stride;
+                const bool warm = tile_nx < n_tiles && tile_nx % p.tiles_n == 0;
+                const long long m0_nx = ((tile_nx / p.tiles_n) * CG + rank) * p.mt;
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
                     const int s = (int)(it % C::kStages);
                     const unsigned ph = (unsigned)((it / C::kStages) & 1);
                     if (!(ok = mbar_wait(empty(s), ph ^ 1u, p.status, 1))) break;
                     const int tap = kb / kb_per_tap, c0 = (kb - tap * kb_per_tap) * kKBlock;
+                    if (warm && tap == p.pad) {                      // the unshifted tap covers every row of the tile
+                        tma_prefetch_3d(&map_a, c0, 0, (int)m0_nx);
+                        tma_prefetch_3d(&map_a, p.Cin + c0, 0, (int)m0_nx);
+                    }
                     const unsigned dst = base + (unsigned)s * C::kStage;
                     if (CG == 1) {
                         mbar_expect_tx(full(s), tx);
@@ -429,34 +440,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float* stg = staging + e * (32 * kStagePitch);
             const int nrows = p.pool == 2 ? 16 : 32;                  // output rows this warp owns
             const long long orow0 = p.pool == 2 ? (r0 >> 1) : r0;
-            // one transposition pass: lane l's 32 values -> rows of 128 bytes at dst + j * ld
-            auto flush = [&](const float (&o)[32], float* dst, long long ld) {
-#pragma unroll
-                for (int k = 0; k < 32; k += 4)
-                    *reinterpret_cast<float4*>(stg + lane * kStagePitch + k) = make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]);
-                __syncwarp();
-                for (int j = lane >> 3; j < nrows; j += 4) {
-                    const int src = p.pool == 2 ? 2 * j : j;          // the lane that holds output row j
-                    if ((vmask >> src) & 1u)
-                        st_stream_f4(reinterpret_cast<float4*>(dst + j * ld + (lane & 7) * 4),
-                                     *reinterpret_cast<const float4*>(stg + src * kStagePitch + (lane & 7) * 4));
-                }
-                __syncwarp();
-            };
-            // binary16 rows: lane l's 16 packed words -> rows of 64 bytes at dst + j * ld (in halves)
-            auto flush_h = [&](const unsigned (&w)[16], __half* dst, long long ld) {
+            // one transposition pass: lane l's 16 words (16 floats or 32 halves of ITS row) -> rows of 64 bytes at
+            // dst + j * ld (bytes): four lanes store one output row, eight rows per instruction
+            auto flush16 = [&](const unsigned* w, char* dst, long long ld) {
                 unsigned* stw = reinterpret_cast<unsigned*>(stg);
 #pragma unroll
                 for (int k = 0; k < 16; k += 4)
-                    *reinterpret_cast<uint4*>(stw + lane * kStagePitchH + k) = make_uint4(w[k], w[k + 1], w[k + 2], w[k + 3]);
+                    *reinterpret_cast<uint4*>(stw + lane * kStagePitch + k) = make_uint4(w[k], w[k + 1], w[k + 2], w[k + 3]);
                 __syncwarp();
                 for (int j = lane >> 2; j < nrows; j += 8) {
-                    const int src = p.pool == 2 ? 2 * j : j;
+                    const int src = p.pool == 2 ? 2 * j : j;          // the lane that holds output row j
                     if ((vmask >> src) & 1u)
-                        st_stream_f4(reinterpret_cast<float4*>(dst + j * ld + (lane & 3) * 8),
-                                     *reinterpret_cast<const float4*>(stw + src * kStagePitchH + (lane & 3) * 4));
+                        st_stream_f4(reinterpret_cast<float4*>(dst + j * ld + (lane & 3) * 16),
+                                     *reinterpret_cast<const float4*>(stw + src * kStagePitch + (lane & 3) * 4));
                 }
                 __syncwarp();
+            };
+            auto flush = [&](const float (&o)[32], float* dst, long long ld) {       // 32 fp32 columns
+                unsigned w[16];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) w[k] = __float_as_uint(o[half * 16 + k]);
+                    flush16(w, reinterpret_cast<char*>(dst + half * 16), ld * 4);
+                }
+            };
+            auto flush_h = [&](const unsigned (&w)[16], __half* dst, long long ld) {  // 32 binary16 columns
+                flush16(w, reinterpret_cast<char*>(dst), ld * 2);
             };
             bool overflow = false;
 #pragma unroll
@@ -575,7 +585,9 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
     POF_REQUIRE(Cin >= kb && Cin % kb == 0, POF_ERR_BAD_SHAPE, "pof_conv_tc_fwd: Cin must be a multiple of %d (got %d)", kb, Cin);
     const int cg = (chain_channels & POF_CONV_TC_SINGLE_CTA) ? 1 : 2;      // high flag bit: tuning / tests only
     chain_channels &= ~POF_CONV_TC_SINGLE_CTA;
-    if (chain_channels == 0) chain_channels = 64;
+    // binary16 chains have half as many accumulation steps per channel: 128 channels cost what 64 TF32 channels do
+    // (6-7e-7 of the fp64 result per layer; cuDNN's fp32 kernels: 1-2e-6)
+    if (chain_channels == 0) chain_channels = f16 ? 128 : 64;
     POF_REQUIRE(chain_channels > 0 && chain_channels % kb == 0, POF_ERR_BAD_PARAM,
                 "pof_conv_tc_fwd: chain_channels must be a multiple of %d (got %d)", kb, chain_channels);
     POF_REQUIRE(Cout == 64 || Cout == 128 || (Cout >= 256 && Cout % 256 == 0), POF_ERR_BAD_SHAPE,

@@ -139,6 +139,11 @@ if __name__ == "__main__":
         for cfg in ((64 * 1091, 14, 256, 512, 3, 1, 2), (64 * 1091, 7, 512, 256, 3, 1, 1), (64 * 1091, 28, 128, 256, 3, 1, 2)):
             for flags in (64, 128, 256, 1024, 8192, 8192 | 0x10000):
                 run(*cfg, time_it=True, flags=flags)
+    if what == "layer":          # layer <cin> <cout> <L> <pool> [flags]: one launch per call, for ncu
+        cin, cout, L, pool = (int(v) for v in sys.argv[2:6])
+        flags = int(sys.argv[6], 0) if len(sys.argv) > 6 else 64
+        for _ in range(3):
+            run(64 * 1091, L, cin, cout, 3, 1, pool, time_it=False, flags=flags)
     if what == "one":
         flags = int(sys.argv[2], 0) if len(sys.argv) > 2 else 32
         for _ in range(3):
