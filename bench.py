@@ -364,6 +364,7 @@ def run_ours(args):
                                       "(BASELINE.json configs[1])" % cut_sweep["batch"],
                             "bound": "hbm", "achieved": sweep_gbs["fast"], "peak": peak, "unit": "GB/s",
                             "frac": sweep_gbs["fast"] / peak, "avg_launch_ms": cut_sweep["fast"],
+                            "traffic": 961529088,    # dram read + write of one launch, profiles/r1_cutout_scan_kernel_ncu.txt
                             "algorithmic_bytes_per_launch": sweep_bytes,
                             "exact_arithmetic": {"achieved": sweep_gbs["exact"], "frac": sweep_gbs["exact"] / peak,
                                                  "avg_launch_ms": cut_sweep["exact"]},

@@ -25,7 +25,10 @@ def _tf32_round(x):
 
 def _emit(v, want_plain, want_split, parts=3):
     split = None
-    if want_split:
+    if want_split and parts == ops.SPLIT_F16:
+        hi = v.half()
+        split = torch.cat([hi, (v - hi.float()).half()], dim=1)
+    elif want_split:
         hi = _tf32_round(v)
         split = torch.cat([hi, v - hi, hi], dim=1) if parts == 3 else torch.cat([hi, _tf32_round(v - hi)], dim=1)
     return (v if want_plain else None), split
@@ -47,18 +50,22 @@ def fake_conv_first(cutouts, weight, bias, slope=0.1, want_plain=False, want_spl
     return _emit(v, want_plain, want_split, parts)
 
 
-def fake_conv_tc(a_split, w_split, bias, Mcut, LA, Lout, taps, pad, pool=1, slope=0.1, want_plain=False, want_split=True):
-    """The definition pof_conv_tc_fwd implements, with the three split products in plain fp32."""
+def fake_conv_tc(a_split, w_split, bias, Mcut, LA, Lout, taps, pad, pool=1, slope=0.1, want_plain=False, want_split=True,
+                 chain_channels=0, out_scale=1.0):
+    """The definition pof_conv_tc_fwd / pof_conv_tc_f16_fwd implement, with the three split products in plain fp32."""
+    parts = ops.SPLIT_F16 if a_split.dtype == torch.float16 else 2
+    a_split, w_split = a_split.float(), w_split.float()
     cin = a_split.shape[1] // 2
     hi, lo = a_split[:, :cin].view(Mcut, LA, cin).permute(0, 2, 1), a_split[:, cin:].view(Mcut, LA, cin).permute(0, 2, 1)
     w_hi, w_lo = w_split[:, 0].permute(1, 2, 0), w_split[:, 1].permute(1, 2, 0)          # [Cout, Cin, taps]
     y = F.conv1d(lo, w_hi, None, padding=pad) + F.conv1d(hi, w_lo, None, padding=pad) + F.conv1d(hi, w_hi, None, padding=pad)
+    y = y * out_scale
     if bias is not None:
         y = y + bias[None, :, None]
     if pool == 2:
         y = F.max_pool1d(y, 2)
     y = torch.where(y > 0, y, y * slope).permute(0, 2, 1).reshape(Mcut * Lout // pool, -1)
-    return _emit(y, want_plain, want_split, 2)
+    return _emit(y, want_plain, want_split, parts)
 
 
 def fake_head(y, bias, M, L, w_head, b_head, n_sigmoid, slope=0.1):
@@ -87,14 +94,14 @@ def test_split_tf32_is_exact_and_tf32_representable():
     assert float((lo.abs() / w.abs()).max()) <= 2.0 ** -11
 
 
-@pytest.mark.parametrize("split,tc", [(False, False), (True, False), (True, True)])
-def test_channels_last_backbone_matches_oracle(cpu_glue, split, tc):
+@pytest.mark.parametrize("split,tc,f16", [(False, False, False), (True, False, False), (True, True, False), (True, True, True)])
+def test_channels_last_backbone_matches_oracle(cpu_glue, split, tc, f16):
     sd = omodel.randomize_bn_stats(omodel.init_state_dict(56, True, seed=5))
     m = SpatialDROW(num_scans=10, num_pts=56, alpha=0.5, window_size=11, pedestrian_only=True)
     m.load_state_dict(sd, strict=True)
     m.eval()
     with torch.no_grad():
-        net = engine._ChannelsLastBackbone(m, split=split, tc=tc)
+        net = engine._ChannelsLastBackbone(m, split=split, tc=tc, f16=f16)
         b, n = 2, 9
         torch.manual_seed(1)
         cut = torch.randn(b, n, 56).clamp(-1, 1)
