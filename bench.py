@@ -94,12 +94,14 @@ def build_model(seed=0):
 
 
 # ----------------------------------------------------------------------------- CPU reference path
-def cpu_reference_scans_per_s(shape, n_scans, warmup=2, sequences=1):
+def cpu_reference_scans_per_s(shape, n_scans, warmup=2, sequences=1, model_device="cpu"):
     """The reference's algorithm on the host cores (oracle/, all threads torch can use).
 
     Streams `sequences` independent sequences one scan at a time exactly like the reference loop
-    (depracted_scripts/infer_person_flow.py:101-139): NumPy cutout -> torch-CPU SpatialDROW with
-    dense attention -> sigmoid -> NumPy NMS.
+    (depracted_scripts/infer_person_flow.py:101-139): NumPy cutout -> torch SpatialDROW with
+    dense attention -> sigmoid -> NumPy NMS.  model_device="cuda" is the reference's PyTorch-GPU
+    path (:66-77,129-135: cutout and NMS stay on the host, the network runs on the GPU in strict
+    fp32, one H2D and one D2H per scan) - a reported baseline like the CPU one.
     """
     import numpy as np
     import torch
@@ -111,7 +113,11 @@ def cpu_reference_scans_per_s(shape, n_scans, warmup=2, sequences=1):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     model = build_model()
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    sd = {k: v.detach().clone().to(model_device) for k, v in model.state_dict().items()}
+    on_gpu = model_device != "cpu"
+    if on_gpu:
+        tf32_was = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
     per_seq = -(-(n_scans + warmup * sequences) // sequences)
     phi, scans = make_sequences(shape, sequences, per_seq, seed0=900)
     tmpl = [None] * sequences
@@ -126,10 +132,11 @@ def cpu_reference_scans_per_s(shape, n_scans, warmup=2, sequences=1):
                 a = time.perf_counter()
                 ct = ocut.scans_to_cutout(scans[t, b][None], phi, stride=1, **CUTOUT_KW)
                 c = time.perf_counter()
-                cls, reg, tmpl[b], _ = omodel.spatial_drow_stream(torch.from_numpy(ct)[None], sd, ALPHA, WINDOW, tmpl[b])
-                conf = torch.sigmoid(cls[0]).numpy()
+                cls, reg, tmpl[b], _ = omodel.spatial_drow_stream(torch.from_numpy(ct)[None].to(model_device), sd, ALPHA, WINDOW, tmpl[b])
+                conf = torch.sigmoid(cls[0]).cpu().numpy()
+                reg_h = reg[0].cpu().numpy()
                 d = time.perf_counter()
-                onms.nms_predicted_center(scans[t, b], phi, conf, reg[0].numpy())
+                onms.nms_predicted_center(scans[t, b], phi, conf, reg_h)
                 e = time.perf_counter()
                 stage["cutout"] += c - a
                 stage["model"] += d - c
@@ -137,6 +144,8 @@ def cpu_reference_scans_per_s(shape, n_scans, warmup=2, sequences=1):
                 done += 1
     timed = done - warmup * sequences
     dt = time.perf_counter() - t0
+    if on_gpu:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32_was
     return timed / dt, cores, timed, {k: 1e3 * v / timed for k, v in stage.items()}
 
 
@@ -339,7 +348,7 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": world * B * K / (ms_dev / 1e3), "unit": "scans/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "f32 (operands split into two float16 parts, three kind::f16 products per term on tcgen05, 64-channel chains promoted to fp32 registers; 3-4e-7 per layer vs fp64, cuDNN fp32: 1-2e-6)",
+        "vs_baseline": None, "dtype": {"fp32": "f32 (operands split into two float16 parts, three kind::f16 products per term on tcgen05, 128-channel chains promoted to fp32 registers; 6-7e-7 per layer vs fp64, cuDNN fp32: 1-2e-6)",
                                       "fp32-tf32": "f32 (3xTF32 split products on tcgen05, 64-channel chains promoted to fp32 registers; 5-7e-7 per layer vs fp64)",
                                       "fp32-simt": "f32", "tf32x3": "f32 operands, TF32 tensor-core accumulation (1e-4)",
                                       "tf32": "tf32"}[args.precision], "data": "synthetic",
@@ -386,6 +395,13 @@ def run_ours(args):
                                "sample": "%d scans of one %s-shaped sequence streamed through the oracle "
                                          "(NumPy cutout, torch-CPU SpatialDROW with dense attention, NumPy NMS)" % (n, args.shape.upper()),
                                "stage_ms_per_scan": stage}
+        # the reference's PyTorch-GPU path (north_star's second bar): same loop, the network on this GPU
+        vg, _, ng, stage_g = cpu_reference_scans_per_s(args.shape, 4 * args.cpu_scans, warmup=4, model_device="cuda")
+        out["torch_gpu_baseline"] = {"value": vg, "unit": "scans/s", "kind": "port",
+                                     "sample": "%d scans of one %s-shaped sequence: NumPy cutout on the host, the oracle's "
+                                               "SpatialDROW (dense attention) on cuda in strict fp32, NumPy NMS; batch 1 as in "
+                                               "depracted_scripts/infer_person_flow.py" % (ng, args.shape.upper()),
+                                     "stage_ms_per_scan": stage_g}
     _JSON_OUT.write(json.dumps(out) + "\n")
     _JSON_OUT.flush()
     if world > 1:

@@ -87,10 +87,22 @@ def neighbour_table(n, window_size):
     return cols, mask
 
 
+_TABLES = {}
+
+
+def _cached_table(n, window_size, device):
+    """The reference builds its neighbour table once per module (:171-173); same here, per (n, window, device)."""
+    key = (n, int(window_size), str(device))
+    if key not in _TABLES:
+        cols, mask = neighbour_table(n, window_size)
+        _TABLES[key] = (cols.to(device), mask.to(device))
+    return _TABLES[key]
+
+
 def gate_dense(x, template, sd, alpha, window_size, training=False):
     """The reference's dense formulation.  Returns (new_template, feat_fused, weights[B,N,N])."""
     b, n, c, l = x.shape
-    cols, mask = neighbour_table(n, window_size)
+    cols, mask = _cached_table(n, window_size, x.device)
     e_x = gate_embed(x, sd, training)                                # :176-177
     e_t = gate_embed(template, sd, training)                         # :180-181
     sim = torch.matmul(e_x, e_t.transpose(1, 2))                     # :184

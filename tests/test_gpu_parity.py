@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from oracle import cutout as ocut
 from oracle import model as omodel
@@ -437,6 +438,61 @@ def test_conv_first_and_head_kernels_match_torch():
         wh, bh = torch.randn(H, C) * 0.2, torch.randn(H)
         got = ops.head(y.cuda(), bias.cuda(), 29, L, wh.cuda(), bh.cuda(), n_sigmoid=nsig)
         assert_rel(got.cpu(), fake_head(y, bias, 29, L, wh, bh, nsig), tol=2e-6, what="heads")
+
+
+# ------------------------------------------------------------------ tcgen05 convolution (row N1)
+def _tc_weights(w, f16):
+    """[Cout, Cin, taps] -> ([taps, 2, Cout, Cin] parts, out_scale), as engine._ChannelsLastBackbone does."""
+    from planar_optical_flow_b200.engine import _ChannelsLastBackbone
+
+    holder = _ChannelsLastBackbone.__new__(_ChannelsLastBackbone)
+    holder.f16 = f16
+    return holder._tc_weight(w)
+
+
+@pytest.mark.parametrize("f16", [True, False])
+@pytest.mark.parametrize("M,LA,Cin,Cout,taps,pad,pool", [(5, 56, 64, 64, 3, 1, 1), (9, 28, 128, 256, 3, 1, 2), (40, 14, 256, 512, 3, 1, 2),
+                                                         (61, 7, 512, 256, 3, 1, 1), (130, 14, 256, 128, 14, 0, 1)])
+def test_conv_tc_matches_fp64(f16, M, LA, Cin, Cout, taps, pad, pool):
+    """pof_conv_tc_fwd / pof_conv_tc_f16_fwd against an fp64 convolution: fp32-level accuracy from split tensor-core products."""
+    g = torch.Generator().manual_seed(M + Cin)
+    x = torch.randn(M, LA, Cin, generator=g).abs() * torch.rand(M, LA, Cin, generator=g)
+    x = torch.where(torch.rand(M, LA, Cin, generator=g) < 0.3, -0.1 * x, x).cuda()
+    w = (torch.randn(Cout, Cin, taps, generator=g) * (2.0 / (Cin * taps)) ** 0.5).cuda()
+    b = (torch.randn(Cout, generator=g) * 0.1).cuda()
+    Lout = LA if pad else LA - taps + 1
+    parts = ops.SPLIT_F16 if f16 else 2
+    _, a = ops.act(x.view(M * LA, Cin), None, pool=1, slope=1.0, want_plain=False, want_split=True, parts=parts)
+    assert a.dtype == (torch.float16 if f16 else torch.float32)
+    assert_rel((a[:, :Cin].double() + a[:, Cin:].double()).cpu(), x.view(M * LA, Cin).double().cpu(), tol=2.0 ** -21, what="operand split")
+    ws, out_scale = _tc_weights(w, f16)
+    plain, split = ops.conv_tc(a, ws, b, M, LA, Lout, taps, pad, pool=pool, slope=0.1, want_plain=True, want_split=True,
+                               out_scale=out_scale)
+    torch.cuda.synchronize()
+    assert ops.conv_tc_status(x.device) == 0
+    y = F.conv1d(x.permute(0, 2, 1).double(), w.double(), b.double(), padding=pad)
+    if pool == 2:
+        y = F.max_pool1d(y, 2)
+    want = torch.where(y > 0, y, y * 0.1).permute(0, 2, 1).reshape(-1, Cout)
+    assert_rel(plain.double().cpu(), want.cpu(), tol=1.5e-6, what="convolution")
+    assert_rel((split[:, :Cout].double() + split[:, Cout:].double()).cpu(), plain.double().cpu(), tol=2.0 ** -21, what="output split")
+
+
+def test_conv_tc_f16_reports_activations_beyond_float16():
+    """An output the float16 split cannot hold must raise the device status, not pass silently."""
+    M, LA, C = 4, 14, 64
+    x = torch.full((M * LA, C), 40.0).cuda()
+    w = torch.full((C, C, 3), 30.0).cuda()                      # sums of 64 * 3 * 1200 = 230,400 > 65504
+    _, a = ops.act(x, None, pool=1, slope=1.0, want_plain=False, want_split=True, parts=ops.SPLIT_F16)
+    ws, out_scale = _tc_weights(w, True)
+    try:
+        ops.conv_tc(a, ws, None, M, LA, LA, 3, 1, want_plain=False, want_split=True, out_scale=out_scale)
+        torch.cuda.synchronize()
+        assert ops.conv_tc_status(x.device) == 16
+        plain, _ = ops.conv_tc(a, ws, None, M, LA, LA, 3, 1, want_plain=True, want_split=False, out_scale=out_scale)
+        assert float(plain.max()) == 40.0 * 30.0 * 64 * 3          # the fp32 output itself is exact
+    finally:
+        ops._conv_tc_status[x.device].zero_()
 
 
 # ------------------------------------------------------------------ legacy preprocessing (row N4)
