@@ -52,12 +52,17 @@
 namespace pof {
 namespace {
 
-constexpr int kThreads = 384;
+constexpr int kThreadsBase = 128;               // warps 0-3: TMA producer, MMA issuer, TMEM allocator, (idle)
 constexpr int kTileM = 128;
-constexpr int kRowBytes = 64;                  // one swizzled operand row: 16 fp32 or 32 binary16 channels
-template <bool F16> struct KBlock { static constexpr int value = F16 ? 32 : 16; };
+#ifndef POF_CONV_ROW_BYTES
+#define POF_CONV_ROW_BYTES 128
+#endif
+constexpr int kRowBytes = POF_CONV_ROW_BYTES;  // one swizzled operand row (= the TMA box's inner extent): 64 or 128 bytes
+static_assert(kRowBytes == 64 || kRowBytes == 128, "operand rows are 64 or 128 bytes");
+template <bool F16> struct KBlock { static constexpr int value = kRowBytes / (F16 ? 2 : 4); };   // channels per k-block
 constexpr int kATile = kTileM * kRowBytes;     // bytes of one A operand tile (hi or lo)
 constexpr int kTmemCols = 512;
+constexpr int kMaxStages = 12;                 // barrier slots: full[12] | empty[12] | tfull[2] | tempty[2] | wfull | tmem pointer
 constexpr long long kWaitLimit = 2000000000LL; // ~1 s of SM clocks
 
 // CG = 1: one CTA computes a 128 x BN tile.  CG = 2: an SM pair (cta_group::2) computes 256 x BN, each CTA
@@ -65,15 +70,23 @@ constexpr long long kWaitLimit = 2000000000LL; // ~1 s of SM clocks
 // instead of 96, which is what lets it run at full rate next to the TMA fill (shared memory moves 128 B/clk).
 constexpr int kRingBytes = 205 * 1024;                 // operand ring (227 KB per CTA minus staging, barriers and alignment slack)
 constexpr int kStagePitch = 20;                        // words per staged output row: 16 + 4 (conflict-free 16-byte accesses)
-constexpr int kStagingBytes = 8 * 32 * kStagePitch * 4;   // one 32 x 16-word transposition buffer per epilogue warp
+constexpr int kStagingWarp = 32 * kStagePitch * 4;      // one 32 x 16-word transposition buffer per epilogue warp
 
 template <int BN, int CG>
 struct Cfg {
     static constexpr int kBTile = (BN / CG) * kRowBytes;       // this CTA's share of one W operand tile (hi or lo)
-    static constexpr int kStage = 2 * kATile + 2 * kBTile;
-    static constexpr int kStages = (kRingBytes / kStage) < 10 ? (kRingBytes / kStage) : 10;
-    static constexpr int kSmem = kStages * kStage + 1024 /* alignment slack */ + 256 /* barriers */ + kStagingBytes;
-    static constexpr int kAcc = BN / 2;        // accumulators per epilogue thread
+    static constexpr int kStage = 2 * kATile + 2 * kBTile;     // streamed weights: a stage holds A hi/lo and W hi/lo of one k-block
+    static constexpr int kStageA = 2 * kATile;                 // resident weights: a stage holds A hi/lo only
+    // Epilogue warps: 8 (two column halves per TMEM lane quarter) for the wide tile, whose epilogue hides behind the
+    // tensor pipe; 16 (four column quarters) for the narrow tiles, which are bound by the issue rate of dependent
+    // epilogue code - two warps per scheduler cannot fill it, four can.  (With 16 warps the register budget is
+    // 96 per thread, enough for 32 accumulators but not for the wide tile's 64.)
+    static constexpr int kEpiWarps = BN == 128 ? 16 : 8;      // (BN = 64 would leave 16 columns per thread: keeps 8)
+    static constexpr int kThreads = kThreadsBase + 32 * kEpiWarps;
+    static constexpr int kSlices = kEpiWarps / 4;              // column slices per TMEM lane quarter
+    static constexpr int kAcc = BN / kSlices;                  // accumulators per epilogue thread
+    static constexpr int kRing = kRingBytes - (kEpiWarps - 8) * kStagingWarp;
+    static constexpr int kSmem = kRing + 1024 /* alignment slack */ + 256 /* barriers */ + kEpiWarps * kStagingWarp;
 };
 
 struct Params {
@@ -84,6 +97,8 @@ struct Params {
     int mt;              // cutouts per tile, mt * Lout <= 128
     int Cin, Cout, taps, pad, pool;
     int chain;           // k-blocks accumulated in tensor memory before a promotion to registers
+    int w_resident;      // the CTA's share of ALL weight k-blocks stays in shared memory for the whole launch
+    int stages;          // ring depth (<= kMaxStages)
     float slope;
     float out_scale;     // multiplies the accumulated sum before the bias (F16: the inverse of the weights' power of two)
     const float* bias;   // [Cout] or null
@@ -149,7 +164,7 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
 __device__ __forceinline__ unsigned long long umma_desc(unsigned addr) {
     return (unsigned long long)((addr >> 4) & 0x3fffu) | (1ull << 16) /* LBO (unused with swizzle) */ |
            ((unsigned long long)(8 * kRowBytes >> 4) << 32) /* SBO */ | (1ull << 46) /* descriptor version (sm_100) */ |
-           (4ull << 61) /* SWIZZLE_64B */;
+           ((kRowBytes == 128 ? 2ull : 4ull) << 61) /* SWIZZLE_128B / SWIZZLE_64B */;
 }
 // Instruction descriptor: D = fp32, A = B = TF32 (format 2) or binary16 (format 0), both K-major, M = m, N = bn.
 __device__ __forceinline__ unsigned umma_idesc(int bn, int m, bool f16) {
@@ -265,18 +280,19 @@ __device__ __forceinline__ float tf32_rn(float x) {
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
 template <int BN, int CG, bool F16>
-__global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__((Cfg<BN, CG>::kThreads), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Params p) {
     using C = Cfg<BN, CG>;
     constexpr int kKBlock = KBlock<F16>::value;
     extern __shared__ unsigned char smem_raw[];
     const unsigned base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const unsigned bars = base + C::kStages * C::kStage;       // full[S] | empty[S] | tfull[2] | tempty[2] | tmem ptr
+    const unsigned bars = base + C::kRing;                     // full[12] | empty[12] | tfull[2] | tempty[2] | wfull | tmem ptr
     auto full = [&](int s) { return bars + 8u * s; };
-    auto empty = [&](int s) { return bars + 8u * (C::kStages + s); };
-    auto tfull = [&](int b) { return bars + 8u * (2 * C::kStages + b); };
-    auto tempty = [&](int b) { return bars + 8u * (2 * C::kStages + 2 + b); };
-    const unsigned tmem_slot = bars + 8u * (2 * C::kStages + 4);
+    auto empty = [&](int s) { return bars + 8u * (kMaxStages + s); };
+    auto tfull = [&](int b) { return bars + 8u * (2 * kMaxStages + b); };
+    auto tempty = [&](int b) { return bars + 8u * (2 * kMaxStages + 2 + b); };
+    const unsigned wfull = bars + 8u * (2 * kMaxStages + 4);
+    const unsigned tmem_slot = bars + 8u * (2 * kMaxStages + 5);
     float* staging = reinterpret_cast<float*>(smem_raw + (bars + 256u - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -287,10 +303,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const long long n_tiles = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;
     const long long first_tile = blockIdx.x / CG, tile_stride = gridDim.x / CG;
     const int rows_tile = p.mt * p.Lout;
+    // shared-memory plan: [resident weights: n_kb x (W hi | W lo)] [ring: stages x stage_bytes]
+    const int n_stages = p.stages;
+    const unsigned stage_bytes = p.w_resident ? C::kStageA : C::kStage;
+    const unsigned ring = base + (p.w_resident ? (unsigned)n_kb * 2u * C::kBTile : 0u);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < C::kStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tfull(b), 1); mbar_init(tempty(b), 8 * CG); }
+        for (int s = 0; s < kMaxStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        mbar_init(wfull, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull(b), 1); mbar_init(tempty(b), C::kEpiWarps * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -313,9 +334,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 0 && lane == 0) {
             // ------------------------------------------------------------------ TMA producer
-            const unsigned tx = CG * (2u * (unsigned)rows_tile * kRowBytes + 2u * (unsigned)C::kBTile);   // both CTAs' loads land on the leader's barrier
+            const unsigned tx = CG * (2u * (unsigned)rows_tile * kRowBytes + (p.w_resident ? 0u : 2u * (unsigned)C::kBTile));   // both CTAs' loads land on the leader's barrier
             long long it = 0;
+            int s = 0;
+            unsigned ph = 0;
             bool ok = true;
+            if (p.w_resident && first_tile < n_tiles) {          // every weight k-block of this CTA's columns, once
+                const int n0 = (int)rank * (BN / CG);
+                if (rank == 0) mbar_expect_tx(wfull, CG * (unsigned)n_kb * 2u * (unsigned)C::kBTile);
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    const int tap = kb / kb_per_tap, c0 = (kb - tap * kb_per_tap) * kKBlock;
+                    const unsigned dst = base + (unsigned)kb * 2u * C::kBTile;
+                    if (CG == 1) {
+                        tma_load_2d(dst, &map_w, c0, (tap * 2 + 0) * p.Cout + n0, wfull);
+                        tma_load_2d(dst + C::kBTile, &map_w, c0, (tap * 2 + 1) * p.Cout + n0, wfull);
+                    } else {
+                        tma_load_2d_pair(dst, &map_w, c0, (tap * 2 + 0) * p.Cout + n0, wfull);
+                        tma_load_2d_pair(dst + C::kBTile, &map_w, c0, (tap * 2 + 1) * p.Cout + n0, wfull);
+                    }
+                }
+            }
             for (long long tile = first_tile; tile < n_tiles && ok; tile += tile_stride) {
                 const int nt = (int)(tile % p.tiles_n);
                 const long long m0 = ((tile / p.tiles_n) * CG + rank) * p.mt;
@@ -324,50 +362,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const bool warm = tile_nx < n_tiles && tile_nx % p.tiles_n == 0;
                 const long long m0_nx = ((tile_nx / p.tiles_n) * CG + rank) * p.mt;
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                    const int s = (int)(it % C::kStages);
-                    const unsigned ph = (unsigned)((it / C::kStages) & 1);
                     if (!(ok = mbar_wait(empty(s), ph ^ 1u, p.status, 1))) break;
                     const int tap = kb / kb_per_tap, c0 = (kb - tap * kb_per_tap) * kKBlock;
                     if (warm && tap == p.pad) {                      // the unshifted tap covers every row of the tile
                         tma_prefetch_3d(&map_a, c0, 0, (int)m0_nx);
                         tma_prefetch_3d(&map_a, p.Cin + c0, 0, (int)m0_nx);
                     }
-                    const unsigned dst = base + (unsigned)s * C::kStage;
+                    const unsigned dst = ring + (unsigned)s * stage_bytes;
                     if (CG == 1) {
                         mbar_expect_tx(full(s), tx);
                         tma_load_3d(dst, &map_a, c0, tap - p.pad, (int)m0, full(s));
                         tma_load_3d(dst + kATile, &map_a, p.Cin + c0, tap - p.pad, (int)m0, full(s));
-                        tma_load_2d(dst + 2 * kATile, &map_w, c0, (tap * 2 + 0) * p.Cout + nt * BN, full(s));
-                        tma_load_2d(dst + 2 * kATile + C::kBTile, &map_w, c0, (tap * 2 + 1) * p.Cout + nt * BN, full(s));
+                        if (!p.w_resident) {
+                            tma_load_2d(dst + 2 * kATile, &map_w, c0, (tap * 2 + 0) * p.Cout + nt * BN, full(s));
+                            tma_load_2d(dst + 2 * kATile + C::kBTile, &map_w, c0, (tap * 2 + 1) * p.Cout + nt * BN, full(s));
+                        }
                     } else {
                         const int n0 = nt * BN + (int)rank * (BN / CG);          // my half of the weight tile's rows
                         if (rank == 0) mbar_expect_tx(full(s), tx);
                         tma_load_3d_pair(dst, &map_a, c0, tap - p.pad, (int)m0, full(s));
                         tma_load_3d_pair(dst + kATile, &map_a, p.Cin + c0, tap - p.pad, (int)m0, full(s));
-                        tma_load_2d_pair(dst + 2 * kATile, &map_w, c0, (tap * 2 + 0) * p.Cout + n0, full(s));
-                        tma_load_2d_pair(dst + 2 * kATile + C::kBTile, &map_w, c0, (tap * 2 + 1) * p.Cout + n0, full(s));
+                        if (!p.w_resident) {
+                            tma_load_2d_pair(dst + 2 * kATile, &map_w, c0, (tap * 2 + 0) * p.Cout + n0, full(s));
+                            tma_load_2d_pair(dst + 2 * kATile + C::kBTile, &map_w, c0, (tap * 2 + 1) * p.Cout + n0, full(s));
+                        }
                     }
+                    if (++s == n_stages) { s = 0; ph ^= 1u; }
                 }
             }
         } else if (warp == 1 && lane == 0 && rank == 0) {
             // ------------------------------------------------------------------ MMA issuer (the pair's leader only)
             const unsigned idesc = umma_idesc(BN, kTileM * CG, F16);
-            long long it = 0, ic = 0;                                  // k-blocks, chains issued so far
+            long long ic = 0;                                          // chains issued so far
+            int s = 0;
+            unsigned ph = 0;
             bool ok = true;
+            if (p.w_resident && first_tile < n_tiles) ok = mbar_wait(wfull, 0u, p.status, 5);
             for (long long tile = first_tile; tile < n_tiles && ok; tile += tile_stride) {
-                for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                    const int s = (int)(it % C::kStages);
-                    const unsigned ph = (unsigned)((it / C::kStages) & 1);
+                for (int kb = 0; kb < n_kb; ++kb) {
                     const int buf = (int)(ic & 1);
                     const bool first = kb % p.chain == 0, last = (kb + 1) % p.chain == 0 || kb + 1 == n_kb;
                     if (first && !(ok = mbar_wait(tempty(buf), (unsigned)((ic >> 1) & 1) ^ 1u, p.status, 2))) break;   // chain ic-2 promoted
                     if (!(ok = mbar_wait(full(s), ph, p.status, 3))) break;                // operands landed
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const unsigned st = base + (unsigned)s * C::kStage;
+                    const unsigned st = ring + (unsigned)s * stage_bytes;
+                    const unsigned wst = p.w_resident ? base + (unsigned)kb * 2u * C::kBTile : st + 2 * kATile;
                     const unsigned long long a_hi = umma_desc(st), a_lo = umma_desc(st + kATile);
-                    const unsigned long long b_hi = umma_desc(st + 2 * kATile), b_lo = umma_desc(st + 2 * kATile + C::kBTile);
+                    const unsigned long long b_hi = umma_desc(wst), b_lo = umma_desc(wst + C::kBTile);
                     const unsigned d = tmem_base + (unsigned)(buf * BN);
-                    constexpr int kSteps = 2;                                              // one MMA consumes 32 B of the row: K = 8 (tf32) or 16 (f16)
+                    constexpr int kSteps = kRowBytes / 32;                                  // one MMA consumes 32 B of the row: K = 8 (tf32) or 16 (f16)
                     auto mma = [&](unsigned long long a, unsigned long long b, unsigned acc) {
                         if (CG == 1) { if (F16) umma_f16(d, a, b, idesc, acc); else umma_tf32(d, a, b, idesc, acc); }
                         else { if (F16) umma_f16_pair(d, a, b, idesc, acc); else umma_tf32_pair(d, a, b, idesc, acc); }
@@ -385,12 +428,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         umma_commit_pair(empty(s));                      // both CTAs' producers may refill their slot
                         if (last) { umma_commit_pair(tfull(buf)); ++ic; }  // both CTAs' epilogues may read their rows
                     }
+                    if (++s == n_stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else {
         // ---------------------------------------------------------------------- promotion + epilogue
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+        if constexpr (C::kEpiWarps == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");   // 16 warps: compiled for <= 96 already
         const int e = warp - 4, q = e & 3, h = e >> 2;           // TMEM lane quarter (= warp % 4), column half
         const int row = q * 32 + lane;
         const unsigned lane_addr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(h * C::kAcc);
@@ -468,7 +512,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             auto flush_h = [&](const unsigned (&w)[16], __half* dst, long long ld) {  // 32 binary16 columns
                 flush16(w, reinterpret_cast<char*>(dst), ld * 2);
             };
-            bool overflow = false;
+            float amax = 0.f;                                 // largest activation magnitude of this lane's row
 #pragma unroll
             for (int g = 0; g < C::kAcc / 32; ++g) {
                 float o[32];
@@ -479,9 +523,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         float v = acc[g * 32 + k + i];
-                        if (F16) v *= p.out_scale;                      // a power of two: exact
                         if (p.pool == 2) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-                        o[k + i] = lrelu(v + bb[i], p.slope);
+                        // out_scale is a positive power of two: v * out_scale is exact, so the fused form rounds once
+                        // like the separate bias add, and it commutes with the max above
+                        v = F16 ? fmaf(v, p.out_scale, bb[i]) : v + bb[i];
+                        o[k + i] = fmaxf(v, v * p.slope);               // LeakyReLU for 0 <= slope <= 1
                     }
                 }
                 if (p.out_plain) flush(o, p.out_plain + orow0 * p.Cout + cbase + g * 32, p.Cout);
@@ -494,7 +540,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             const __half2 h2 = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
                             const float2 hf = __half22float2(h2);
                             const __half2 l2 = __floats2half2_rn(o[2 * k] - hf.x, o[2 * k + 1] - hf.y);
-                            overflow |= !(fabsf(o[2 * k]) <= 65504.f) || !(fabsf(o[2 * k + 1]) <= 65504.f);
+                            amax = fmaxf(amax, fmaxf(fabsf(o[2 * k]), fabsf(o[2 * k + 1])));
                             hi[k] = *reinterpret_cast<const unsigned*>(&h2);
                             lo[k] = *reinterpret_cast<const unsigned*>(&l2);
                         }
@@ -512,7 +558,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
             }
-            if (F16 && __any_sync(0xffffffffu, overflow && valid) && lane == 0) atomicCAS(p.status, 0, 16);   // beyond binary16
+            if (F16 && __any_sync(0xffffffffu, !(amax <= 65504.f) && valid) && lane == 0) atomicCAS(p.status, 0, 16);   // beyond binary16
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -555,7 +601,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mw, const Params& p, cudaSt
     const long long tiles = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;
     const long long groups = sm_count() / CG;
     const int grid = CG * (int)(tiles < groups ? tiles : groups);
-    conv_tc_kernel<BN, CG, F16><<<grid, kThreads, C::kSmem, stream>>>(ma, mw, p);
+    conv_tc_kernel<BN, CG, F16><<<grid, C::kThreads, C::kSmem, stream>>>(ma, mw, p);
     POF_CUDA(cudaGetLastError());
     return POF_OK;
 }
@@ -583,8 +629,9 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
     POF_REQUIRE(Mcut > 0 && Mcut < (1ll << 31) && LA >= 1 && Lout >= 1 && Lout <= 128 && LA <= 256, POF_ERR_BAD_SHAPE,
                 "pof_conv_tc_fwd: bad shape Mcut=%lld LA=%d Lout=%d", Mcut, LA, Lout);
     POF_REQUIRE(Cin >= kb && Cin % kb == 0, POF_ERR_BAD_SHAPE, "pof_conv_tc_fwd: Cin must be a multiple of %d (got %d)", kb, Cin);
-    const int cg = (chain_channels & POF_CONV_TC_SINGLE_CTA) ? 1 : 2;      // high flag bit: tuning / tests only
-    chain_channels &= ~POF_CONV_TC_SINGLE_CTA;
+    const int chain_flags = chain_channels;
+    const int cg = (chain_channels & POF_CONV_TC_SINGLE_CTA) ? 1 : 2;      // high flag bits: tuning / tests only
+    chain_channels &= ~(POF_CONV_TC_SINGLE_CTA | POF_CONV_TC_STREAM_W);
     // binary16 chains have half as many accumulation steps per channel: 128 channels cost what 64 TF32 channels do
     // (6-7e-7 of the fp64 result per layer; cuDNN's fp32 kernels: 1-2e-6)
     if (chain_channels == 0) chain_channels = f16 ? 128 : 64;
@@ -595,6 +642,7 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
     POF_REQUIRE(taps >= 1 && pad >= 0 && pad < taps, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: bad taps/pad %d/%d", taps, pad);
     POF_REQUIRE(pool == 1 || (pool == 2 && Lout % 2 == 0), POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: pool must be 1, or 2 with even Lout");
     POF_REQUIRE(out_scale > 0.f, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: out_scale must be positive");
+    POF_REQUIRE(slope >= 0.f && slope <= 1.f, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: slope must lie in [0, 1] (got %g)", (double)slope);
     const uintptr_t al = reinterpret_cast<uintptr_t>(a_split) | reinterpret_cast<uintptr_t>(w_split) |
                          reinterpret_cast<uintptr_t>(out_plain) | reinterpret_cast<uintptr_t>(out_split) |
                          reinterpret_cast<uintptr_t>(bias);
@@ -613,6 +661,18 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
     p.chain = chain_channels / kb;
     p.out_scale = out_scale;
     p.bias = bias; p.out_plain = out_plain; p.out_split = out_split; p.status = status;
+    {   // narrow layers: this CTA's share of ALL weight k-blocks fits next to a deep ring of activation stages, so the
+        // weights are loaded once per launch instead of once per tile (they are 35-55 % of those layers' L2->SM traffic)
+        const int n_kb = taps * (Cin / kb);
+        const int b_tile = (bn / cg) * kRowBytes;                       // one W part of one k-block
+        const long long w_bytes = (long long)n_kb * 2 * b_tile;
+        const int stage_a = 2 * kTileM * kRowBytes, stage_full = stage_a + 2 * b_tile;
+        const bool forbid = (chain_flags & POF_CONV_TC_STREAM_W) != 0;
+        const long long ring = bn == 128 ? kRingBytes - 8 * kStagingWarp : kRingBytes;      // Cfg<BN, CG>::kRing
+        p.w_resident = !forbid && p.tiles_n == 1 && w_bytes <= ring - 4 * stage_a;
+        const long long st = p.w_resident ? (ring - w_bytes) / stage_a : ring / stage_full;
+        p.stages = (int)(st < kMaxStages ? st : kMaxStages);
+    }
     const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
 
     alignas(64) CUtensorMap ma, mw;
@@ -622,7 +682,7 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
         const cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)Lout, (cuuint32_t)p.mt};
         const cuuint32_t es[3] = {1, 1, 1};
         const CUresult r = enc(&ma, dt, 3, const_cast<void*>(a_split), dims, strides, box, es,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, kRowBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         POF_REQUIRE(r == CUDA_SUCCESS, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
     }
@@ -632,7 +692,7 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
         const cuuint32_t box[2] = {(cuuint32_t)kb, (cuuint32_t)(bn / cg)};            // each CTA of a pair loads its half
         const cuuint32_t es[2] = {1, 1};
         const CUresult r = enc(&mw, dt, 2, const_cast<void*>(w_split), dims, strides, box, es,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, kRowBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         POF_REQUIRE(r == CUDA_SUCCESS, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
     }

@@ -150,13 +150,13 @@ if __name__ == "__main__":
             run(64 * 1091, 14, 256, 512, 3, 1, 2, time_it=False, flags=flags)
     if what in ("small", "all"):
         for k, c in enumerate(SMALL):
-            for flags in (64, 64 | 0x10000, 32):
+            for flags in (64, 64 | 0x10000, 128):
                 if run(*c, seed=k, flags=flags):
                     sys.exit("pipeline wait timed out")
     if what in ("layers", "all"):
         M = int(sys.argv[2]) if len(sys.argv) > 2 else 64 * 1091
         for cin, cout, L, pool in LAYERS:
-            for flags in (64, 64 | 0x10000, 32, 128):
+            for flags in (64, 128, 128 | 0x10000):
                 run(M, L, cin, cout, 3, 1, pool, time_it=True, flags=flags)
         for flags in (64, 64 | 0x10000):
             run(M, 14, 256, 128, 14, 0, 1, time_it=True, flags=flags)
