@@ -135,28 +135,75 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const NmsArgs a)
 }
 
 // ---- 2. adjacency bit matrix in sorted space --------------------------------------------------
+// D[a, c] = sqrt((x_a - x_c)^2 + (y_a - y_c)^2) < min_dist in the promoted dtype (:550-552, :562), every operation
+// rounded separately as NumPy does.  The square root is monotone, so the comparison is made on the sum of squares
+// against `s_max`, the largest value whose ROUNDED root is still below the threshold (found once per CTA by
+// stepping ulps around min_dist^2): the same boolean for every input, without N^2 square roots.
+// A CTA stages the scan's centres in shared memory in the compute dtype (the float64 -> float32 conversion used to
+// be done N^2 times from global memory); a thread owns one 32-column word of one row and visits its columns in an
+// order rotated by its lane index, which makes the shared-memory reads bank-conflict free.
+template <typename T> __device__ __forceinline__ T next_after(T v, int dir);
+template <> __device__ __forceinline__ float next_after<float>(float v, int dir) {           // v >= 0
+    if (v == 0.f) return dir > 0 ? __int_as_float(1) : -__int_as_float(1);
+    return __int_as_float(__float_as_int(v) + dir);
+}
+template <> __device__ __forceinline__ double next_after<double>(double v, int dir) {
+    if (v == 0.0) return dir > 0 ? __longlong_as_double(1) : -__longlong_as_double(1);
+    return __longlong_as_double(__double_as_longlong(v) + dir);
+}
+template <typename T2>
+__device__ T2 largest_square_below(T2 thr) {
+    if (!(thr > (T2)0)) return (T2)-1;                       // nothing is closer than a non-positive distance
+    T2 s = Fn<T2>::mul(thr, thr);
+    if (!(s < (T2)3.0e38)) return s;                         // infinite threshold: everything finite qualifies
+    for (int i = 0; i < 64 && Fn<T2>::sqrt_(s) < thr; ++i) s = next_after<T2>(s, +1);
+    for (int i = 0; i < 128 && !(Fn<T2>::sqrt_(s) < thr); ++i) s = next_after<T2>(s, -1);
+    return s;                                                 // sqrt_rn(s) < thr and sqrt_rn(next(s)) >= thr
+}
+
 template <typename T2>
 __global__ void __launch_bounds__(kAdjThreads) nms_adjacency_kernel(const NmsArgs a) {
+    extern __shared__ __align__(16) unsigned char adj_smem[];
+    __shared__ T2 s_max_sh;
     const int b = blockIdx.y;
     const int N = a.N, nw = a.n_words;
+    T2* sx = reinterpret_cast<T2*>(adj_smem);
+    T2* sy = sx + N;
     const double* xs = a.xs + (size_t)b * N;
     const double* ys = a.ys + (size_t)b * N;
     unsigned* adj = a.adj + (size_t)b * N * nw;
-    const T2 thr = (T2)a.min_dist;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { sx[i] = (T2)xs[i]; sy[i] = (T2)ys[i]; }
+    if (threadIdx.x == 0) s_max_sh = largest_square_below<T2>((T2)a.min_dist);
+    __syncthreads();
+    const T2 s_max = s_max_sh;
+    const int lane = threadIdx.x & 31;
     const long long total = (long long)N * nw;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
         const int row = (int)(t / nw);
         const int w = (int)(t - (long long)row * nw);
-        const T2 xa = (T2)xs[row], ya = (T2)ys[row];
-        unsigned bits = 0;
+        const T2 xa = sx[row], ya = sy[row];
         const int c0 = w << 5;
-        const int c1 = min(N, c0 + 32);
-        for (int c = c0; c < c1; ++c) {
-            const T2 ddx = Fn<T2>::sub(xa, (T2)xs[c]);                       // :550-552
-            const T2 ddy = Fn<T2>::sub(ya, (T2)ys[c]);
-            const T2 d = Fn<T2>::sqrt_(Fn<T2>::add(Fn<T2>::mul(ddx, ddx), Fn<T2>::mul(ddy, ddy)));
-            if (d < thr) bits |= 1u << (c - c0);                             // :562
+        unsigned bits = 0;
+        if (c0 + 32 <= N) {
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+                const int k = (i + lane) & 31;
+                const T2 ddx = Fn<T2>::sub(xa, sx[c0 + k]);                      // :550-552
+                const T2 ddy = Fn<T2>::sub(ya, sy[c0 + k]);
+                const T2 q = Fn<T2>::add(Fn<T2>::mul(ddx, ddx), Fn<T2>::mul(ddy, ddy));
+                bits |= (q <= s_max ? 1u : 0u) << k;                             // :562
+            }
+        } else {
+            for (int i = 0; i < 32; ++i) {
+                const int k = (i + lane) & 31;
+                if (c0 + k < N) {
+                    const T2 ddx = Fn<T2>::sub(xa, sx[c0 + k]);
+                    const T2 ddy = Fn<T2>::sub(ya, sy[c0 + k]);
+                    const T2 q = Fn<T2>::add(Fn<T2>::mul(ddx, ddx), Fn<T2>::mul(ddy, ddy));
+                    bits |= (q <= s_max ? 1u : 0u) << k;
+                }
+            }
         }
         adj[t] = bits;
     }
@@ -286,10 +333,14 @@ int pof_nms_centers(const void* scan, int scan_is_f64, const void* phi, int phi_
     POF_CUDA(cudaGetLastError());
 
     const long long words = (long long)N * a.n_words;
-    unsigned gx = (unsigned)((words + kAdjThreads - 1) / kAdjThreads);
-    dim3 grid_adj(gx, (unsigned)B);
-    if (scan_is_f64 || phi_is_f64) nms_adjacency_kernel<double><<<grid_adj, kAdjThreads, 0, stream>>>(a);
-    else nms_adjacency_kernel<float><<<grid_adj, kAdjThreads, 0, stream>>>(a);
+    // a few CTAs per scan (each stages the scan's centres once), enough scans x CTAs to fill the SMs
+    unsigned gx = (unsigned)((words + kAdjThreads * 16 - 1) / (kAdjThreads * 16));
+    dim3 grid_adj(gx > 0 ? gx : 1, (unsigned)B);
+    if ((scan_is_f64 || phi_is_f64) && (size_t)N * 2 * sizeof(double) > 48 * 1024)
+        POF_CUDA(cudaFuncSetAttribute(nms_adjacency_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kMaxPoints * 2 * (int)sizeof(double)));
+    if (scan_is_f64 || phi_is_f64) nms_adjacency_kernel<double><<<grid_adj, kAdjThreads, (size_t)N * 2 * sizeof(double), stream>>>(a);
+    else nms_adjacency_kernel<float><<<grid_adj, kAdjThreads, (size_t)N * 2 * sizeof(float), stream>>>(a);
     POF_CUDA(cudaGetLastError());
 
     nms_sweep_kernel<<<B, kSweepThreads, 0, stream>>>(a);
