@@ -68,8 +68,9 @@ __global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ y, c
                                                   int C, long long rows_out, float* plain, void* split, int parts) {
     const int c4n = C >> 2;
     const long long total = rows_out * c4n;
+    const bool small = total < (1ll << 32);             // 32-bit index arithmetic (a 64-bit division costs ~50 issue slots)
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const long long row = t / c4n;
+        const long long row = small ? (long long)((unsigned)t / (unsigned)c4n) : t / c4n;
         const int c = (int)(t - row * c4n) << 2;
         const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 v = ld_stream_f4(reinterpret_cast<const float4*>(y + (size_t)row * POOL * C + c));
@@ -82,30 +83,30 @@ __global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ y, c
     }
 }
 
-// out[m, l, c] = lrelu(b[c] + sum_k w[c, k] * x[m, l + k - 1]),  x = cutouts [M, P], zero padded
+// out[m, l, c] = lrelu(b[c] + sum_k w[c, k] * x[m, l + k - 1]),  x = cutouts [M, P], zero padded.
+// A thread keeps ONE group of four channels for all the rows it visits (C/4 divides the block size), so its twelve
+// weights and four biases live in registers; the first version re-read them from shared memory for every row with
+// an 8-way bank conflict and ran at 30 % of the write bandwidth.
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float slope, int P, int C,
                                                          long long rows /* M*P */, float* plain, void* split, int parts) {
-    extern __shared__ float wsm[];                 // [C][4]: w0, w1, w2, bias
-    for (int i = threadIdx.x; i < C; i += blockDim.x) {
-        wsm[4 * i] = w[3 * i]; wsm[4 * i + 1] = w[3 * i + 1]; wsm[4 * i + 2] = w[3 * i + 2]; wsm[4 * i + 3] = bias[i];
+    const unsigned c4n = (unsigned)C >> 2;
+    const unsigned rpb = blockDim.x / c4n;             // rows per block and pass
+    const int c = (int)(threadIdx.x % c4n) << 2;
+    float w0[4], w1[4], w2[4], bb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        w0[j] = __ldg(w + 3 * (c + j)); w1[j] = __ldg(w + 3 * (c + j) + 1); w2[j] = __ldg(w + 3 * (c + j) + 2);
+        bb[j] = __ldg(bias + c + j);
     }
-    __syncthreads();
-    const int c4n = C >> 2;
-    const long long total = rows * c4n;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const long long row = t / c4n;
-        const int c = (int)(t - row * c4n) << 2;
-        const int l = (int)(row % P);
+    for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / c4n; row < rows; row += (long long)gridDim.x * rpb) {
+        const int l = rows < (1ll << 32) ? (int)((unsigned)row % (unsigned)P) : (int)(row % P);
         const float xc = __ldg(x + row);
         const float xl = l > 0 ? __ldg(x + row - 1) : 0.f;
         const float xr = l < P - 1 ? __ldg(x + row + 1) : 0.f;
         float o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 q = *reinterpret_cast<const float4*>(wsm + 4 * (c + j));
-            o[j] = lrelu(fmaf(q.z, xr, fmaf(q.y, xc, fmaf(q.x, xl, q.w))), slope);
-        }
+        for (int j = 0; j < 4; ++j) o[j] = lrelu(fmaf(w2[j], xr, fmaf(w1[j], xc, fmaf(w0[j], xl, bb[j]))), slope);
         emit(make_float4(o[0], o[1], o[2], o[3]), (size_t)row, c, C, plain, split, parts);
     }
 }
@@ -197,9 +198,9 @@ int pof_conv_first_fwd(const float* cutouts, const float* weight, const float* b
     POF_REQUIRE(split_parts == 2 || split_parts == 3 || split_parts == POF_SPLIT_F16, POF_ERR_BAD_PARAM,
                 "pof_conv_first_fwd: split_parts must be 2, 3 or POF_SPLIT_F16");
     const long long rows = M * P;
+    POF_REQUIRE(256 % (C >> 2) == 0, POF_ERR_BAD_SHAPE, "pof_conv_first_fwd: C / 4 must divide 256 (got C = %d)", C);
     const unsigned grid = stream_grid(rows * (C >> 2), 256);
-    conv_first_kernel<<<grid, 256, (size_t)C * 4 * sizeof(float), stream>>>(cutouts, weight, bias, slope, P, C, rows, out_plain,
-                                                                           out_split, split_parts);
+    conv_first_kernel<<<grid, 256, 0, stream>>>(cutouts, weight, bias, slope, P, C, rows, out_plain, out_split, split_parts);
     POF_CUDA(cudaGetLastError());
     return POF_OK;
 }

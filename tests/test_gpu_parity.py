@@ -433,6 +433,12 @@ def test_conv_first_and_head_kernels_match_torch():
     hi = s[:, :64].cpu()
     assert torch.equal(hi, s[:, 128:].cpu()) and torch.equal(hi + s[:, 64:128].cpu(), p.cpu())
     assert int((hi.view(torch.int32) & 0x1fff).abs().max()) == 0
+    # float16 parts (the engine's operand format)
+    _, s16 = ops.conv_first(cut.cuda(), w.cuda(), b.cuda(), want_plain=False, want_split=True, parts=ops.SPLIT_F16)
+    p16, s16b = ops.conv_first(cut.cuda(), w.cuda(), b.cuda(), want_plain=True, want_split=True, parts=ops.SPLIT_F16)
+    assert s16.dtype == torch.float16 and torch.equal(s16, s16b) and torch.equal(p16, p)
+    assert torch.equal(s16[:, :64], p.half())
+    assert_rel((s16[:, :64].double() + s16[:, 64:].double()).cpu(), p.double().cpu(), tol=2.0 ** -21, what="float16 split")
     for L, C, H, nsig in ((7, 128, 3, 1), (3, 256, 6, 4), (1, 4, 1, 0)):
         y, bias = torch.randn(29 * L, C), torch.randn(C)
         wh, bh = torch.randn(H, C) * 0.2, torch.randn(H)
