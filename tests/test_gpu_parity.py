@@ -162,6 +162,45 @@ def test_cutout_stride_ragged_and_batched():
     assert tuple(empty.shape) == (0, 450, 1, 56)
 
 
+@pytest.mark.parametrize("flags", [dict(), dict(fixed=False), dict(centered=False), dict(area_mode=False),
+                                   dict(window_width=1.66, window_depth=1.0, num_cutout_pts=48), dict(num_cutout_pts=4),
+                                   dict(window_depth=0.3, num_cutout_pts=64)])
+@pytest.mark.parametrize("shape,kind", [("drow", "adversarial"), ("jrdb", "structured"), ("drow", "edge"), ("jrdb", "edge")])
+def test_cutout_single_scan_kernel(shape, kind, flags):
+    """S = 1 with FAST numerics runs cutout_scan_kernel (one CTA per scan, what the engine and the configs[1] sweep use):
+    every flag combination, through the same five-way check."""
+    phi = synth.phi_for(shape)
+    n = len(phi)
+    scans = {"adversarial": lambda: synth.adversarial_scans(1, n, seed=21),
+             "structured": lambda: synth.structured_sequence(1, n, seed=22, phi=phi),
+             "edge": lambda: synth.edge_scans(n, seed=23)[:1]}[kind]()
+    _check_cutout(scans, phi, dict(CFG, **flags))
+
+
+def test_cutout_single_scan_kernel_ragged_strided_and_close_range():
+    for n in (2, 3, 5, 31, 32, 33, 129, 450):
+        p = synth.drow_phi(n)
+        _check_cutout(synth.adversarial_scans(1, n, seed=100 + n), p, CFG)
+    phi = synth.drow_phi()
+    scans = synth.adversarial_scans(1, 450, seed=5)
+    for stride in (2, 3, 7):
+        _check_cutout(scans, phi, CFG, stride=stride)
+    # ranges below half the window width (ratio > 1: the reciprocal branch of the table arctangent), below the 1e-2
+    # clamp, and a scan where EVERY row is area-resampled
+    close = np.linspace(0.004, 0.6, 450, dtype=np.float32)[None]
+    _check_cutout(close, phi, CFG)
+    _check_cutout(np.full((1, 450), 0.2, np.float32), phi, CFG)
+    # batched: per-scan s_area from the near-sensor rows == the oracle's, FAST == per-scan FAST calls
+    batch = np.stack([synth.adversarial_scans(1, 450, seed=60 + b, lo=0.3 + 0.5 * b) for b in range(6)])
+    out, s_area = ops.cutout(torch.from_numpy(batch).cuda(), torch.from_numpy(phi).cuda(), return_s_area=True, fast=True, **CFG)
+    for b in range(6):
+        diag = ocut.cutout_diagnostics(batch[b], phi, **CFG)
+        assert abs(int(s_area[b]) - diag["s_area"]) <= (diag.get("s_area_margin", 1.0) < 1e-3)
+        one = ops.cutout(torch.from_numpy(batch[b:b + 1]).cuda(), torch.from_numpy(phi).cuda(), fast=True, **CFG)
+        assert torch.equal(one[0], out[b])
+    assert len(set(s_area.tolist())) > 1
+
+
 def test_cutout_torch_signature_and_full_size_properties():
     """BASELINE config 2 size (B=4096 JRDB rows): properties that need no oracle pass."""
     phi = synth.jrdb_phi()
