@@ -11,7 +11,7 @@ import os
 import threading
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libpof.so")
+LIB_PATH = os.environ.get("POF_LIB") or os.path.join(_PKG_DIR, "libpof.so")      # POF_LIB: a tuning variant (build.build_variant)
 ABI_VERSION = 1
 
 _lock = threading.Lock()

@@ -562,25 +562,20 @@ __device__ __forceinline__ void chunk_load(ChunkTaps& t, long long& fx, long lon
         t.ok[u] = INSIDE || (unsigned long long)fx <= limit;
     }
 }
-// PRECISE = false: pairs are (C, D) in output units, one fma + the row's bias: three roundings at the magnitude of
-// range * scale.  PRECISE = true (chosen per scan when that magnitude's ulp is too coarse for the 1e-5 bar): pairs are
-// (v, v' - v) in metres; the row's own range is subtracted FIRST (exact for every sample inside the depth window:
-// Sterbenz), so the blend rounds at the magnitude of the window, not of the range.  `bias` is then the range (or 0).
-template <bool INSIDE, bool PRECISE>
-__device__ __forceinline__ void chunk_finish(const ChunkTaps& t, float bias, float scale, float lo_f, float hi_f, float pad_f, float* dst) {
+template <bool INSIDE>
+__device__ __forceinline__ void chunk_finish(const ChunkTaps& t, float bias, float lo_f, float hi_f, float pad_f, float* dst) {
     float res[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        const float x = PRECISE ? fmaf(t.w[u] - 1.0f, t.cd[u].y, t.cd[u].x - bias) * scale : fmaf(t.w[u], t.cd[u].y, t.cd[u].x) + bias;
-        const float v = fminf(fmaxf(x, lo_f), hi_f);
+        const float v = fminf(fmaxf(fmaf(t.w[u], t.cd[u].y, t.cd[u].x) + bias, lo_f), hi_f);
         res[u] = t.ok[u] ? v : pad_f;
     }
     *reinterpret_cast<float4*>(dst) = make_float4(res[0], res[1], res[2], res[3]);
 }
 // One two-tap row of P = 4*nchunks samples into `dst`; chunks in the order rot, rot+1, ..., nchunks-1, (0 if rot).
-template <bool INSIDE, bool PRECISE>
+template <bool INSIDE>
 __device__ __forceinline__ void scan_row(long long fx0, long long slope, unsigned rot, int nchunks, const float2* pairs, int nm1,
-                                         unsigned long long limit, float bias, float scale, float lo_f, float hi_f, float pad_f, float* dst) {
+                                         unsigned long long limit, float bias, float lo_f, float hi_f, float pad_f, float* dst) {
     long long fx = fx0 + (rot ? 4 * slope : 0);
     float* p = dst + 4 * rot;
     ChunkTaps t0, t1;
@@ -588,17 +583,17 @@ __device__ __forceinline__ void scan_row(long long fx0, long long slope, unsigne
 #pragma unroll(INSIDE ? 2 : 1)
     for (int j = 0; j < nchunks - 2; ++j, p += 4) {
         chunk_load<INSIDE>(t1, fx, slope, pairs, nm1, limit);
-        chunk_finish<INSIDE, PRECISE>(t0, bias, scale, lo_f, hi_f, pad_f, p);
+        chunk_finish<INSIDE>(t0, bias, lo_f, hi_f, pad_f, p);
         t0 = t1;
     }
     if (nchunks > 1) {
         if (rot) fx = fx0;                                    // the rotated order ends with chunk 0
         chunk_load<INSIDE>(t1, fx, slope, pairs, nm1, limit);
-        chunk_finish<INSIDE, PRECISE>(t0, bias, scale, lo_f, hi_f, pad_f, p);
+        chunk_finish<INSIDE>(t0, bias, lo_f, hi_f, pad_f, p);
         p = rot ? dst : p + 4;
-        chunk_finish<INSIDE, PRECISE>(t1, bias, scale, lo_f, hi_f, pad_f, p);
+        chunk_finish<INSIDE>(t1, bias, lo_f, hi_f, pad_f, p);
     } else {
-        chunk_finish<INSIDE, PRECISE>(t0, bias, scale, lo_f, hi_f, pad_f, dst);
+        chunk_finish<INSIDE>(t0, bias, lo_f, hi_f, pad_f, dst);
     }
 }
 
@@ -667,7 +662,7 @@ template <typename PhiT>
 __global__ void __launch_bounds__(kScanWarpsMax * 32, 2) cutout_scan_kernel(const CutoutArgs a) {
     extern __shared__ __align__(16) float smem_f[];          // pairs [N+1] float2 | arctangent table | ranges [N] | per-warp tiles [32][P]
     __shared__ double warp_span[kScanWarpsMax];
-    __shared__ float warp_min[kScanWarpsMax], warp_vmax[kScanWarpsMax];
+    __shared__ float warp_min[kScanWarpsMax];
     const Consts c = make_consts<PhiT>(a);
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
     const int b = blockIdx.x;                                // S == 1: scan == sample
@@ -683,9 +678,8 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 2) cutout_scan_kernel(cons
     const float* ha_in = a.half_alpha_in ? a.half_alpha_in + (size_t)b * a.M : nullptr;
     float* ha_out = a.half_alpha_out ? a.half_alpha_out + (size_t)b * a.M : nullptr;
 
-    // ---- stage the scan: raw ranges, (C, D) blend pairs (entry N repeats beam N-1 so index N-1 + 0 reads in bounds),
-    //      the nearest row and the largest finite range ---------------------------------------------------------------
-    float dmin = 3.0e38f, vmax = 0.f;
+    // ---- stage the scan as (C, D) pairs; entry N repeats beam N-1 so index N-1 + 0 reads in bounds ---
+    float dmin = 3.0e38f;
     for (int i = tid; i < kAtanDeg * kAtanCells; i += T) atab[i] = (&kAtanTab[0][0])[i];
     for (int i = tid; i <= a.N; i += T) {
         const float r0 = __ldg(scan + min(i, nm1));
@@ -693,29 +687,15 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 2) cutout_scan_kernel(cons
         const float D = (v1 - v0) * scale;
         pairs[i] = make_float2(fmaf(v0, scale, -D), D);
         if (i < a.N) vals[i] = r0;
-        vmax = fmaxf(vmax, fabsf(v0));
     }
     for (int m = tid; m < a.M; m += T) dmin = fminf(dmin, fmaxf(__ldg(scan + m * a.stride), 1e-2f));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    }
-    if (lane == 0) { warp_min[warp] = dmin; warp_vmax[warp] = vmax; }
+    for (int o = 16; o > 0; o >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    if (lane == 0) warp_min[warp] = dmin;
     __syncthreads();
-    for (int w = 0; w < nwarps; ++w) vmax = fmaxf(vmax, warp_vmax[w]);
-    // the (C, D) form rounds three times at the magnitude of range * scale: fine while 1.5 ulp of that stays below
-    // 6e-6 of the output range (the standard configs: 2 * 30 m -> 5.7e-6); otherwise blend around the row's own range
-    const bool precise = a.centered && 1.5f * (vmax * scale) * 1.1920929e-7f > 6.0e-6f;
-    if (precise)                                             // rare: restage as (v, v' - v) in metres
-        for (int i = tid; i <= a.N; i += T) {
-            const float v0 = fminf(vals[min(i, nm1)], 1e6f), v1 = fminf(vals[min(i + 1, nm1)], 1e6f);
-            pairs[i] = make_float2(v0, v1 - v0);
-        }
 
     // ---- the scan's maximal index span, from the rows nearest to the sensor -----------------------------
     int s_area = 0;
-    if (precise && !(a.area_mode || a.s_area_out)) __syncthreads();     // restaged pairs (the other branch has its own barrier)
     if (a.area_mode || a.s_area_out) {
         dmin = warp_min[0];
         for (int w = 1; w < nwarps; ++w) dmin = fminf(dmin, warp_min[w]);
@@ -766,11 +746,10 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 2) cutout_scan_kernel(cons
         const bool valid = lane < rows_here;
         bool is_area = false;
         long long fx_base = 0, fx_slope = 0, fx_slope_a = 0;
-        float lo_f = 0.f, hi_f = 0.f, pad_f = 0.f, bias = 0.f, range = 0.f;
+        float lo_f = 0.f, hi_f = 0.f, pad_f = 0.f, bias = 0.f;
         if (valid) {                                          // :274-285, from the staged scan
             const int m = m0 + lane, i = m * a.stride;
             const float d = vals[i];
-            range = d;
             const float ratio = __fdiv_rn(a.half_width, fmaxf(d, 1e-2f));
             const float ha = ha_in ? __ldg(ha_in + m) : atan_f32_tab(ratio, atab);             // :279
             if (ha_out) ha_out[m] = ha;
@@ -811,13 +790,8 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 2) cutout_scan_kernel(cons
         // ---- two-tap rows ---------------------------------------------------------------------------
         if (valid && !is_area) {
             float* dst = tile + lane * P;
-            if (!precise) {
-                if (inside) scan_row<true, false>(fx0, fx_slope, rot, nchunks, pairs, nm1, limit, bias, scale, lo_f, hi_f, pad_f, dst);
-                else scan_row<false, false>(fx0, fx_slope, rot, nchunks, pairs, nm1, limit, bias, scale, lo_f, hi_f, pad_f, dst);
-            } else {                                          // CTA-uniform
-                if (inside) scan_row<true, true>(fx0, fx_slope, rot, nchunks, pairs, nm1, limit, range, scale, lo_f, hi_f, pad_f, dst);
-                else scan_row<false, true>(fx0, fx_slope, rot, nchunks, pairs, nm1, limit, range, scale, lo_f, hi_f, pad_f, dst);
-            }
+            if (inside) scan_row<true>(fx0, fx_slope, rot, nchunks, pairs, nm1, limit, bias, lo_f, hi_f, pad_f, dst);
+            else scan_row<false>(fx0, fx_slope, rot, nchunks, pairs, nm1, limit, bias, lo_f, hi_f, pad_f, dst);
         }
 
         // ---- area rows of the group: one at a time, the lanes along its samples (:310-323) --------------
@@ -972,7 +946,14 @@ int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64, int B, i
     a.fixed = fixed; a.centered = centered; a.area_mode = area_mode;
     POF_REQUIRE((long long)a.tiles_per_scan * B * S < (1ll << 31), POF_ERR_BAD_SHAPE, "pof_cutout_fwd: too many tiles");
 
-    if (numerics == POF_CUTOUT_FAST && S == 1) {        // one CTA per scan: span reduction, half-angles and samples in one launch
+    // The scan kernel blends in output units: three roundings at the magnitude of range * scale.  That is within the
+    // FAST contract (1e-5 of the output range) while 1.5 ulp(padding_val * scale) <= 6e-6 - every config of the
+    // reference (2 x 30 m: 5.7e-6; ranges are clipped to padding_val upstream) - otherwise the rows kernel, which
+    // blends in metres first, takes the call.
+    int mag_exp = 0;
+    frexp(centered ? fabs(padding_val / window_depth) : 0.0, &mag_exp);           // |x| = m * 2^e, 0.5 <= m < 1
+    const bool coarse = 1.5 * ldexp(1.0, mag_exp - 1 - 23) > 6.0e-6;              // 1.5 float32 ulps of padding_val * scale
+    if (numerics == POF_CUTOUT_FAST && S == 1 && !coarse) {        // one CTA per scan: span reduction, half-angles and samples in one launch
         int status = POF_OK;
         if (phi_is_f64 ? launch_cutout_scan<double>(a, stream, &status) : launch_cutout_scan<float>(a, stream, &status)) return status;
     }
