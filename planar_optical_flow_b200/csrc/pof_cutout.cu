@@ -531,7 +531,16 @@ __global__ void __launch_bounds__(kThreads) cutout_rows_kernel(const CutoutArgs 
 //             group's area rows are then resampled by the whole warp, two rows at a time.  The 32 rows are
 //             adjacent in the output, so they leave as ONE TMA bulk store issued by lane 0.  No CTA-wide
 //             barrier after the set-up.
-constexpr int kScanWarpsMax = 12;
+constexpr int kScanWarpsMax = 4;       // measured 4 > 5 > 6 > 8 > 12 warps per CTA (five 4-warp CTAs fit an SM)
+// tuning knobs (build.build_variant): launch bounds of the scan kernel and the unroll factor of its sample loop
+#ifndef POF_SCAN_LB_THREADS
+#define POF_SCAN_LB_THREADS (kScanWarpsMax * 32)
+#define POF_SCAN_LB_BLOCKS 5
+#endif
+#ifndef POF_SCAN_UNROLL
+#define POF_SCAN_UNROLL 2
+#endif
+constexpr int kScanUnroll = POF_SCAN_UNROLL;
 
 __device__ __forceinline__ unsigned hi32(long long v) {
     unsigned lo, hi;
@@ -580,7 +589,7 @@ __device__ __forceinline__ void scan_row(long long fx0, long long slope, unsigne
     float* p = dst + 4 * rot;
     ChunkTaps t0, t1;
     chunk_load<INSIDE>(t0, fx, slope, pairs, nm1, limit);
-#pragma unroll(INSIDE ? 2 : 1)
+#pragma unroll(INSIDE ? kScanUnroll : 1)
     for (int j = 0; j < nchunks - 2; ++j, p += 4) {
         chunk_load<INSIDE>(t1, fx, slope, pairs, nm1, limit);
         chunk_finish<INSIDE>(t0, bias, lo_f, hi_f, pad_f, p);
@@ -659,7 +668,7 @@ __device__ __forceinline__ float div_taps(float acc, float taps_f, float taps_rc
 __device__ __forceinline__ unsigned nchunks_rot(int P, int lane) { return P >= 8 ? ((unsigned)lane >> 2) & 1u : 0u; }
 
 template <typename PhiT>
-__global__ void __launch_bounds__(kScanWarpsMax * 32, 2) cutout_scan_kernel(const CutoutArgs a) {
+__global__ void __launch_bounds__(POF_SCAN_LB_THREADS, POF_SCAN_LB_BLOCKS) cutout_scan_kernel(const CutoutArgs a) {
     extern __shared__ __align__(16) float smem_f[];          // pairs [N+1] float2 | arctangent table | ranges [N] | per-warp tiles [32][P]
     __shared__ double warp_span[kScanWarpsMax];
     __shared__ float warp_min[kScanWarpsMax];

@@ -391,7 +391,7 @@ class StreamingDetector:
         with self._precision():
             with self._timed("cutout"):      # one launch for all B sequences: [B, N, 1, P]
                 cutouts = ops.cutout(scans.unsqueeze(1), self.phi, fast=True, **self.cutout_kwargs)
-            self.kernel_launches += 2 if self.cutout_kwargs.get("area_mode") else 1
+            self.kernel_launches += 1          # cutout_scan_kernel: span reduction, half-angles and samples in one launch
             chunk = self._chunk_channels_last if self.channels_last else self._chunk_ncl
             for b0 in range(0, B, self.seq_chunk):
                 chunk(cutouts, b0, min(B, b0 + self.seq_chunk), first, prev, nxt, pred_cls, pred_reg, feat_fused)
