@@ -28,8 +28,58 @@ from .loss_utils import BinaryFocalLoss, FocalLoss, flow_loss
 _SLOPE = 0.1
 
 
+class _ConvBnAct(nn.Sequential):
+    """Conv1d + BatchNorm1d + LeakyReLU with the reference's child names ("0", "1", "2": dr_spaam.py:8-12).
+
+    A 3-D input [M, C, L] runs the children as the reference does.  A 4-D channels-last input [M, C, 1, L] (the
+    training branch of SpatialDROW) runs the SAME parameters through conv2d / batch_norm: cuDNN then stays in NHWC for
+    the TF32 implicit GEMMs and the batch-norm statistics, instead of transposing around every convolution and using
+    its per-channel NCHW batch-norm kernels, which took 45 % + 16 % of the training step (profiles/r1_train_step.txt).
+    """
+
+    def forward(self, x):
+        if x.dim() != 4:
+            return super().forward(x)
+        conv, bn = self[0], self[1]
+        w4, pad = conv.weight.unsqueeze(2), (0, conv.padding[0])
+        track = bn.track_running_stats
+        if not (bn.training or not track):                      # eval: running statistics
+            y = F.batch_norm(F.conv2d(x, w4, conv.bias, padding=pad), bn.running_mean, bn.running_var, bn.weight, bn.bias,
+                             False, 0.0, bn.eps)
+            return F.leaky_relu_(y, _SLOPE)
+        # Batch statistics: the convolution's bias cancels in (y + b) - mean(y + b), so it is left out of the forward
+        # pass (no bias-add pass, and no reduction of the output gradient for a bias gradient that is zero in exact
+        # arithmetic - 27 % of the step).  It still belongs to the running mean, and it still gets its (zero) gradient.
+        if bn.training and track:
+            bn.num_batches_tracked.add_(1)
+        factor = bn.momentum if bn.momentum is not None else 1.0 / max(float(bn.num_batches_tracked), 1.0)
+        skip_bias = conv.bias is not None and factor < 1.0
+        if skip_bias and bn.training and track:
+            # rm <- (1 - f) rm + f (mean(y) + b): fold f b in before batch_norm's own update.  Through .data: earlier calls of
+            # the same layer in this step (the gate embeds every scan) saved the buffer, and a version bump would make
+            # autograd refuse their backward although batch-statistics backward never reads it.
+            bn.running_mean.data.add_(conv.bias.detach(), alpha=factor / (1.0 - factor))
+        y = F.batch_norm(F.conv2d(x, w4, None if skip_bias else conv.bias, padding=pad), bn.running_mean if track else None,
+                         bn.running_var if track else None, bn.weight, bn.bias, True, factor, bn.eps)
+        y = F.leaky_relu_(y, _SLOPE)
+        return _ZeroGradOperand.apply(y, conv.bias) if skip_bias else y
+
+
+class _ZeroGradOperand(torch.autograd.Function):
+    """y unchanged; `p` joins the graph with an exactly-zero gradient (DDP wants every parameter to receive one)."""
+
+    @staticmethod
+    def forward(ctx, y, p):
+        ctx.p_shape, ctx.p_dtype, ctx.p_device = p.shape, p.dtype, p.device
+        return y.view_as(y)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, torch.zeros(ctx.p_shape, dtype=ctx.p_dtype, device=ctx.p_device)
+
+
 def _conv(in_channel, out_channel, kernel_size, padding):
-    return nn.Sequential(
+    return _ConvBnAct(
         nn.Conv1d(in_channel, out_channel, kernel_size=kernel_size, padding=padding),
         nn.BatchNorm1d(out_channel),
         nn.LeakyReLU(negative_slope=_SLOPE, inplace=True),
@@ -78,6 +128,28 @@ class DROW(nn.Module):
 
     def _fuse_cutout(self, x):
         return torch.sum(x, dim=2)
+
+    # -- the same two halves on channels-last 4-D activations [M, C, 1, L] (see _ConvBnAct) ------------------
+    def _features_cl(self, scan_cutouts):
+        """[B, N, P] cutouts of one scan -> [B*N, 256, 1, P/4], channels-last memory."""
+        b, n, p = scan_cutouts.shape
+        y = scan_cutouts.reshape(b * n, 1, 1, p).contiguous(memory_format=torch.channels_last)
+        for blk in (self.conv_block_1, self.conv_block_2):
+            for layer in blk:
+                y = layer(y)
+            y = F.max_pool2d(y, kernel_size=(1, 2))
+        return y
+
+    def _votes_cl(self, t, b, n):
+        """[B*N, 256, 1, L] channels-last fused features -> ([B, N, C], [B, N, 2])."""
+        y = t
+        for layer in self.conv_block_3:
+            y = layer(y)
+        y = F.max_pool2d(y, kernel_size=(1, 2))
+        for layer in self.conv_block_4:
+            y = layer(y)
+        y = y.mean(dim=3)                                      # avg_pool1d over the whole length: [M, 128, 1]
+        return self.conv_cls(y).view(b, n, -1), self.conv_reg(y).view(b, n, 2)
 
     # -- fused feature -> votes: [B, N, 256, L] -> ([B, N, C], [B, N, 2])     (:102-114)
     def _forward_fused_cutout(self, x):
@@ -139,10 +211,21 @@ class SpatialDROW(DROW):
             pred_cls, pred_reg = self._forward_fused_cutout(out_template)
             return pred_cls, pred_reg, out_template, feat_fused
 
-        n_scan = x.shape[2]                                           # training / eval branch (:262-277)
-        out_template = self._scan_features(x, 0)
+        # training / eval branch (:262-277), on channels-last activations.  The gate kernel works on whole rows of
+        # C*L features and only needs x and the memory to agree on their order: here both are [L, C]
+        b, n, n_scan = x.shape[0], x.shape[1], x.shape[2]
+
+        def rows(t4):                                                 # [M, C, 1, L] channels-last -> [B, N, L, C] view
+            return t4.permute(0, 2, 3, 1).reshape(b, n, t4.shape[3], t4.shape[1])
+
+        def embed(t4):
+            return self.gate.conv(t4).view(b, n, -1)
+
+        tmpl = self._features_cl(x[:, :, 0, :])
         feat_fused = None
         for s in range(1, max(n_scan, 2)):          # a single-scan input gates scan 0 with itself (:271-273)
-            out_template, feat_fused = self.gate(self._scan_features(x, min(s, n_scan - 1)), out_template)
-        pred_cls, pred_reg = self._forward_fused_cutout(out_template)
+            cur = self._features_cl(x[:, :, min(s, n_scan - 1), :])
+            out_rows, feat_fused = ops.gate(rows(cur), rows(tmpl), embed(cur), embed(tmpl), self.gate._alpha, self.gate.window)
+            tmpl = out_rows.view(b * n, 1, out_rows.shape[2], out_rows.shape[3]).permute(0, 3, 1, 2)
+        pred_cls, pred_reg = self._votes_cl(tmpl, b, n)
         return pred_cls, pred_reg, feat_fused
