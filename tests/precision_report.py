@@ -1,6 +1,6 @@
 """Relative error (vs the CPU oracle, magnitude-relative) of every engine precision mode, per output and step.
 
-    python tools/precision_report.py [steps] [sequences] [points]        (needs a B200; reads nothing outside the repo)
+    python tests/precision_report.py [steps] [sequences] [points]        (needs a B200; reads nothing outside the repo)
 """
 import os
 import sys
