@@ -293,10 +293,12 @@ def run_ours(args):
         buf = torch.empty((cb, N, 1, CUTOUT_KW["num_cutout_pts"]), dtype=torch.float32, device=dev)
         cut_sweep = {}
         for name, fast in (("fast", True), ("exact", False)):
-            for _ in range(3):
+            # the sweep follows seconds of power-capped tensor-core work: let the SM clock settle at THIS kernel's power
+            # level (~0.15 s of its own launches) before timing it - it is issue bound, so its time follows the clock
+            for _ in range(400 if fast else 200):
                 ops.cutout(big, phi_d, out=buf, fast=fast, **CUTOUT_KW)
             torch.cuda.synchronize(dev)
-            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
             for s_ev, e_ev in ev:
                 s_ev.record()
                 ops.cutout(big, phi_d, out=buf, fast=fast, **CUTOUT_KW)
