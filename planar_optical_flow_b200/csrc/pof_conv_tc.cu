@@ -77,11 +77,13 @@ struct Cfg {
     static constexpr int kBTile = (BN / CG) * kRowBytes;       // this CTA's share of one W operand tile (hi or lo)
     static constexpr int kStage = 2 * kATile + 2 * kBTile;     // streamed weights: a stage holds A hi/lo and W hi/lo of one k-block
     static constexpr int kStageA = 2 * kATile;                 // resident weights: a stage holds A hi/lo only
-    // Epilogue warps: 8 (two column halves per TMEM lane quarter) for the wide tile, whose epilogue hides behind the
-    // tensor pipe; 16 (four column quarters) for the narrow tiles, which are bound by the issue rate of dependent
-    // epilogue code - two warps per scheduler cannot fill it, four can.  (With 16 warps the register budget is
-    // 96 per thread, enough for 32 accumulators but not for the wide tile's 64.)
-    static constexpr int kEpiWarps = BN == 128 ? 16 : 8;      // (BN = 64 would leave 16 columns per thread: keeps 8)
+    // Epilogue warps: 8 (two column halves per TMEM lane quarter).  A 16-warp form (four column quarters, 96 registers
+    // per thread) exists for the 128-column tile behind POF_CONV_EPI16: it was expected to help the narrow layers'
+    // dependent epilogue code and measured 2-5 % slower.
+#ifndef POF_CONV_EPI16
+#define POF_CONV_EPI16 0     // measured on one GPU (A/B): 64->128 0.85 ms with 16 epilogue warps, 0.81 ms with 8
+#endif
+    static constexpr int kEpiWarps = (BN == 128 && POF_CONV_EPI16) ? 16 : 8;      // (BN = 64 would leave 16 columns per thread: keeps 8)
     static constexpr int kThreads = kThreadsBase + 32 * kEpiWarps;
     static constexpr int kSlices = kEpiWarps / 4;              // column slices per TMEM lane quarter
     static constexpr int kAcc = BN / kSlices;                  // accumulators per epilogue thread
@@ -668,7 +670,7 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
         const long long w_bytes = (long long)n_kb * 2 * b_tile;
         const int stage_a = 2 * kTileM * kRowBytes, stage_full = stage_a + 2 * b_tile;
         const bool forbid = (chain_flags & POF_CONV_TC_STREAM_W) != 0;
-        const long long ring = bn == 128 ? kRingBytes - 8 * kStagingWarp : kRingBytes;      // Cfg<BN, CG>::kRing
+        const long long ring = (bn == 128 && POF_CONV_EPI16) ? kRingBytes - 8 * kStagingWarp : kRingBytes;      // Cfg<BN, CG>::kRing
         p.w_resident = !forbid && p.tiles_n == 1 && w_bytes <= ring - 4 * stage_a;
         const long long st = p.w_resident ? (ring - w_bytes) / stage_a : ring / stage_full;
         p.stages = (int)(st < kMaxStages ? st : kMaxStages);
