@@ -298,13 +298,15 @@ def run_ours(args):
             for _ in range(400 if fast else 200):
                 ops.cutout(big, phi_d, out=buf, fast=fast, **CUTOUT_KW)
             torch.cuda.synchronize(dev)
-            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
-            for s_ev, e_ev in ev:
-                s_ev.record()
+            # 20 back-to-back launches between ONE event pair: the average launch duration of the kernel in steady state
+            # (an event pair per launch adds the 3-5 us a start event waits for the launch that follows it)
+            s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_ev.record()
+            for _ in range(20):
                 ops.cutout(big, phi_d, out=buf, fast=fast, **CUTOUT_KW)
-                e_ev.record()
+            e_ev.record()
             torch.cuda.synchronize(dev)
-            cut_sweep[name] = sum(s_ev.elapsed_time(e_ev) for s_ev, e_ev in ev) / len(ev)
+            cut_sweep[name] = s_ev.elapsed_time(e_ev) / 20
         cut_sweep["batch"] = cb
         del big, buf
         torch.cuda.empty_cache()
