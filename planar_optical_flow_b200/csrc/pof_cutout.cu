@@ -696,8 +696,10 @@ __global__ void __launch_bounds__(POF_SCAN_LB_THREADS, POF_SCAN_LB_BLOCKS) cutou
         const float D = (v1 - v0) * scale;
         pairs[i] = make_float2(fmaf(v0, scale, -D), D);
         if (i < a.N) vals[i] = r0;
+        if (a.stride == 1) dmin = fminf(dmin, fmaxf(r0, 1e-2f));     // every beam is a row (entry N repeats beam N-1)
     }
-    for (int m = tid; m < a.M; m += T) dmin = fminf(dmin, fmaxf(__ldg(scan + m * a.stride), 1e-2f));
+    if (a.stride != 1)
+        for (int m = tid; m < a.M; m += T) dmin = fminf(dmin, fmaxf(__ldg(scan + m * a.stride), 1e-2f));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
     if (lane == 0) warp_min[warp] = dmin;
