@@ -54,6 +54,9 @@ namespace {
 
 constexpr int kThreadsBase = 128;               // warps 0-3: TMA producer, MMA issuer, TMEM allocator, (idle)
 constexpr int kTileM = 128;
+#ifndef POF_CONV_L2_PROMO
+#define POF_CONV_L2_PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+#endif
 #ifndef POF_CONV_ROW_BYTES
 #define POF_CONV_ROW_BYTES 128
 #endif
@@ -366,10 +369,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
                     if (!(ok = mbar_wait(empty(s), ph ^ 1u, p.status, 1))) break;
                     const int tap = kb / kb_per_tap, c0 = (kb - tap * kb_per_tap) * kKBlock;
+#ifndef POF_CONV_NO_PREFETCH
                     if (warm && tap == p.pad) {                      // the unshifted tap covers every row of the tile
                         tma_prefetch_3d(&map_a, c0, 0, (int)m0_nx);
                         tma_prefetch_3d(&map_a, p.Cin + c0, 0, (int)m0_nx);
                     }
+#else
+                    (void)warm; (void)m0_nx;
+#endif
                     const unsigned dst = ring + (unsigned)s * stage_bytes;
                     if (CG == 1) {
                         mbar_expect_tx(full(s), tx);
@@ -684,7 +691,7 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
         const cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)Lout, (cuuint32_t)p.mt};
         const cuuint32_t es[3] = {1, 1, 1};
         const CUresult r = enc(&ma, dt, 3, const_cast<void*>(a_split), dims, strides, box, es,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, kRowBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, kRowBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, POF_CONV_L2_PROMO,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         POF_REQUIRE(r == CUDA_SUCCESS, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
     }
@@ -694,7 +701,7 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
         const cuuint32_t box[2] = {(cuuint32_t)kb, (cuuint32_t)(bn / cg)};            // each CTA of a pair loads its half
         const cuuint32_t es[2] = {1, 1};
         const CUresult r = enc(&mw, dt, 2, const_cast<void*>(w_split), dims, strides, box, es,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, kRowBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, kRowBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, POF_CONV_L2_PROMO,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         POF_REQUIRE(r == CUDA_SUCCESS, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
     }
