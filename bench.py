@@ -382,8 +382,8 @@ def run_ours(args):
                             "exact_arithmetic": {"achieved": sweep_gbs["exact"], "frac": sweep_gbs["exact"] / peak,
                                                  "avg_launch_ms": cut_sweep["exact"]},
                             "in_streaming_step": {"achieved": cut_gbs, "frac": cut_gbs / peak, "avg_launch_ms": cut_avg_ms,
-                                                  "note": "one launch pair per step over %d sequences (64 MB): "
-                                                          "launch-latency bound at this size" % B}},
+                                                  "note": "the engine's own cutout call (EXACT arithmetic, span + cutout launch) per step "
+                                                          "over %d sequences (64 MB): launch-latency bound at this size" % B}},
         "stage_ms_per_step": {"cutout": sum(cut_ms) / K, "gate": sum(gate_ms) / K, "nms": sum(nms_ms) / K,
                               "convolutions_tcgen05": sum(sum(v) for v in conv_ms.values()) / K,
                               "rest": ms_dev / K - (sum(cut_ms) + sum(gate_ms) + sum(nms_ms) + sum(sum(v) for v in conv_ms.values())) / K},

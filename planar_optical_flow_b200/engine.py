@@ -208,7 +208,7 @@ class StreamingDetector:
     """
 
     def __init__(self, model, scan_phi, cutout_kwargs, num_sequences, device=None, precision="fp32",
-                 min_dist=0.5, seq_chunk=None, record_events=False):
+                 min_dist=0.5, seq_chunk=None, record_events=False, cutout_fast=False):
         if not torch.cuda.is_available():
             raise RuntimeError("StreamingDetector needs a CUDA device; there is no CPU path")
         if precision not in ("fp32", "fp32-tf32", "fp32-simt", "tf32x3", "tf32"):
@@ -216,6 +216,9 @@ class StreamingDetector:
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.precision = precision
         self.cutout_kwargs = dict(cutout_kwargs)
+        # The cutout is 0.1 % of a step, so the engine takes the reference's exact arithmetic (bit-equal samples given the
+        # half-angles); cutout_fast=True selects the fixed-point kernel that the cutout-only sweep is about (1e-5 bar).
+        self.cutout_fast = bool(cutout_fast)
         self.min_dist = float(min_dist)
         self.B = int(num_sequences)
         phi = np.ascontiguousarray(scan_phi)
@@ -390,8 +393,9 @@ class StreamingDetector:
         first = not self.has_memory
         with self._precision():
             with self._timed("cutout"):      # one launch for all B sequences: [B, N, 1, P]
-                cutouts = ops.cutout(scans.unsqueeze(1), self.phi, fast=True, **self.cutout_kwargs)
-            self.kernel_launches += 1          # cutout_scan_kernel: span reduction, half-angles and samples in one launch
+                cutouts = ops.cutout(scans.unsqueeze(1), self.phi, fast=self.cutout_fast, **self.cutout_kwargs)
+            # FAST: cutout_scan_kernel does the span reduction, the half-angles and the samples in one launch
+            self.kernel_launches += 1 if self.cutout_fast else (2 if self.cutout_kwargs.get("area_mode") else 1)
             chunk = self._chunk_channels_last if self.channels_last else self._chunk_ncl
             for b0 in range(0, B, self.seq_chunk):
                 chunk(cutouts, b0, min(B, b0 + self.seq_chunk), first, prev, nxt, pred_cls, pred_reg, feat_fused)
