@@ -220,7 +220,10 @@ _conv_tc_status = {}
 
 def conv_tc_status(device):
     """The device-side status word of `conv_tc` launches on `device` (0 = every pipeline wait completed)."""
-    t = _conv_tc_status.get(torch.device(device))
+    dev = torch.device(device)
+    if dev.type == "cuda" and dev.index is None:          # "cuda" means the current device, as everywhere in torch
+        dev = torch.device("cuda", torch.cuda.current_device())
+    t = _conv_tc_status.get(dev)
     return 0 if t is None else int(t.item())
 
 
