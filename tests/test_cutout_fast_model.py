@@ -3,11 +3,11 @@
 The scan kernel (csrc/pof_cutout.cu::cutout_scan_kernel) replaces the reference's float64 index / blend arithmetic by
   * a 32.32 fixed-point sample index (base and step rounded once, then a running 64-bit add; + 2^-24 so that the
     23-bit fraction is rounded rather than truncated),
-  * blend pairs (C, D) = (v*scale - D, (v' - v)*scale) in float32 and ONE fma on w' = 1.fraction, + the row's bias,
+  * blend pairs (V, D) = (v*scale, (v' - v)*scale) in float32, (V - d*scale) first, then ONE fma on the fraction,
   * float32 clip bounds.
-This model evaluates exactly that arithmetic for two-tap rows and checks the error budget DESIGN.md states: within 1e-5
-of the output range for the reference's configs (range * scale <= 60), so the bound is a property of the arithmetic,
-not only of the inputs the GPU tests happen to use."""
+This model evaluates exactly that arithmetic for two-tap rows and checks the error budget DESIGN.md states (5e-6 of the
+output range; the reference's bar is 1e-5), so the bound is a property of the arithmetic, not only of the inputs the GPU
+tests happen to use."""
 import numpy as np
 import pytest
 
@@ -29,8 +29,8 @@ def fast_model(scan, phi, window_width, window_depth, num_cutout_pts, padding_va
     v0 = np.minimum(scan, np.float32(1e6))
     v1 = np.minimum(np.append(scan[1:], scan[-1]), np.float32(1e6))
     D = ((v1 - v0) * scale).astype(np.float32)
-    C = _fma32(v0, np.full(n, scale, np.float32), -D)
-    C, D = np.append(C, C[-1]), np.append(D, D[-1])                    # entry N repeats beam N - 1
+    V = (v0 * scale).astype(np.float32)
+    V, D = np.append(V, V[-1]), np.append(D, D[-1])                    # entry N repeats beam N - 1
     ha = np.asarray(half_alpha, np.float32)
     step = ((np.float32(2.0) * ha) / np.float32(P - 1)).astype(np.float32)
     start = (phi - ha.astype(phi.dtype)).astype(np.float64)
@@ -48,7 +48,7 @@ def fast_model(scan, phi, window_width, window_depth, num_cutout_pts, padding_va
     lo = (((d - depth) - d) * scale).astype(np.float32)
     hi = (((d + depth) - d) * scale).astype(np.float32)
     pad = np.minimum(np.maximum(((np.float32(padding_val) - d) * scale).astype(np.float32), lo), hi)
-    x = (_fma32(w, D[beam], C[beam]) + bias).astype(np.float32)
+    x = _fma32((w - np.float32(1.0)).astype(np.float32), D[beam], (V[beam] + bias).astype(np.float32))
     out = np.minimum(np.maximum(x, lo), hi)
     return np.where(inside, out, pad).astype(np.float32)
 
@@ -66,5 +66,5 @@ def test_fast_arithmetic_stays_within_the_parity_bar(shape, kind, seed):
     # a sample whose index sits within 2^-24 of a beam or of the scan's end may take the other side of a floor / bound test
     diag = ocut.cutout_diagnostics(scans, phi, half_alpha=ha, **CFG)
     near_edge = diag["edge_margin"].transpose(1, 0, 2)[:, 0, :] < 1e-6
-    assert err[~near_edge].max() <= 1e-5, err[~near_edge].max()
+    assert err[~near_edge].max() <= 5e-6, err[~near_edge].max()      # 2^-24 of the fraction x the largest neighbour difference
     print("max error %.2e, bit-equal %.1f %%" % (err[~near_edge].max(), 100 * (got == want).mean()))
