@@ -15,7 +15,8 @@ One JSON line on stdout (rank 0):
              of the detections inside the timed region
   roofline   the dominant kernel of the step, the tcgen05 convolution (conv_tc_kernel<256,2>): algorithmic
              fp32 FLOPs (45.9 MFLOP per point) / CUDA-event time around every launch
-             inside the timed steps, against the measured bf16 peak / 2 (TF32 rate)
+             inside the timed steps, against the measured sustained bf16 peak (kind::f16 runs at the bf16 rate; the
+             kernel issues three MMAs per algorithmic product, reported beside it as mma_tflops)
   roofline_gate / roofline_cutout   the two HBM-bound hot-path kernels: algorithmic bytes (SURVEY.md
              §8d: N*44,076 B per sequence-step, N*228 B per scan row) / CUDA-event launch time,
              against the measured copy bandwidth (MEASURED_PEAKS.json)

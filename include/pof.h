@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define POF_ABI_VERSION 1
+#define POF_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define POF_API __attribute__((visibility("default")))
@@ -119,11 +119,19 @@ POF_API int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64,
  *    feat_fused   [B, N, W] float   raw similarities at CLAMPED neighbour indices (:187)
  *    attn_w       [B, N, W] float or NULL   softmax weights over the UNIQUE in-range
  *                                   neighbours (0 on clamped duplicates); saved for bwd
+ *    out_split    [B, N, CL / split_channels, 2 * split_channels] binary16 or NULL
+ *                                   the new memory again as the [hi | lo] operand rows of
+ *                                   pof_conv_tc_f16_fwd (channels-last memory rows of
+ *                                   split_channels channels), written in the same pass
+ *    status       device int or NULL   set to 32 if a staged copy never landed (results
+ *                                   invalid), 16 if a value of out_split left the binary16
+ *                                   range; the caller zeroes it
  * ------------------------------------------------------------------------- */
 POF_API int pof_spaam_gate_fwd(const float* x, const float* tmpl,
                        const float* emb_x, const float* emb_t,
                        int B, int N, int CL, int E, int W, float alpha,
                        float* out_tmpl, float* feat_fused, float* attn_w,
+                       void* out_split, int split_channels, int* status,
                        void* stream);
 
 /*    Backward of the above for training (autograd through the sequential gate
@@ -188,22 +196,27 @@ POF_API int pof_nms_centers(const void* scan, int scan_is_f64, const void* phi, 
  *                        cutout are its L positions, L even); slope = 1 -> identity.
  *    pof_conv_first_fwd  cutouts [M, P] (x) weight [C, 3], bias [C] -> [M*P, C] / [M*P, 3C]:
  *                        the 1 -> C, k = 3, zero-padded first layer + LeakyReLU (+ split).
+ *    `status` (device int or NULL): with split_parts = POF_SPLIT_F16 an activation beyond 65504 sets it to 16.
  * ------------------------------------------------------------------------- */
 #define POF_SPLIT_F16 16   /* split_parts: out_split rows are [hi | lo] in binary16 (operand of pof_conv_tc_f16_fwd) */
 POF_API int pof_act_fwd(const float* y, const float* bias, long long rows_in, int C, int pool,
-                        float slope, float* out_plain, void* out_split, int split_parts, void* stream);
+                        float slope, float* out_plain, void* out_split, int split_parts, int* status,
+                        void* stream);
 
 POF_API int pof_conv_first_fwd(const float* cutouts, const float* weight, const float* bias,
                                long long M, int P, int C, float slope,
-                               float* out_plain, void* out_split, int split_parts, void* stream);
+                               float* out_plain, void* out_split, int split_parts, int* status, void* stream);
 
 /*    pof_head_fwd        the tail of DROW._forward_fused_cutout (dr_spaam.py:110-114): y [M, L, C] raw
  *                        output of the last convolution -> +bias, LeakyReLU -> avg_pool1d over L ->
  *                        H 1x1-convolution heads (w_head [H, C], b_head [H]; conv_cls rows first, then
- *                        conv_reg) -> sigmoid on the first n_sigmoid heads -> out [M, H].  H <= 8.       */
+ *                        conv_reg) -> sigmoid on the first n_sigmoid heads -> out [M, H].  H <= 8.
+ *                        With out_rest != NULL the heads are written as two matrices instead: the first
+ *                        n_sigmoid to out [M, n_sigmoid], the others to out_rest [M, H - n_sigmoid] (the
+ *                        pred_cls / pred_reg tensors of dr_spaam.py:116-121).                            */
 POF_API int pof_head_fwd(const float* y, const float* bias, long long M, int L, int C, float slope,
                          const float* w_head, const float* b_head, int H, int n_sigmoid,
-                         float* out, void* stream);
+                         float* out, float* out_rest, void* stream);
 
 /*    pof_conv_tc_fwd     fp32-accurate convolution / whole-row GEMM on tcgen05 (3xTF32 split products,
  *                        chained accumulation promoted to fp32 registers):

@@ -12,7 +12,7 @@ import threading
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("POF_LIB") or os.path.join(_PKG_DIR, "libpof.so")      # POF_LIB: a tuning variant (build.build_variant)
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lock = threading.Lock()
 _lib = None
@@ -33,20 +33,20 @@ SIGNATURES = {
                                c_double, c_double, c_double, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pof_spaam_gate_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                   c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                   c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "pof_spaam_gate_bwd_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pof_spaam_gate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int, c_int, c_int, c_int, c_int, c_float,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "pof_act_fwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p]),
+    "pof_act_fwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "pof_conv_first_fwd": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_float,
-                                   c_void_p, c_void_p, c_int, c_void_p]),
+                                   c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "pof_conv_tc_fwd": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pof_conv_tc_f16_fwd": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pof_head_fwd": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_int,
-                             c_void_p, c_void_p]),
+                             c_void_p, c_void_p, c_void_p]),
     "pof_patch_corr_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pof_patch_corr_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "pof_cutout_original_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_double, c_double, c_double,
@@ -67,10 +67,20 @@ def lib():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.isfile(LIB_PATH) or os.environ.get("POF_REBUILD") == "1":
+        if not os.environ.get("POF_LIB"):          # a tuning variant is loaded as it is
             from . import build as _build
 
-            _build.build(force=os.environ.get("POF_REBUILD") == "1")
+            force = os.environ.get("POF_REBUILD") == "1"
+            missing = not os.path.isfile(LIB_PATH)
+            if force or missing or _build._stale():
+                try:
+                    _build.build(force=force)
+                except RuntimeError:
+                    if force or missing:               # nothing to load: fail loudly (there is no CPU fallback)
+                        raise
+                    import warnings                    # no nvcc on this box: say that the sources are newer than the binary
+
+                    warnings.warn("libpof.so is older than its sources and could not be rebuilt here; loading the stale binary")
         try:
             handle = ctypes.CDLL(LIB_PATH)
         except OSError as e:  # noqa: PERF203

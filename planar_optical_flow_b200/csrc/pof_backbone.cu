@@ -37,9 +37,10 @@ __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? 
 // parts = 3: [hi | lo | hi] with the exact remainder (operand of a cuDNN TF32 convolution against
 //            [w_hi | w_hi | w_lo]);  parts = 2: [hi | lo] with lo rounded to TF32 (operand of pof_conv_tc_fwd).
 //            parts = POF_SPLIT_F16: [hi | lo] in binary16 (operand of pof_conv_tc_f16_fwd).
-__device__ __forceinline__ void emit(float4 v, size_t row, int c, int C, float* plain, void* split_, int parts) {
+__device__ __forceinline__ void emit(float4 v, size_t row, int c, int C, float* plain, void* split_, int parts, float& amax) {
     if (plain) *reinterpret_cast<float4*>(plain + row * C + c) = v;
     if (split_ && parts == POF_SPLIT_F16) {
+        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
         const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
         const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
         const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
@@ -65,7 +66,8 @@ __device__ __forceinline__ void emit(float4 v, size_t row, int c, int C, float* 
 
 template <int POOL>
 __global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ y, const float* __restrict__ bias, float slope,
-                                                  int C, long long rows_out, float* plain, void* split, int parts) {
+                                                  int C, long long rows_out, float* plain, void* split, int parts, int* status) {
+    float amax = 0.f;
     const int c4n = C >> 2;
     const long long total = rows_out * c4n;
     const bool small = total < (1ll << 32);             // 32-bit index arithmetic (a 64-bit division costs ~50 issue slots)
@@ -79,8 +81,9 @@ __global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ y, c
             v = make_float4(fmaxf(v.x, w.x), fmaxf(v.y, w.y), fmaxf(v.z, w.z), fmaxf(v.w, w.w));   // lrelu is monotone
         }
         v = make_float4(lrelu(v.x + b.x, slope), lrelu(v.y + b.y, slope), lrelu(v.z + b.z, slope), lrelu(v.w + b.w, slope));
-        emit(v, (size_t)row, c, C, plain, split, parts);
+        emit(v, (size_t)row, c, C, plain, split, parts, amax);
     }
+    if (status && !(amax <= 65504.f)) atomicCAS(status, 0, 16);      // beyond binary16 (or NaN): the split is not a split
 }
 
 // out[m, l, c] = lrelu(b[c] + sum_k w[c, k] * x[m, l + k - 1]),  x = cutouts [M, P], zero padded.
@@ -89,7 +92,8 @@ __global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ y, c
 // an 8-way bank conflict and ran at 30 % of the write bandwidth.
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float slope, int P, int C,
-                                                         long long rows /* M*P */, float* plain, void* split, int parts) {
+                                                         long long rows /* M*P */, float* plain, void* split, int parts, int* status) {
+    float amax = 0.f;
     const unsigned c4n = (unsigned)C >> 2;
     const unsigned rpb = blockDim.x / c4n;             // rows per block and pass
     const int c = (int)(threadIdx.x % c4n) << 2;
@@ -107,8 +111,9 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[j] = lrelu(fmaf(w2[j], xr, fmaf(w1[j], xc, fmaf(w0[j], xl, bb[j]))), slope);
-        emit(make_float4(o[0], o[1], o[2], o[3]), (size_t)row, c, C, plain, split, parts);
+        emit(make_float4(o[0], o[1], o[2], o[3]), (size_t)row, c, C, plain, split, parts, amax);
     }
+    if (status && !(amax <= 65504.f)) atomicCAS(status, 0, 16);
 }
 
 // One warp per cutout: y [M, L, C] (raw output of the last convolution, channels last)
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ y, const float* __restrict__ bias, float slope,
                                                    int L, int C, const float* __restrict__ w_head,
                                                    const float* __restrict__ b_head, int H, int n_sig, long long M,
-                                                   float* __restrict__ out) {
+                                                   float* __restrict__ out, float* __restrict__ out_rest) {
     const int lane = threadIdx.x & 31;
     const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
@@ -146,7 +151,11 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ y, 
             if (h < H) {
                 float v = warp_sum(acc[h]) + __ldg(b_head + h);
                 if (h < n_sig) v = 1.f / (1.f + expf(-v));
-                if (lane == 0) out[(size_t)m * H + h] = v;
+                if (lane == 0) {
+                    if (!out_rest) out[(size_t)m * H + h] = v;
+                    else if (h < n_sig) out[(size_t)m * n_sig + h] = v;
+                    else out_rest[(size_t)m * (H - n_sig) + (h - n_sig)] = v;
+                }
             }
         }
     }
@@ -164,7 +173,7 @@ unsigned stream_grid(long long items, int threads) {
 extern "C" {
 
 int pof_act_fwd(const float* y, const float* bias, long long rows_in, int C, int pool, float slope, float* out_plain,
-                void* out_split, int split_parts, void* stream_) {
+                void* out_split, int split_parts, int* status, void* stream_) {
     using namespace pof;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (rows_in == 0) return POF_OK;
@@ -179,14 +188,14 @@ int pof_act_fwd(const float* y, const float* bias, long long rows_in, int C, int
     POF_REQUIRE((al & 15) == 0, POF_ERR_BAD_PARAM, "pof_act_fwd: tensors must be 16-byte aligned");
     const long long rows_out = rows_in / pool;
     const unsigned grid = stream_grid(rows_out * (C >> 2), 256);
-    if (pool == 1) act_kernel<1><<<grid, 256, 0, stream>>>(y, bias, slope, C, rows_out, out_plain, out_split, split_parts);
-    else act_kernel<2><<<grid, 256, 0, stream>>>(y, bias, slope, C, rows_out, out_plain, out_split, split_parts);
+    if (pool == 1) act_kernel<1><<<grid, 256, 0, stream>>>(y, bias, slope, C, rows_out, out_plain, out_split, split_parts, status);
+    else act_kernel<2><<<grid, 256, 0, stream>>>(y, bias, slope, C, rows_out, out_plain, out_split, split_parts, status);
     POF_CUDA(cudaGetLastError());
     return POF_OK;
 }
 
 int pof_conv_first_fwd(const float* cutouts, const float* weight, const float* bias, long long M, int P, int C, float slope,
-                       float* out_plain, void* out_split, int split_parts, void* stream_) {
+                       float* out_plain, void* out_split, int split_parts, int* status, void* stream_) {
     using namespace pof;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (M == 0) return POF_OK;
@@ -200,13 +209,13 @@ int pof_conv_first_fwd(const float* cutouts, const float* weight, const float* b
     const long long rows = M * P;
     POF_REQUIRE(256 % (C >> 2) == 0, POF_ERR_BAD_SHAPE, "pof_conv_first_fwd: C / 4 must divide 256 (got C = %d)", C);
     const unsigned grid = stream_grid(rows * (C >> 2), 256);
-    conv_first_kernel<<<grid, 256, 0, stream>>>(cutouts, weight, bias, slope, P, C, rows, out_plain, out_split, split_parts);
+    conv_first_kernel<<<grid, 256, 0, stream>>>(cutouts, weight, bias, slope, P, C, rows, out_plain, out_split, split_parts, status);
     POF_CUDA(cudaGetLastError());
     return POF_OK;
 }
 
 int pof_head_fwd(const float* y, const float* bias, long long M, int L, int C, float slope, const float* w_head,
-                 const float* b_head, int H, int n_sigmoid, float* out, void* stream_) {
+                 const float* b_head, int H, int n_sigmoid, float* out, float* out_rest, void* stream_) {
     using namespace pof;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (M == 0) return POF_OK;
@@ -217,7 +226,7 @@ int pof_head_fwd(const float* y, const float* bias, long long M, int L, int C, f
     const uintptr_t al = reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(w_head);
     POF_REQUIRE((al & 15) == 0, POF_ERR_BAD_PARAM, "pof_head_fwd: y, bias and w_head must be 16-byte aligned");
     const unsigned grid = stream_grid(M * 32, 256);
-    head_kernel<<<grid, 256, 0, stream>>>(y, bias, slope, L, C, w_head, b_head, H, n_sigmoid, M, out);
+    head_kernel<<<grid, 256, 0, stream>>>(y, bias, slope, L, C, w_head, b_head, H, n_sigmoid, M, out, out_rest);
     POF_CUDA(cudaGetLastError());
     return POF_OK;
 }

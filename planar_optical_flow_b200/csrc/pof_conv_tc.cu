@@ -20,19 +20,24 @@
 // against fp64 (profiles/r1_conv_tc_layers_v3.txt): 5-7e-7 per layer with 64-channel chains, 3e-7 with 32,
 // against 1-2e-6 for cuDNN's fp32 SIMT kernels on the same layers.
 //
-// Structure (one persistent CTA per SM, 384 threads, tiles of 128 rows x BN output channels):
-//   warp 0     TMA producer: per k-block (tap, 16 input channels) four tensor-map loads into a shared-memory
-//              ring — A_hi / A_lo as 3-D boxes (16 ch, Lout, mt cutouts) whose row coordinate is shifted by
-//              the tap, so the convolution's zero padding is the TMA's out-of-bounds fill; W_hi / W_lo as
-//              2-D boxes.  64-byte swizzle, completion on an mbarrier (complete_tx).  The k-block is small
-//              (48 KB at BN = 256) so that FOUR of them fit: the kernel is bound by the latency of these
-//              loads, not by their bandwidth (ncu: L2->SM at 31 %), and depth is what hides it.
-//   warp 1     MMA issuer: 6 x tcgen05.mma.kind::tf32 (M = 128, N = BN, K = 8) per k-block into one of two
-//              tensor-memory accumulators; tcgen05.commit releases the ring slot and signals the chain.
+// Structure (one persistent CTA per SM, 384 threads; an SM pair works on 256 rows x BN output channels with
+// cta_group::2, each CTA holding its own 128 rows and half of the weight tile):
+//   warp 0     TMA producer: per k-block (one tap, one 128-byte row of input channels: 64 binary16 / 32 TF32) four
+//              tensor-map loads into a shared-memory ring - A_hi / A_lo as 3-D boxes (channels, Lout rows, mt cutouts)
+//              whose row coordinate is shifted by the tap, so the convolution's zero padding is the TMA's
+//              out-of-bounds fill; W_hi / W_lo as 2-D boxes (or, for the narrow layers, resident for the whole
+//              launch).  128-byte swizzle, completion on an mbarrier (complete_tx).  The ring takes as many stages
+//              as fit in 205 KB (3 at BN = 256, up to 12 with resident weights).
+//   warp 1     MMA issuer (the pair's leader only): per k-block 3 products x (128 / 32) k-steps of tcgen05.mma
+//              (kind::f16, K = 16, or kind::tf32, K = 8) into one of two tensor-memory accumulators; tcgen05.commit
+//              releases the ring slot and, at the end of a chain, hands the accumulator to the epilogue warps.
 //   warp 2     tensor-memory allocation (512 columns) and release.
 //   warps 4-11 promotion + epilogue: tcgen05.ld the finished chain, add into registers, hand the TMEM
-//              buffer back; after the last chain: + bias, LeakyReLU, max-pool over row pairs (shuffle),
-//              optional hi/lo split for the next layer, 128-bit stores.
+//              buffer back; after the last chain: scale + bias, LeakyReLU, max-pool over row pairs (shuffle),
+//              optional hi/lo split for the next layer, transposition through shared memory, 128-bit stores.
+// What bounds it (profiles/r1_conv_tc_f16_ncu_256to512.txt): the wide layers run the tensor
+// pipe at ~60 % next to 104 of 128 B/clk of shared-memory traffic; the narrow layers stream their split
+// activations from and to HBM.
 // Every mbarrier wait is bounded: on a timeout the role records an error code and leaves, so a bug
 // surfaces as a status, never as a hung GPU.
 //
@@ -165,7 +170,7 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
         : "memory");
 }
 
-// Shared-memory matrix descriptor, K-major, 64-byte swizzle: rows of 64 B, 8-row groups 512 B apart.
+// Shared-memory matrix descriptor, K-major, swizzled rows of kRowBytes (128 B; 8-row groups 1024 B apart).
 __device__ __forceinline__ unsigned long long umma_desc(unsigned addr) {
     return (unsigned long long)((addr >> 4) & 0x3fffu) | (1ull << 16) /* LBO (unused with swizzle) */ |
            ((unsigned long long)(8 * kRowBytes >> 4) << 32) /* SBO */ | (1ull << 46) /* descriptor version (sm_100) */ |

@@ -26,7 +26,8 @@
 //            per-sample path; the clip is applied to the final float (all steps are monotone).
 //   POF_CUTOUT_FAST   index line in 32.32 fixed point (one 64-bit add per sample), blend and
 //            centring in float32: <= ~3e-6 of the output range from EXACT (parity bar 1e-5).
-//            Used by the streaming engine; `scans_to_cutout` uses EXACT.
+//            What the configs[1] cutout sweep measures and `StreamingDetector(cutout_fast=True)` selects;
+//            `scans_to_cutout` and the engine's default use EXACT.
 //
 // Area mode needs `s_area = ceil(max_span / P)` over a whole reference call (utils.py:308) =
 // over one sample b here: cutout_span_kernel (one CTA per b) reduces it into `ws` first.

@@ -34,6 +34,7 @@
 //     as one float4 per lane, dot products finished with warp shuffles) while the
 //     first ring stages are already in flight, and are broadcast from shared
 //     memory in the streaming loop.
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "pof_common.cuh"
@@ -76,6 +77,9 @@ struct GateArgs {
     int B, N, CL, E;
     int chunk_len, n_chunks;
     float alpha, beta;   // beta = (float)(1.0 - alpha)
+    void* out_split;     // forward only, optional: the new memory as binary16 [hi | lo] rows of split_c channels
+    int split_c;         //   (operand of pof_conv_tc_f16_fwd: row r = point * (CL / split_c) + l is [hi(split_c) | lo(split_c)])
+    int* status;         // optional device int: 32 = a ring wait timed out, 16 = a memory value left the binary16 range
 };
 
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -154,16 +158,32 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+__device__ __forceinline__ bool mbar_try(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+// Bounded like every wait of the convolution kernel: a copy that never lands (a bad pointer) becomes status 32 and
+// garbage in the output, never a hung GPU.  The fast path is one try_wait (which itself blocks for a hardware time slice).
+constexpr long long kGateWaitLimit = 2000000000LL;     // ~1 s of SM clocks
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity, int* status) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 64; ++i)
+            if (mbar_try(bar, parity)) return;
+        if (clock64() - t0 > kGateWaitLimit) {
+            if (status) atomicCAS(status, 0, 32);
+            return;
+        }
+    }
 }
 // 1-D bulk copy global -> shared (SASS: UBLKCP), bytes % 16 == 0, both addresses 16-byte aligned.
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
@@ -234,6 +254,14 @@ __global__ void __launch_bounds__(kGateThreads, kGateMinBlocks) gate_stream_kern
 #pragma unroll
     for (int k = 0; k < W; ++k) win[k] = f4_zero();
     const float alpha = a.alpha, beta = a.beta;
+    // optional second output (forward): the same row as the binary16 [hi | lo] operand of the convolutions that consume
+    // the new memory (the gate embedding and conv block 3), written in the pass that already holds it in registers
+    __half* s_col = nullptr;
+    float amax = 0.f;
+    if (MODE == 0 && a.out_split && active) {
+        const int l = ch / a.split_c, c = ch - l * a.split_c;
+        s_col = reinterpret_cast<__half*>(a.out_split) + (size_t)b * a.N * 2 * CL + (size_t)l * 2 * a.split_c + c;
+    }
 
     for (int s0 = 0; s0 < n_stages; s0 += W) {
 #pragma unroll
@@ -241,7 +269,7 @@ __global__ void __launch_bounds__(kGateThreads, kGateMinBlocks) gate_stream_kern
             const int s = s0 + u;
             if (s < n_stages) {
                 const int slot = s % R;
-                mbar_wait(&full[slot], (unsigned)(s / R) & 1u);
+                mbar_wait(&full[slot], (unsigned)(s / R) & 1u, a.status);
                 const float4 tv = stage[(size_t)slot * 2 * kGateThreads + tid];
                 float4 xv = f4_zero();
                 if (MODE == 0 && s >= W - 1) xv = stage[((size_t)slot * 2 + 1) * kGateThreads + tid];
@@ -267,6 +295,15 @@ __global__ void __launch_bounds__(kGateThreads, kGateMinBlocks) gate_stream_kern
                         o.z = fmaf(alpha, xv.z, beta * acc.z);
                         o.w = fmaf(alpha, xv.w, beta * acc.w);
                         if (active) st_stream_f4(reinterpret_cast<float4*>(o_col + (size_t)i * CL), o);
+                        if (s_col) {
+                            const __half2 h01 = __floats2half2_rn(o.x, o.y), h23 = __floats2half2_rn(o.z, o.w);
+                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                            const __half2 l01 = __floats2half2_rn(o.x - f01.x, o.y - f01.y), l23 = __floats2half2_rn(o.z - f23.x, o.w - f23.y);
+                            __half* dst = s_col + (size_t)i * 2 * CL;
+                            *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const unsigned*>(&h01), *reinterpret_cast<const unsigned*>(&h23));
+                            *reinterpret_cast<uint2*>(dst + a.split_c) = make_uint2(*reinterpret_cast<const unsigned*>(&l01), *reinterpret_cast<const unsigned*>(&l23));
+                            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+                        }
                     } else {
                         const float4 c = win[(u + 1 + HW) % W];          // g_out[j] itself
                         if (active) {
@@ -280,6 +317,7 @@ __global__ void __launch_bounds__(kGateThreads, kGateMinBlocks) gate_stream_kern
             }
         }
     }
+    if (MODE == 0 && s_col && !(amax <= 65504.f) && a.status) atomicCAS(a.status, 0, 16);   // beyond binary16 (or NaN)
 }
 
 template <int W>
@@ -428,7 +466,8 @@ int launch_gate_bwd_small(const GateArgs& a, const float* g_out, const float* g_
 extern "C" {
 
 int pof_spaam_gate_fwd(const float* x, const float* tmpl, const float* emb_x, const float* emb_t, int B, int N, int CL,
-                       int E, int W, float alpha, float* out_tmpl, float* feat_fused, float* attn_w, void* stream_) {
+                       int E, int W, float alpha, float* out_tmpl, float* feat_fused, float* attn_w, void* out_split,
+                       int split_channels, int* status, void* stream_) {
     using namespace pof;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (B == 0) return POF_OK;
@@ -446,11 +485,16 @@ int pof_spaam_gate_fwd(const float* x, const float* tmpl, const float* emb_x, co
                          reinterpret_cast<uintptr_t>(out_tmpl);
     POF_REQUIRE((al & 15) == 0, POF_ERR_BAD_PARAM, "pof_spaam_gate_fwd: tensors must be 16-byte aligned");
     POF_REQUIRE(B <= 65535, POF_ERR_BAD_SHAPE, "pof_spaam_gate_fwd: B must be <= 65535");
-    if (B == 0) return POF_OK;
+    if (out_split) {
+        POF_REQUIRE(split_channels >= 4 && split_channels % 4 == 0 && CL % split_channels == 0, POF_ERR_BAD_SHAPE,
+                    "pof_spaam_gate_fwd: split_channels must be a multiple of 4 that divides CL (got %d for CL = %d)", split_channels, CL);
+        POF_REQUIRE((reinterpret_cast<uintptr_t>(out_split) & 15) == 0, POF_ERR_BAD_PARAM, "pof_spaam_gate_fwd: out_split must be 16-byte aligned");
+    }
 
     GateArgs a;
     a.x = x; a.tmpl = tmpl; a.emb_x = emb_x; a.emb_t = emb_t;
     a.out = out_tmpl; a.feat_fused = feat_fused; a.attn_w = attn_w;
+    a.out_split = out_split; a.split_c = out_split ? split_channels : 0; a.status = status;
     a.B = B; a.N = N; a.CL = CL; a.E = E;
     a.alpha = alpha;
     a.beta = (float)(1.0 - (double)alpha);
@@ -490,6 +534,7 @@ int pof_spaam_gate_bwd(const float* tmpl, const float* emb_x, const float* emb_t
     a.alpha = alpha;
     a.beta = (float)(1.0 - (double)alpha);
     a.chunk_len = 0; a.n_chunks = 0;
+    a.out_split = nullptr; a.split_c = 0; a.status = nullptr;
     float* g_s = reinterpret_cast<float*>(ws);
 
     int rc = POF_ERR_UNSUPPORTED;

@@ -5,9 +5,11 @@ sequence, one scan at a time, and crosses the host boundary twice per scan: CPU 
 H2D -> network -> D2H -> CPU NMS.  `StreamingDetector` runs B independent sequences in
 lock-step with nothing but the raw ranges going up and the detections coming down:
 
-    ranges [B, N] --H2D--> cutout kernel -> conv blocks 1-2 (cuDNN) -> embeddings (cuDNN)
+    ranges [B, N] --H2D--> cutout kernel -> conv blocks 1-2 -> embeddings
         -> fused attention-memory kernel (memory [B, N, 256, 14] stays resident, ping-pong)
-        -> conv blocks 3-4 + heads (cuDNN) -> sigmoid -> NMS kernels --D2H--> detections
+        -> conv blocks 3-4 + heads -> sigmoid -> NMS kernels --D2H--> detections
+
+(the convolutions run on libpof's tcgen05 kernel in the default precision, on cuDNN in the library modes below)
 
 Sequences never interact, so multi-GPU use is one detector per rank over a
 disjoint set of sequences with no data-path collective.
@@ -86,6 +88,7 @@ class _ChannelsLastBackbone:
         self.f16 = bool(f16) and self.tc    # ... with float16 hi / lo parts (kind::f16) instead of TF32 parts
         self.parts = ops.SPLIT_F16 if self.f16 else (2 if tc else 3)
         self.timer = None                   # optional: callable(name, flops) -> context manager around each tcgen05 launch
+        self.status = None                  # the owner's device status word (ops.new_status), passed to every libpof launch
         blocks = [model.conv_block_1, model.conv_block_2, model.conv_block_3, model.conv_block_4]
         folded = [[fold_conv_bn(layer) for layer in blk] for blk in blocks]
         w0, b0 = folded[0][0]
@@ -139,51 +142,68 @@ class _ChannelsLastBackbone:
         """ops.conv_tc, optionally bracketed by the owner's event timer (algorithmic FLOPs: 2 * rows * Cin * Cout * taps)."""
         w, out_scale = w
         if self.timer is None:
-            return ops.conv_tc(a, w, b, M, LA, Lout, taps, pad, out_scale=out_scale, **kw)
+            return ops.conv_tc(a, w, b, M, LA, Lout, taps, pad, out_scale=out_scale, status=self.status, **kw)
         cin, cout = a.shape[1] // 2, w.shape[2]
         with self.timer("conv%d" % min(cout, 256), 2.0 * M * Lout * cin * cout * taps):
-            return ops.conv_tc(a, w, b, M, LA, Lout, taps, pad, out_scale=out_scale, **kw)
+            return ops.conv_tc(a, w, b, M, LA, Lout, taps, pad, out_scale=out_scale, status=self.status, **kw)
 
-    def _layer(self, a, M, L, w, b, cout, pool, plain=False):
+    def _layer(self, a, M, L, w, b, cout, pool, plain=False, plain_out=None):
         """One conv + bias + LeakyReLU (+ max-pool) layer -> (plain or None, operand for the next convolution)."""
         if self.tc:
-            return self._conv_tc(a, w, b, M, L, L, 3, 1, pool=pool, slope=_SLOPE, want_plain=plain, want_split=True)
+            return self._conv_tc(a, w, b, M, L, L, 3, 1, pool=pool, slope=_SLOPE, want_plain=plain, want_split=True,
+                                 plain_out=plain_out if plain else None)
         y = self._conv(a, M, L, w, cout)
-        p, s = ops.act(y, b, pool=pool, slope=_SLOPE, want_plain=plain or not self.split, want_split=self.split)
+        p, s = ops.act(y, b, pool=pool, slope=_SLOPE, want_plain=plain or not self.split, want_split=self.split,
+                       status=self.status)
+        if plain and plain_out is not None:
+            plain_out.view(p.shape).copy_(p)
+            p = plain_out
         return p, (s if self.split else p)
+
+    @property
+    def gate_emits_operand(self):
+        """float16 parts: the attention kernel writes the new memory's operand split itself (no extra pass)."""
+        return self.f16
 
     def operand(self, plain_rows):
         """The convolution operand of already-activated rows (the attention memory)."""
         if not self.split:
             return plain_rows
-        return ops.act(plain_rows, None, pool=1, slope=1.0, want_plain=False, want_split=True, parts=self.parts)[1]
+        return ops.act(plain_rows, None, pool=1, slope=1.0, want_plain=False, want_split=True, parts=self.parts,
+                       status=self.status)[1]
 
-    def features(self, cutouts):
-        """cutouts [M, P] -> (features [M * P/4, 256] plain, the same rows as a convolution operand)."""
+    def features(self, cutouts, plain_out=None):
+        """cutouts [M, P] -> (features [M * P/4, 256] plain, the same rows as a convolution operand).
+        `plain_out`: write the plain features there (the first frame's memory) instead of a fresh tensor."""
         M, L = cutouts.shape
         p, s = ops.conv_first(cutouts, self.w_first, self.b_first, slope=_SLOPE, want_plain=not self.split,
-                              want_split=self.split, parts=self.parts)
+                              want_split=self.split, parts=self.parts, status=self.status)
         a = s if self.split else p
         plain = None
         for bi in (0, 1):
             todo = self.layers[bi][1:] if bi == 0 else self.layers[bi]
             for k, (w4, b, cout) in enumerate(todo):
                 last = k == len(todo) - 1
-                plain, a = self._layer(a, M, L, w4, b, cout, 2 if last else 1, plain=last and bi == 1)
+                plain, a = self._layer(a, M, L, w4, b, cout, 2 if last else 1, plain=last and bi == 1,
+                                       plain_out=plain_out)
                 if last:
                     L //= 2
         return plain, a
 
-    def embed(self, operand, M):
-        """Gate embedding (Conv1d k = L, no padding == one GEMM over whole rows) + BN + LeakyReLU."""
+    def embed(self, operand, M, out=None):
+        """Gate embedding (Conv1d k = L, no padding == one GEMM over whole rows) + BN + LeakyReLU -> [M, E]."""
         if self.tc:
             L = self.emb_w[0].shape[0]
             return self._conv_tc(operand, self.emb_w, self.emb_b, M, L, 1, L, 0, pool=1, slope=_SLOPE, want_plain=True,
-                                 want_split=False)[0]
-        return F.leaky_relu_(torch.addmm(self.emb_b, operand.view(M, -1), self.emb_w), _SLOPE)
+                                 want_split=False, plain_out=out)[0]
+        e = F.leaky_relu_(torch.addmm(self.emb_b, operand.view(M, -1), self.emb_w), _SLOPE)
+        if out is not None:
+            out.view(e.shape).copy_(e)
+            return out
+        return e
 
-    def votes(self, operand, M, L):
-        """memory rows (as operand) [M * L, Ceff] -> [M, n_cls + 2]: (sigmoid(cls) | reg)."""
+    def votes(self, operand, M, L, out_cls, out_reg):
+        """memory rows (as operand) [M * L, Ceff] -> sigmoid(cls) into out_cls [M, n_cls], reg into out_reg [M, 2]."""
         a = operand
         for bi in (2, 3):
             for k, (w4, b, cout) in enumerate(self.layers[bi]):
@@ -191,9 +211,11 @@ class _ChannelsLastBackbone:
                 if bi == 3 and last:
                     if self.tc:         # bias + LeakyReLU already applied by the convolution's epilogue
                         y = self._conv_tc(a, w4, b, M, L, L, 3, 1, pool=1, slope=_SLOPE, want_plain=True, want_split=False)[0]
-                        return ops.head(y, None, M, L, self.w_head, self.b_head, n_sigmoid=self.n_cls, slope=1.0)
+                        return ops.head(y, None, M, L, self.w_head, self.b_head, n_sigmoid=self.n_cls, slope=1.0,
+                                        out=out_cls, out_rest=out_reg)
                     y = self._conv(a, M, L, w4, cout)
-                    return ops.head(y, b, M, L, self.w_head, self.b_head, n_sigmoid=self.n_cls, slope=_SLOPE)
+                    return ops.head(y, b, M, L, self.w_head, self.b_head, n_sigmoid=self.n_cls, slope=_SLOPE,
+                                    out=out_cls, out_rest=out_reg)
                 _, a = self._layer(a, M, L, w4, b, cout, 2 if last else 1)
                 if last:
                     L //= 2
@@ -234,8 +256,11 @@ class StreamingDetector:
         self.channels_last = precision != "fp32-simt"
         with torch.no_grad():
             if self.channels_last:
-                if self.P % 4:
-                    raise ValueError("the channels-last pipeline needs num_cutout_pts to be a multiple of 4")
+                # two max-pools, then a third inside block 3: every pooled length must be even (the reference's
+                # max_pool1d floors instead; precision="fp32-simt" keeps that behaviour for other sizes)
+                if self.P % 8:
+                    raise ValueError("precision=%r needs num_cutout_pts to be a multiple of 8 (got %d); "
+                                     "precision='fp32-simt' takes any size" % (precision, self.P))
                 self.net = _ChannelsLastBackbone(model, split=precision != "tf32", tc=precision in ("fp32", "fp32-tf32"),
                                                  f16=precision == "fp32")
             self.block1 = _FoldedStack(model.conv_block_1, 1)
@@ -278,6 +303,11 @@ class StreamingDetector:
         }
         self.h2d_bytes_per_step = self.h_scans.numel() * 4
         self.d2h_bytes_per_step = sum(t.numel() * t.element_size() for t in self.h_out.values())
+        # one status word per detector: float16-range overflow of the operand split, or a bounded device wait that timed out
+        self.status = ops.new_status(self.device)
+        self.h_status = torch.zeros(1, dtype=torch.int32).pin_memory()
+        if self.channels_last:
+            self.net.status = self.status
         self.record_events = record_events
         self.events = {"cutout": [], "gate": [], "nms": []}
         self.event_work = {}               # stage -> algorithmic FLOPs of each recorded launch (tcgen05 convolutions)
@@ -322,30 +352,34 @@ class StreamingDetector:
     def _chunk_channels_last(self, cutouts, b0, b1, first, prev, nxt, pred_cls, pred_reg, feat_fused):
         N = self.N
         nb, M, L = b1 - b0, (b1 - b0) * N, self.P // 4
-        feat, x_op = self.net.features(cutouts[b0:b1].view(M, self.P))
-        feat = feat.view(nb, N, L, -1)
-        emb_x = self.net.embed(x_op, M).view(nb, N, -1)
+        # every stage writes straight into the step's own tensors (slices along the sequence axis are contiguous)
         if first:                # memory := features; similarities against itself (dr_spaam.py:242-244)
-            nxt[b0:b1].copy_(feat)
+            feat, x_op = self.net.features(cutouts[b0:b1].view(M, self.P), plain_out=nxt[b0:b1])
+            emb_x = self.net.embed(x_op, M, out=self.emb_memory[b0:b1]).view(nb, N, -1)
             with self._timed("gate"):
-                _, ff, _ = ops.gate_forward(feat, nxt[b0:b1], emb_x, emb_x, self.alpha, self.window, out=prev[b0:b1])
-            self.emb_memory[b0:b1] = emb_x
+                ops.gate_forward(nxt[b0:b1], nxt[b0:b1], emb_x, emb_x, self.alpha, self.window, out=prev[b0:b1],
+                                 feat_out=feat_fused[b0:b1], status=self.status)      # blended output is discarded
             t_op = x_op
         else:
+            feat, x_op = self.net.features(cutouts[b0:b1].view(M, self.P))
+            feat = feat.view(nb, N, L, -1)
+            emb_x = self.net.embed(x_op, M).view(nb, N, -1)
+            fused = self.net.gate_emits_operand
+            t_op = torch.empty((M * L, 2 * feat.shape[-1]), dtype=torch.float16, device=self.device) if fused else None
             with self._timed("gate"):
-                _, ff, _ = ops.gate_forward(feat, prev[b0:b1], emb_x, self.emb_memory[b0:b1], self.alpha,
-                                            self.window, out=nxt[b0:b1])
-            t_op = self.net.operand(nxt[b0:b1].view(M * L, -1))
+                ops.gate_forward(feat, prev[b0:b1], emb_x, self.emb_memory[b0:b1], self.alpha, self.window, out=nxt[b0:b1],
+                                 feat_out=feat_fused[b0:b1], split_out=t_op, split_channels=feat.shape[-1],
+                                 status=self.status)
+            if not fused:
+                t_op = self.net.operand(nxt[b0:b1].view(M * L, -1))
+                self.kernel_launches += 1 if self.net.split else 0
             # the embedding of the NEW memory is what the next step's gate needs (dr_spaam.py:180-181)
-            self.emb_memory[b0:b1] = self.net.embed(t_op, M).view(nb, N, -1)
-            self.kernel_launches += (1 if self.net.split else 0) + (1 if self.net.tc else 0)
-        feat_fused[b0:b1] = ff
-        v = self.net.votes(t_op, M, L).view(nb, N, -1)
+            self.net.embed(t_op, M, out=self.emb_memory[b0:b1])
+            self.kernel_launches += 1 if self.net.tc else 0
+        self.net.votes(t_op, M, L, pred_cls[b0:b1], pred_reg[b0:b1])
         # cuDNN modes: first layer + 9 activation passes + head + gate; tcgen05 mode: first layer + 10 convolutions
         # + embedding + head + gate
         self.kernel_launches += 14 if self.net.tc else 12
-        pred_cls[b0:b1] = v[:, :, 0]
-        pred_reg[b0:b1] = v[:, :, 1:]
 
     def _chunk_ncl(self, cutouts, b0, b1, first, prev, nxt, pred_cls, pred_reg, feat_fused):
         N = self.N
@@ -409,14 +443,18 @@ class StreamingDetector:
         self._last = res
         return res
 
-    def check(self):
-        """Synchronise and raise if a tcgen05 pipeline wait timed out on the device (results would be invalid)."""
-        code = ops.conv_tc_status(self.device)
+    def _raise_status(self, code):
         if code == 16:
             raise RuntimeError("an activation left the float16 range of precision='fp32' (|x| > 65504) on %s: "
                                "use precision='fp32-tf32' for this checkpoint" % self.device)
         if code:
-            raise RuntimeError("pof_conv_tc_fwd reported pipeline status %d on %s" % (code, self.device))
+            raise RuntimeError("a libpof kernel reported device status %d on %s (a bounded pipeline wait timed out; "
+                               "the results of that step are invalid)" % (code, self.device))
+
+    def check(self):
+        """Synchronise and raise if a step since the last check left the float16 range or timed out on the device.
+        The status word belongs to this detector and is cleared by the read, so a new step starts clean."""
+        self._raise_status(ops.read_status(self.status))
 
     @property
     def template(self):
@@ -433,7 +471,11 @@ class StreamingDetector:
         res = self.step_device(self.d_scans)
         for k, h in self.h_out.items():
             h.copy_(res[k], non_blocking=True)
+        self.h_status.copy_(self.status, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+        if int(self.h_status[0]):            # never hand back detections computed from an invalid step
+            self.status.zero_()
+            self._raise_status(int(self.h_status[0]))
         return {k: v.numpy() for k, v in self.h_out.items()}
 
     def detections(self, host_result, b):

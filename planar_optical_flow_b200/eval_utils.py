@@ -16,7 +16,11 @@ from . import ops
 
 def batch_cutouts(batch, cutout_kwargs, device, fast=False):
     """Raw ranges [B, S, N] (NumPy) -> device cutouts [B, N, S, P] (dataset_dr_spaam.py:445 on the GPU)."""
-    scans = torch.from_numpy(np.ascontiguousarray(batch["scans"], dtype=np.float32)).to(device, non_blocking=True)
+    scans = batch["scans"]
+    if isinstance(scans, torch.Tensor):                 # pinned staging tensor of the loader: asynchronous copy
+        scans = scans.to(device, dtype=torch.float32, non_blocking=True).contiguous()
+    else:
+        scans = torch.from_numpy(np.ascontiguousarray(scans, dtype=np.float32)).to(device, non_blocking=True)
     if "area_mode" not in cutout_kwargs:          # legacy configs (dataset_dr_spaam.py:440-443): integer window + cv2.resize
         phi_h = np.asarray(batch["scan_phi"])
         incre = phi_h[1] - phi_h[0]
@@ -25,37 +29,60 @@ def batch_cutouts(batch, cutout_kwargs, device, fast=False):
     return ops.cutout(scans, phi, fast=fast, **cutout_kwargs)
 
 
-def make_model_fn_obj_det(cutout_kwargs):
-    def model_fn_obj_det(model, batch, rtn_result=False):
-        device = next(model.parameters()).device
-        net_input = batch_cutouts(batch, cutout_kwargs, device)
-        model_rtn = model(net_input)
-        pred_cls, pred_reg = model_rtn[0], model_rtn[1]
-        target_cls = torch.from_numpy(batch["target_cls"]).to(device, non_blocking=True).long()
-        target_reg = torch.from_numpy(batch["target_reg"]).to(device, non_blocking=True).float()
-        n_batch, n_pts = target_cls.shape[:2]
-        target_cls = target_cls.view(n_batch * n_pts)
-        pred_cls = pred_cls.view(n_batch * n_pts, -1)
-        core = model.module if hasattr(model, "module") else model
-        if pred_cls.shape[1] == 1:                                   # eval_utils.py:55-58
-            cls_loss = core.cls_loss(torch.sigmoid(pred_cls.squeeze(-1)), target_cls.float(), reduction="mean")
-        else:
-            cls_loss = core.cls_loss(pred_cls, target_cls, reduction="mean")
-        total, tb = cls_loss, {"cls_loss": cls_loss.item()}
-        fg = target_cls.ne(0)
-        tb["fg_ratio"] = float(fg.sum().item()) / (n_batch * n_pts)
-        if tb["fg_ratio"] > 0.0:                                     # eval_utils.py:69-76
-            reg = F.mse_loss(pred_reg.view(n_batch * n_pts, -1)[fg], target_reg.view(n_batch * n_pts, -1)[fg],
-                             reduction="none")
-            reg_loss = torch.sqrt(torch.sum(reg, dim=1)).mean()
-            total = total + reg_loss
-            tb["reg_loss"] = reg_loss.item()
-        rtn = {}
-        if rtn_result:
-            rtn = {"pred_reg": pred_reg.view(n_batch, n_pts, -1), "pred_cls": pred_cls.view(n_batch, n_pts, -1)}
-        return total, tb, rtn
+def _to_device(a, device):
+    """NumPy array or (possibly pinned) CPU tensor -> device tensor, asynchronously when the source is pinned."""
+    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+    return t.to(device, non_blocking=True)
 
-    return model_fn_obj_det
+
+def model_fn_obj_det(model, batch, rtn_result=False, cutout_kwargs=None):
+    """The reference's `model_fn_obj_det(model, batch, rtn_result=False)` (eval_utils.py:31-88).
+
+    A batch in the reference's own format (`input` = cutouts made by the dataset, `target_flow_cls/_reg`) is taken as
+    it is; a batch of this package's loaders carries raw `scans` and the cutouts are made on the device with
+    `cutout_kwargs` (or the batch's own `cutout_kwargs` entry)."""
+    device = next(model.parameters()).device
+    if "input" in batch:
+        net_input = _to_device(batch["input"], device).float()
+    else:
+        kw = cutout_kwargs if cutout_kwargs is not None else batch.get("cutout_kwargs")
+        if kw is None:
+            raise KeyError("the batch has neither `input` (cutouts) nor `cutout_kwargs` to make them from `scans`")
+        net_input = batch_cutouts(batch, kw, device)
+    model_rtn = model(net_input)
+    pred_cls, pred_reg = model_rtn[0], model_rtn[1]
+    cls_key, reg_key = ("target_flow_cls", "target_flow_reg") if "target_flow_cls" in batch else ("target_cls", "target_reg")
+    target_cls = _to_device(batch[cls_key], device).long()
+    target_reg = _to_device(batch[reg_key], device).float()
+    n_batch, n_pts = target_cls.shape[:2]
+    target_cls = target_cls.view(n_batch * n_pts)
+    pred_cls = pred_cls.view(n_batch * n_pts, -1)
+    core = model.module if hasattr(model, "module") else model
+    if pred_cls.shape[1] == 1:                                   # eval_utils.py:55-58
+        cls_loss = core.cls_loss(torch.sigmoid(pred_cls.squeeze(-1)), target_cls.float(), reduction="mean")
+    else:
+        cls_loss = core.cls_loss(pred_cls, target_cls, reduction="mean")
+    total, tb = cls_loss, {"cls_loss": cls_loss.item()}
+    fg = target_cls.ne(0)
+    tb["fg_ratio"] = float(fg.sum().item()) / (n_batch * n_pts)
+    if tb["fg_ratio"] > 0.0:                                     # eval_utils.py:69-76
+        reg = F.mse_loss(pred_reg.view(n_batch * n_pts, -1)[fg], target_reg.view(n_batch * n_pts, -1)[fg],
+                         reduction="none")
+        reg_loss = torch.sqrt(torch.sum(reg, dim=1)).mean()
+        total = total + reg_loss
+        tb["reg_loss"] = reg_loss.item()
+    rtn = {}
+    if rtn_result:
+        rtn = {"pred_reg": pred_reg.view(n_batch, n_pts, -1), "pred_cls": pred_cls.view(n_batch, n_pts, -1)}
+    return total, tb, rtn
+
+
+def make_model_fn_obj_det(cutout_kwargs):
+    """`model_fn_obj_det` bound to the config's `cutout_kwargs` (what the Trainer calls as model_fn(model, batch))."""
+    def bound(model, batch, rtn_result=False):
+        return model_fn_obj_det(model, batch, rtn_result=rtn_result, cutout_kwargs=cutout_kwargs)
+
+    return bound
 
 
 # ------------------------------------------------------------------ scan-pair flow prototype (row N3)

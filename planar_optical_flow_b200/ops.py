@@ -97,11 +97,14 @@ def polar_grid(scans, min_range=0.0, max_range=30.0, range_bin_size=1.0, tsdf_cl
 
 
 # --------------------------------------------------------------------------- gate
-def gate_forward(x, tmpl, emb_x, emb_t, alpha, window, want_weights=False, out=None):
+def gate_forward(x, tmpl, emb_x, emb_t, alpha, window, want_weights=False, out=None, feat_out=None, split_out=None,
+                 split_channels=0, status=None):
     """Windowed attention memory update (reference: dr_spaam.py:183-215).
 
     x, tmpl [B, N, C, L] (or [B, N, CL]) float32; emb_* [B, N, E] float32; window = 2*hw+1.
     Returns (out_tmpl like x, feat_fused [B, N, W], attn_w [B, N, W] or None).
+    `split_out` (float16 [B * N * CL / split_channels, 2 * split_channels]) additionally receives the new memory as the
+    [hi | lo] operand rows of `conv_tc`; `status` is the caller's device status word (see `new_status`).
     """
     for name, t in (("x", x), ("tmpl", tmpl), ("emb_x", emb_x), ("emb_t", emb_t)):
         require_cuda_tensor(t, name, torch.float32)
@@ -116,10 +119,20 @@ def gate_forward(x, tmpl, emb_x, emb_t, alpha, window, want_weights=False, out=N
     with torch.cuda.device(dev):
         if out is None:
             out = torch.empty_like(x)
-        feat = torch.empty((B, N, window), dtype=torch.float32, device=dev)
+        if feat_out is None:
+            feat = torch.empty((B, N, window), dtype=torch.float32, device=dev)
+        else:
+            feat = require_cuda_tensor(feat_out, "feat_out", torch.float32)
+            if tuple(feat.shape) != (B, N, window):
+                raise ValueError("feat_out must be [B, N, W] = %s" % ((B, N, window),))
         attn = torch.empty((B, N, window), dtype=torch.float32, device=dev) if want_weights else None
+        if split_out is not None:
+            require_cuda_tensor(split_out, "split_out", torch.float16)
+            if split_out.numel() != 2 * B * N * CL:
+                raise ValueError("split_out must hold 2 * B * N * CL = %d halves (got %d)" % (2 * B * N * CL, split_out.numel()))
         check(_lib.lib().pof_spaam_gate_fwd(_ptr(x), _ptr(tmpl), _ptr(emb_x), _ptr(emb_t), B, N, CL, E, int(window),
-                                            float(alpha), _ptr(out), _ptr(feat), _ptr(attn), current_stream_ptr(dev)),
+                                            float(alpha), _ptr(out), _ptr(feat), _ptr(attn), _ptr(split_out),
+                                            int(split_channels), _ptr(status), current_stream_ptr(dev)),
               "pof_spaam_gate_fwd")
     return out, feat, attn
 
@@ -182,7 +195,22 @@ def _split_buffer(rows, C, parts, dev):
     return torch.empty((rows, parts * C), dtype=torch.float32, device=dev)
 
 
-def act(y, bias=None, pool=1, slope=0.1, want_plain=True, want_split=False, parts=3):
+def new_status(device):
+    """A zeroed device status word for `conv_tc` / `act` / `conv_first` / `gate_forward` (see `read_status`)."""
+    return torch.zeros(1, dtype=torch.int32, device=device)
+
+
+def read_status(status):
+    """Synchronise, return the status word and clear it: 0 = fine, 16 = an activation left the float16 range of the
+    float16 operand split (|x| > 65504 or NaN), 32 = a staged copy of the attention kernel never landed, anything
+    else = a pipeline wait of the tcgen05 convolution timed out (results invalid)."""
+    code = int(status.item())
+    if code:
+        status.zero_()
+    return code
+
+
+def act(y, bias=None, pool=1, slope=0.1, want_plain=True, want_split=False, parts=3, status=None):
     """Channels-last activations y [rows, C] -> (+bias) LeakyReLU, max over `pool` consecutive rows.
 
     Returns (plain [rows/pool, C] or None, split [rows/pool, parts*C] or None); parts = 3: [hi | lo | hi]
@@ -195,11 +223,11 @@ def act(y, bias=None, pool=1, slope=0.1, want_plain=True, want_split=False, part
         plain = torch.empty((rows // pool, C), dtype=torch.float32, device=dev) if want_plain else None
         split = _split_buffer(rows // pool, C, parts, dev) if want_split else None
         check(_lib.lib().pof_act_fwd(_ptr(y), _ptr(bias), rows, C, int(pool), float(slope), _ptr(plain), _ptr(split),
-                                     int(parts), current_stream_ptr(dev)), "pof_act_fwd")
+                                     int(parts), _ptr(status), current_stream_ptr(dev)), "pof_act_fwd")
     return plain, split
 
 
-def conv_first(cutouts, weight, bias, slope=0.1, want_plain=False, want_split=True, parts=3):
+def conv_first(cutouts, weight, bias, slope=0.1, want_plain=False, want_split=True, parts=3, status=None):
     """cutouts [M, P], weight [C, 3], bias [C] -> first conv layer + LeakyReLU, channels-last [M*P, C] / [M*P, 3C]."""
     require_cuda_tensor(cutouts, "cutouts", torch.float32)
     require_cuda_tensor(weight, "weight", torch.float32)
@@ -211,7 +239,7 @@ def conv_first(cutouts, weight, bias, slope=0.1, want_plain=False, want_split=Tr
         plain = torch.empty((M * P, C), dtype=torch.float32, device=dev) if want_plain else None
         split = _split_buffer(M * P, C, parts, dev) if want_split else None
         check(_lib.lib().pof_conv_first_fwd(_ptr(cutouts), _ptr(weight), _ptr(bias), M, P, C, float(slope), _ptr(plain),
-                                            _ptr(split), int(parts), current_stream_ptr(dev)), "pof_conv_first_fwd")
+                                            _ptr(split), int(parts), _ptr(status), current_stream_ptr(dev)), "pof_conv_first_fwd")
     return plain, split
 
 
@@ -219,16 +247,17 @@ _conv_tc_status = {}
 
 
 def conv_tc_status(device):
-    """The device-side status word of `conv_tc` launches on `device` (0 = every pipeline wait completed)."""
+    """The status word shared by `conv_tc` calls on `device` that did not bring their own (0 = every pipeline wait
+    completed); reading clears it, so one failed launch is reported once."""
     dev = torch.device(device)
     if dev.type == "cuda" and dev.index is None:          # "cuda" means the current device, as everywhere in torch
         dev = torch.device("cuda", torch.cuda.current_device())
     t = _conv_tc_status.get(dev)
-    return 0 if t is None else int(t.item())
+    return 0 if t is None else read_status(t)
 
 
 def conv_tc(a_split, w_split, bias, Mcut, LA, Lout, taps, pad, pool=1, slope=0.1, want_plain=False, want_split=True, chain_channels=0,
-            out_scale=1.0):
+            out_scale=1.0, status=None, plain_out=None):
     """fp32-accurate convolution / whole-row GEMM on tcgen05 (csrc/pof_conv_tc.cu).
 
     a_split [Mcut*LA, 2*Cin] = [hi | lo] rows, w_split [taps, 2, Cout, Cin]  ->
@@ -251,11 +280,17 @@ def conv_tc(a_split, w_split, bias, Mcut, LA, Lout, taps, pad, pool=1, slope=0.1
     if not chain_channels:
         chain_channels = int(os.environ.get("POF_CONV_TC_CHAIN", "0"), 0)      # tuning aid; 0 = the library default
     with torch.cuda.device(dev):
-        status = _conv_tc_status.get(dev)
         if status is None:
-            status = _conv_tc_status[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+            status = _conv_tc_status.get(dev)
+            if status is None:
+                status = _conv_tc_status[dev] = new_status(dev)
         rows = Mcut * Lout // pool
-        plain = torch.empty((rows, Cout), dtype=torch.float32, device=dev) if want_plain else None
+        if plain_out is not None:                     # write the fp32 rows straight into the caller's buffer (a view is fine)
+            plain = require_cuda_tensor(plain_out, "plain_out", torch.float32)
+            if plain.numel() != rows * Cout:
+                raise ValueError("plain_out must hold %d x %d values (got %d)" % (rows, Cout, plain.numel()))
+        else:
+            plain = torch.empty((rows, Cout), dtype=torch.float32, device=dev) if want_plain else None
         split = torch.empty((rows, 2 * Cout), dtype=dt, device=dev) if want_split else None
         if f16:
             check(_lib.lib().pof_conv_tc_f16_fwd(_ptr(a_split), _ptr(w_split), _ptr(bias), Mcut, int(LA), int(Lout), Cin, Cout,
@@ -269,8 +304,11 @@ def conv_tc(a_split, w_split, bias, Mcut, LA, Lout, taps, pad, pool=1, slope=0.1
     return plain, split
 
 
-def head(y, bias, M, L, w_head, b_head, n_sigmoid, slope=0.1):
-    """y [M*L, C] raw last-conv output -> +bias, LeakyReLU, mean over L, heads [H, C] (+ sigmoid on the first n_sigmoid) -> [M, H]."""
+def head(y, bias, M, L, w_head, b_head, n_sigmoid, slope=0.1, out=None, out_rest=None):
+    """y [M*L, C] raw last-conv output -> +bias, LeakyReLU, mean over L, heads [H, C] (+ sigmoid on the first n_sigmoid) -> [M, H].
+
+    With `out` [M, n_sigmoid] and `out_rest` [M, H - n_sigmoid] the two groups of heads (classes | regression) go to
+    the caller's own tensors instead of one [M, H] matrix."""
     require_cuda_tensor(y, "y", torch.float32)
     require_cuda_tensor(w_head, "w_head", torch.float32)
     require_cuda_tensor(b_head, "b_head", torch.float32)
@@ -278,10 +316,16 @@ def head(y, bias, M, L, w_head, b_head, n_sigmoid, slope=0.1):
     H = w_head.shape[0]
     dev = y.device
     with torch.cuda.device(dev):
-        out = torch.empty((M, H), dtype=torch.float32, device=dev)
+        if out_rest is not None:
+            require_cuda_tensor(out, "out", torch.float32)
+            require_cuda_tensor(out_rest, "out_rest", torch.float32)
+            if out.numel() != M * n_sigmoid or out_rest.numel() != M * (H - n_sigmoid):
+                raise ValueError("out / out_rest must hold M x n_sigmoid and M x (H - n_sigmoid) values")
+        else:
+            out = torch.empty((M, H), dtype=torch.float32, device=dev)
         check(_lib.lib().pof_head_fwd(_ptr(y), _ptr(bias), M, int(L), C, float(slope), _ptr(w_head), _ptr(b_head), H,
-                                      int(n_sigmoid), _ptr(out), current_stream_ptr(dev)), "pof_head_fwd")
-    return out
+                                      int(n_sigmoid), _ptr(out), _ptr(out_rest), current_stream_ptr(dev)), "pof_head_fwd")
+    return out if out_rest is None else (out, out_rest)
 
 
 # --------------------------------------------------------------------------- patch correlation (prototype)

@@ -34,7 +34,7 @@ def _emit(v, want_plain, want_split, parts=3):
     return (v if want_plain else None), split
 
 
-def fake_act(y, bias=None, pool=1, slope=0.1, want_plain=True, want_split=False, parts=3):
+def fake_act(y, bias=None, pool=1, slope=0.1, want_plain=True, want_split=False, parts=3, status=None):
     rows, C = y.shape
     v = y.view(rows // pool, pool, C).max(dim=1).values
     if bias is not None:
@@ -43,7 +43,7 @@ def fake_act(y, bias=None, pool=1, slope=0.1, want_plain=True, want_split=False,
     return _emit(v, want_plain, want_split, parts)
 
 
-def fake_conv_first(cutouts, weight, bias, slope=0.1, want_plain=False, want_split=True, parts=3):
+def fake_conv_first(cutouts, weight, bias, slope=0.1, want_plain=False, want_split=True, parts=3, status=None):
     M, P = cutouts.shape
     v = F.conv1d(cutouts.view(M, 1, P), weight.view(-1, 1, 3), bias, padding=1)        # [M, C, P]
     v = F.leaky_relu(v, slope).permute(0, 2, 1).reshape(M * P, -1)
@@ -51,7 +51,7 @@ def fake_conv_first(cutouts, weight, bias, slope=0.1, want_plain=False, want_spl
 
 
 def fake_conv_tc(a_split, w_split, bias, Mcut, LA, Lout, taps, pad, pool=1, slope=0.1, want_plain=False, want_split=True,
-                 chain_channels=0, out_scale=1.0):
+                 chain_channels=0, out_scale=1.0, status=None, plain_out=None):
     """The definition pof_conv_tc_fwd / pof_conv_tc_f16_fwd implement, with the three split products in plain fp32."""
     parts = ops.SPLIT_F16 if a_split.dtype == torch.float16 else 2
     a_split, w_split = a_split.float(), w_split.float()
@@ -65,16 +65,25 @@ def fake_conv_tc(a_split, w_split, bias, Mcut, LA, Lout, taps, pad, pool=1, slop
     if pool == 2:
         y = F.max_pool1d(y, 2)
     y = torch.where(y > 0, y, y * slope).permute(0, 2, 1).reshape(Mcut * Lout // pool, -1)
-    return _emit(y, want_plain, want_split, parts)
+    plain, split = _emit(y, want_plain or plain_out is not None, want_split, parts)
+    if plain_out is not None:
+        plain_out.view(plain.shape).copy_(plain)
+        plain = plain_out
+    return plain, split
 
 
-def fake_head(y, bias, M, L, w_head, b_head, n_sigmoid, slope=0.1):
+def fake_head(y, bias, M, L, w_head, b_head, n_sigmoid, slope=0.1, out=None, out_rest=None):
     if bias is None:
         bias = torch.zeros(y.shape[1])
+    dst_cls = out
     v = F.leaky_relu(y + bias, slope).view(M, L, -1).mean(dim=1)
     out = v @ w_head.t() + b_head
     out[:, :n_sigmoid] = torch.sigmoid(out[:, :n_sigmoid])
-    return out
+    if out_rest is None:
+        return out
+    dst_cls.view(M, n_sigmoid).copy_(out[:, :n_sigmoid])
+    out_rest.view(M, -1).copy_(out[:, n_sigmoid:])
+    return dst_cls, out_rest
 
 
 @pytest.fixture
@@ -110,7 +119,8 @@ def test_channels_last_backbone_matches_oracle(cpu_glue, split, tc, f16):
         assert_rel(feat.view(b, n, 14, 256).permute(0, 1, 3, 2), want, tol=2e-6, what="features")
         emb = net.embed(x_op, b * n).view(b, n, -1)
         assert_rel(emb, omodel.gate_embed(want, sd), tol=2e-6, what="embedding")
-        v = net.votes(net.operand(feat), b * n, 14).view(b, n, 3)
+        got_cls, got_reg = torch.empty(b, n, 1), torch.empty(b, n, 2)
+        net.votes(net.operand(feat), b * n, 14, got_cls, got_reg)
         cls, reg = omodel.backbone_back(want, sd)
-        assert_rel(v[:, :, :1], torch.sigmoid(cls), tol=2e-6, what="scores")
-        assert_rel(v[:, :, 1:], reg, tol=2e-6, what="votes")
+        assert_rel(got_cls, torch.sigmoid(cls), tol=2e-6, what="scores")
+        assert_rel(got_reg, reg, tol=2e-6, what="votes")
