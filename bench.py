@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32-tf32", "fp32-simt", "tf32x3", "tf32"])
     ap.add_argument("--cpu-scans", type=int, default=24, help="scans in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-spot", action="store_true", help="skip the oracle replay of two of the timed sequences")
     ap.add_argument("--extra-precisions", default="", help="comma list of further engine precisions to time (device only)")
     ap.add_argument("--seq-chunk", type=int, default=0, help="sequences per backbone chunk (0 = engine default)")
     return ap.parse_args()
@@ -148,6 +149,47 @@ def cpu_reference_scans_per_s(shape, n_scans, warmup=2, sequences=1, model_devic
     if on_gpu:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32_was
     return timed / dt, cores, timed, {k: 1e3 * v / timed for k, v in stage.items()}
+
+
+def parity_spot(det, phi, scans, picks):
+    """Replay `picks` of the sequences the detector just streamed through the oracle's reference loop (NumPy cutout ->
+    torch-CPU SpatialDROW with dense attention -> sigmoid -> NumPy NMS; the checker, after the timed region) and compare
+    the detector's LAST step: scores, votes, attention memory (max error relative to the tensor's magnitude) and the
+    NMS instance masks.  scans: [T, B, N] = every step the detector has seen."""
+    import numpy as np
+    import torch
+
+    from oracle import cutout as ocut
+    from oracle import model as omodel
+    from oracle import nms as onms
+
+    sd = {k: v.detach().cpu() for k, v in build_model().state_dict().items()}
+    worst = {"scores": 0.0, "votes": 0.0, "memory": 0.0, "similarities": 0.0}
+    mask_self = mask_ref = True
+    for b in picks:
+        tmpl = None
+        with torch.no_grad():
+            for t in range(scans.shape[0]):
+                ct = ocut.scans_to_cutout(scans[t, b][None], phi, stride=1, **CUTOUT_KW)
+                cls, reg, tmpl, ff = omodel.spatial_drow_stream(torch.from_numpy(ct)[None], sd, ALPHA, WINDOW, tmpl)
+        conf = torch.sigmoid(cls[0]).numpy()
+        got = {"scores": det._last["pred_cls"][b].cpu().numpy().reshape(-1, 1), "votes": det._last["pred_reg"][b].cpu().numpy(),
+               "memory": det.template[b].cpu().numpy(), "similarities": det._last["feat_fused"][b].cpu().numpy()}
+        want = {"scores": conf, "votes": reg[0].numpy(), "memory": tmpl[0].numpy(), "similarities": ff[0].numpy()}
+        for k in worst:
+            worst[k] = max(worst[k], float(np.abs(got[k].astype(np.float64) - want[k]).max() / np.abs(want[k]).max()))
+        mask = det._last["instance_mask"][b].cpu().numpy()
+        mine = onms.nms_sweep_spec(scans[-1, b], phi, got["scores"], got["votes"])       # NMS spec on the detector's own scores
+        ref = onms.nms_predicted_center(scans[-1, b], phi, conf, reg[0].numpy())[2]       # the reference loop end to end
+        mask_self = mask_self and bool(np.array_equal(mask, mine["instance_mask"]))
+        mask_ref = mask_ref and bool(np.array_equal(mask, ref))
+    return {"sequences": list(picks), "steps_replayed": int(scans.shape[0]), "max_rel": max(worst.values()), "per_tensor": worst,
+            "mask_equal": mask_self, "mask_equal_reference_loop": mask_ref,
+            "note": "max_rel: detector vs the oracle's float32 reference loop on the same ranges after the same history, relative "
+                    "to each tensor's magnitude (bar 1e-5; tests/test_gpu_timed_config.py arbitrates with float64); mask_equal: "
+                    "device NMS == the NMS specification on the detector's own scores (bit-exact bar); "
+                    "mask_equal_reference_loop: == the reference loop's masks (differs only if two scores or a distance "
+                    "sit within float32 noise of each other)"}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -268,6 +310,9 @@ def run_ours(args):
     conv_flops = {k: list(det.event_work.get(k, [])) for k in conv_ms}
     chunk_seqs = det.seq_chunk
     h2d, d2h = det.h2d_bytes_per_step, det.d2h_bytes_per_step
+    spot = None
+    if rank == 0 and not args.no_parity_spot:
+        spot = parity_spot(det, phi, scans, sorted({0, B - 1}))
     del det
     torch.cuda.empty_cache()
     ms_e2e, det2, _, n_det = timed_run(args.precision, host_path=True, record=False)
@@ -368,6 +413,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K, "detections_in_timed_region": n_det,
                 "api": "StreamingDetector.step(host ranges) -> host detections"},
         "gpu_launches": launches,
+        "parity_spot": spot,
         "roofline": conv_roof,
         "roofline_gate": {"kernel": "gate_stream_kernel<11,0> (attention memory update)", "bound": "hbm",
                      "achieved": gate_gbs, "peak": peak, "unit": "GB/s", "frac": gate_gbs / peak, "traffic": None,
