@@ -4,8 +4,9 @@
 Same CLI and YAML schema as the reference's bin/train_dr_spaam.py (:22-35).  What it runs is the
 coherent version of that script: SpatialDROW + the detector loss
 (`model_fn_obj_det`) + Adam(lr=0.01) + the Trainer, with cutouts generated on the GPU.  Under
-torchrun it is data parallel: one process per GPU, DistributedDataParallel gradient all-reduce over
-NCCL, per-rank BatchNorm, rank 0 writes checkpoints.  Extra flags (--max-iters, --out) only bound
+torchrun it is data parallel: one process per GPU, the samples of an epoch sharded by a DistributedSampler,
+DistributedDataParallel gradient all-reduce over NCCL, per-rank BatchNorm, rank 0 writes checkpoints.  `--data` is
+a DROWv2 directory (train/*.csv + .wc/.wa/.wp/.odom2); if it does not exist, seeded synthetic sequences are served.  Extra flags (--max-iters, --out) only bound
 the run; they do not change the training step.
 """
 import argparse
@@ -58,7 +59,7 @@ def main():
         network_type=cfg["network"], train_with_val=cfg["train_with_val"],
         use_data_augumentation=cfg["use_data_augumentation"], cutout_kwargs=cfg["cutout_kwargs"],
         polar_grid_kwargs=cfg["polar_grid_kwargs"], pedestrian_only=cfg["pedestrian_only"],
-        num_samples=args.num_samples)
+        num_samples=args.num_samples, device=device)      # sharded across ranks when world > 1; pinned staging + async H2D
 
     model = SpatialDROW(num_scans=cfg["num_scans"], num_pts=cfg["cutout_kwargs"]["num_cutout_pts"],
                         focal_loss_gamma=cfg["focal_loss_gamma"], alpha=cfg["similarity_kwargs"]["alpha"],
@@ -79,7 +80,7 @@ def main():
                          ckpt_save_interval=max(int(cfg["epochs"] / 10), 1), starting_iteration=int(starting_iteration),
                          starting_epoch=max(int(starting_epoch), 0), max_iters=args.max_iters)
     if rank == 0:
-        print("final loss %.6f" % last)
+        print("final loss %.6f" % last if last is not None else "no training iteration ran (empty loader)")
         if tb_logger is not None:
             tb_logger.close()
 

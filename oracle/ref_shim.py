@@ -57,6 +57,10 @@ def load():
         ref_utils = importlib.import_module("src.utils.utils")
         ref_model = importlib.import_module("src.depracted.model.dr_spaam")
         _cache["prototype"] = importlib.import_module("src.depracted.model.prototype")
+        try:
+            _cache["dataset_dr_spaam"] = importlib.import_module("src.utils.dataset_dr_spaam")
+        except Exception as e:      # noqa: BLE001  (only the dataset test needs it; it reports the reason)
+            _cache["dataset_dr_spaam"] = e
     finally:
         sys.path.remove(REFERENCE_ROOT)
         ref_mods = {k: sys.modules.pop(k) for k in list(sys.modules)
@@ -71,6 +75,15 @@ def load_prototype():
     """The reference's `src.depracted.model.prototype` module (Prototype, flow_loss)."""
     load()
     return _cache["prototype"]
+
+
+def load_dataset_module():
+    """The reference's `src.utils.dataset_dr_spaam` module (DROWDataset2 and the loaders)."""
+    load()
+    mod = _cache["dataset_dr_spaam"]
+    if isinstance(mod, Exception):
+        raise mod
+    return mod
 
 
 class cpu_cuda_noop:

@@ -115,6 +115,9 @@ class Trainer:
             if not lr_scheduler_each_iter:
                 self.lr_scheduler.step(self._epoch)
             running, n_batches = 0.0, max(len(train_loader), 1)
+            sampler = getattr(train_loader, "sampler", None)
+            if hasattr(sampler, "set_epoch"):          # DistributedSampler: a different shard order every epoch
+                sampler.set_epoch(self._epoch)
             for cur_it, batch in enumerate(train_loader):
                 if lr_scheduler_each_iter:
                     self.lr_scheduler.step(self._epoch + cur_it / n_batches)

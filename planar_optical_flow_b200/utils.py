@@ -54,6 +54,84 @@ def global_to_canonical(scan_r, scan_phi, dets_r, dets_phi):
     return dx, dy
 
 
+def global_to_canonical_flow(flow, scan_phi):
+    """Per-point rotation of xy flow vectors into each beam's canonical frame (utils.py:62-76):
+    rows (cos, -sin) and (sin, cos) of the beam angle applied to (fx, fy)."""
+    s, c = np.sin(scan_phi), np.cos(scan_phi)
+    rot = np.stack([np.stack([c, -s], axis=1), np.stack([s, c], axis=1)], axis=1)      # [N, 2, 2]
+    return np.einsum("ijk,ik->ij", rot, flow)
+
+
+def canonical_to_global_flow(flow_canonical, scan_phi):
+    """Inverse of `global_to_canonical_flow` (utils.py:79-91)."""
+    s, c = np.sin(scan_phi), np.cos(scan_phi)
+    rot = np.stack([np.stack([c, s], axis=1), np.stack([-s, c], axis=1)], axis=1)
+    return np.einsum("ijk,ik->ij", rot, flow_canonical)
+
+
+def closest_detection(scan, scan_phi, dets, radii):
+    """1-based index of the closest detection whose radius contains each scan point, 0 = none (utils.py:230-256).
+    `dets`: (r, phi) pairs; distances are Euclidean in the scanner's xy frame, the radius is subtracted before the
+    arg-min over (0 = outside everything, d_1 - radius_1, ...)."""
+    if len(dets) == 0:
+        return np.zeros_like(scan, dtype=int)
+    if len(dets) != len(radii):
+        raise AssertionError("Need to give a radius for each detection!")
+    sx, sy = rphi_to_xy(np.asarray(scan), np.asarray(scan_phi))
+    pts = np.stack([sx, sy], axis=1).astype(np.float64)
+    d = np.asarray(dets, dtype=np.float64).reshape(-1, 2)
+    centres = np.stack(rphi_to_xy(d[:, 0], d[:, 1]), axis=1)
+    diff = pts[:, None, :] - centres[None, :, :]
+    dists = np.sqrt((diff * diff).sum(axis=2)) - np.asarray(radii, dtype=np.float64)[None, :]
+    return np.argmin(np.hstack([np.zeros((len(pts), 1)), dists]), axis=1)
+
+
+def get_regression_target(scan, scan_phi, wcs, was, wps, radius_wc=0.6, radius_wa=0.4, radius_wp=0.35,
+                          label_wc=1, label_wa=2, label_wp=3, pedestrian_only=False):
+    """Per-point class label and canonical (dx, dy) vote to the centre of the closest annotated object
+    (utils.py:143-181): `target_cls [N] int64`, `target_reg [N, 2] float32`."""
+    n = len(scan)
+    target_cls = np.zeros(n, dtype=np.int64)
+    target_reg = np.zeros((n, 2), dtype=np.float32)
+    if pedestrian_only:
+        all_dets, radii, labels = list(wps), [radius_wp] * len(wps), [0] + [1] * len(wps)
+    else:
+        all_dets = list(wcs) + list(was) + list(wps)
+        radii = [radius_wc] * len(wcs) + [radius_wa] * len(was) + [radius_wp] * len(wps)
+        labels = [0] + [label_wc] * len(wcs) + [label_wa] * len(was) + [label_wp] * len(wps)
+    which = closest_detection(scan, scan_phi, all_dets, radii)
+    hit = which > 0
+    if hit.any():
+        d = np.asarray(all_dets, dtype=np.float64).reshape(-1, 2)[which[hit] - 1]
+        target_cls[hit] = np.asarray(labels, dtype=np.int64)[which[hit]]
+        dx, dy = global_to_canonical(np.asarray(scan)[hit], np.asarray(scan_phi)[hit], d[:, 0], d[:, 1])
+        target_reg[hit, 0], target_reg[hit, 1] = dx, dy
+    return target_cls, target_reg
+
+
+def get_displacement_from_odometry(scan1_xy, odom0, odom1):
+    """Apparent displacement of stationary points between two scanner poses (x, y, phi), expressed in the current
+    scanner frame (utils.py:639-662): p - R0^T (R1 p + T1 - T0)."""
+    def rot(phi):
+        c, s = np.cos(phi), np.sin(phi)
+        return np.array([[c, -s], [s, c]], dtype=np.float32)
+
+    r0, r1 = rot(odom0[2]), rot(odom1[2])
+    m = np.eye(2) - np.matmul(r0.T, r1)
+    shift = (odom1[:2] - odom0[:2]).reshape(2, 1)
+    return np.matmul(scan1_xy, m.T) - np.matmul(r0.T, shift).reshape(1, 2)
+
+
+def data_augmentation(sample_dict, rng=np.random):
+    """Random left-right flip of all scans of a sample and of the x component of its votes (utils.py:126-140)."""
+    scans, target_reg = sample_dict["scans"], sample_dict["target_reg"]
+    if rng.rand() < 0.5:
+        scans = scans[:, ::-1]
+        target_reg[:, 0] = -target_reg[:, 0]
+    sample_dict.update({"target_reg": target_reg, "scans": scans})
+    return sample_dict
+
+
 # ------------------------------------------------------------------ cutout
 def _phi_tensor(scan_phi, device):
     phi = np.ascontiguousarray(scan_phi)
