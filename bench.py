@@ -3,6 +3,16 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--sequences 256] [--shape jrdb|drow] [--precision fp32|fp32-tf32|fp32-simt|tf32x3|tf32]
+                    [--scaling weak|strong] [--graph] [--workload stream|train]
+
+Other modes (same JSON contract, `config.workload` says which):
+  --scaling strong      BASELINE.json configs[2] as written: `--sequences` (256) sequences IN TOTAL, sharded round-robin over
+                        the ranks (planar_optical_flow_b200.parallel.shard_sequences); default is weak (256 per GPU)
+  --sequences 1|8 ...   latency mode: a batch of <= 16 sequences replays each step as one CUDA graph (`--graph` forces it
+                        for any size) and the line carries `latency` = ms per step = ms per scan of a sequence
+  --workload train      BASELINE.json configs[3]: the training step of bin/train_dr_spaam.py (SpatialDROW, per-GPU batch 8 x
+                        11 scans x 450 points, cutouts on the device, fused gate forward/backward, Adam; DDP all-reduce
+                        over NCCL when N > 1); metric = training samples/s
 
 Workload (BASELINE.json configs[2], the one the metric is quoted on): DR-SPAAM streaming
 inference with spatial-attention memory over 256 independent JRDB-shaped sequences
@@ -56,6 +66,10 @@ def parse():
     ap.add_argument("--no-parity-spot", action="store_true", help="skip the oracle replay of two of the timed sequences")
     ap.add_argument("--extra-precisions", default="", help="comma list of further engine precisions to time (device only)")
     ap.add_argument("--seq-chunk", type=int, default=0, help="sequences per backbone chunk (0 = engine default)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --sequences per GPU; strong: --sequences in total, sharded over the ranks")
+    ap.add_argument("--graph", action="store_true", help="replay each step as one CUDA graph (automatic for <= 16 sequences)")
+    ap.add_argument("--workload", default="stream", choices=["stream", "train"])
     return ap.parse_args()
 
 
@@ -262,14 +276,33 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B, K, W = args.sequences, args.steps, args.warmup
-    phi, scans = make_sequences(args.shape, B, W + K, seed0=1000 * rank)      # every rank owns ITS sequences
+    K, W = args.steps, args.warmup
+    if args.scaling == "strong":                   # configs[2] as written: the sequences of the job, sharded round-robin
+        from planar_optical_flow_b200.parallel import shard_sequences
+
+        mine = shard_sequences(args.sequences, rank, world)
+        phi, scans = make_sequences(args.shape, args.sequences, W + K, seed0=0)
+        scans = np.ascontiguousarray(scans[:, mine])
+        B, total_seqs = len(mine), args.sequences
+        if B == 0:
+            raise SystemExit("rank %d owns no sequence: --sequences %d < --gpus %d" % (rank, args.sequences, world))
+    else:
+        B, total_seqs = args.sequences, world * args.sequences
+        phi, scans = make_sequences(args.shape, B, W + K, seed0=1000 * rank)      # every rank owns ITS sequences
     N = len(phi)
     model = build_model()
+    use_graph = args.graph or B <= 16
+    if use_graph and W < 4:                        # two eager steps, then one capture per memory parity, all before the timed region
+        W = 4
+        phi, scans = make_sequences(args.shape, total_seqs if args.scaling == "strong" else B, W + K,
+                                    seed0=0 if args.scaling == "strong" else 1000 * rank)
+        if args.scaling == "strong":
+            scans = np.ascontiguousarray(scans[:, mine])
 
-    def timed_run(precision, host_path, record):
-        det = StreamingDetector(model, phi, CUTOUT_KW, B, device=dev, precision=precision, record_events=record,
-                                seq_chunk=args.seq_chunk or None)
+    def timed_run(precision, host_path, record, graph=None):
+        graph = use_graph if graph is None else graph
+        det = StreamingDetector(model, phi, CUTOUT_KW, B, device=dev, precision=precision, record_events=record and not graph,
+                                seq_chunk=args.seq_chunk or None, cuda_graph=graph)
         d_scans = torch.from_numpy(scans).to(dev)
         run = (lambda t: det.step(scans[t])) if host_path else (lambda t: det.step_device(d_scans[t]))
         checksum = 0
@@ -303,6 +336,13 @@ def run_ours(args):
     if sampler:
         sampler.start()
     ms_dev, det, launches, _ = timed_run(args.precision, host_path=False, record=True)
+    spot = None
+    if rank == 0 and not args.no_parity_spot:
+        spot = parity_spot(det, phi, scans, sorted({0, B - 1}))
+    if use_graph:          # per-stage CUDA events cannot sit inside a graph: the stage times come from an eager run of the same steps
+        del det
+        torch.cuda.empty_cache()
+        ms_eager, det, _, _ = timed_run(args.precision, host_path=False, record=True, graph=False)
     gate_ms = det.event_ms("gate")
     cut_ms = det.event_ms("cutout")
     nms_ms = det.event_ms("nms")
@@ -310,9 +350,6 @@ def run_ours(args):
     conv_flops = {k: list(det.event_work.get(k, [])) for k in conv_ms}
     chunk_seqs = det.seq_chunk
     h2d, d2h = det.h2d_bytes_per_step, det.d2h_bytes_per_step
-    spot = None
-    if rank == 0 and not args.no_parity_spot:
-        spot = parity_spot(det, phi, scans, sorted({0, B - 1}))
     del det
     torch.cuda.empty_cache()
     ms_e2e, det2, _, n_det = timed_run(args.precision, host_path=True, record=False)
@@ -324,7 +361,7 @@ def run_ours(args):
         ms_x, d3, _, _ = timed_run(prec, host_path=False, record=False)
         del d3
         torch.cuda.empty_cache()
-        extra[prec] = {"value": world * B * K / (ms_x / 1e3), "unit": "scans/s", "ms_per_step": ms_x / K}
+        extra[prec] = {"value": total_seqs * K / (ms_x / 1e3), "unit": "scans/s", "ms_per_step": ms_x / K}
 
     # BASELINE.json configs[1]: cutout-only sweep, largest batch (4096 JRDB-shaped scans, 1 GB of output per
     # launch, far larger than L2), both arithmetic policies; CUDA events around each launch
@@ -396,20 +433,22 @@ def run_ours(args):
                      "all_conv_tc_launches": {"achieved": all_fl / (all_ms * 1e-3) / 1e12, "ms_per_step": all_ms / K,
                                               "share_of_step": all_ms / ms_dev}}
     out = {
-        "metric": METRIC, "value": world * B * K / (ms_dev / 1e3), "unit": "scans/s", "n_gpus": world,
-        "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": total_seqs * K / (ms_dev / 1e3), "unit": "scans/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": {"fp32": "f32 (operands split into two float16 parts, three kind::f16 products per term on tcgen05, 128-channel chains promoted to fp32 registers; 6-7e-7 per layer vs fp64, cuDNN fp32: 1-2e-6)",
                                       "fp32-tf32": "f32 (3xTF32 split products on tcgen05, 64-channel chains promoted to fp32 registers; 5-7e-7 per layer vs fp64)",
                                       "fp32-simt": "f32", "tf32x3": "f32 operands, TF32 tensor-core accumulation (1e-4)",
                                       "tf32": "tf32"}[args.precision], "data": "synthetic",
         "impl": "ours",
-        "config": {"workload": "DR-SPAAM streaming inference, %d independent %s-shaped sequences per GPU (%d pts), "
-                               "cutout+backbone+attention memory+heads+NMS per scan" % (B, args.shape.upper(), N),
-                   "sequences_per_gpu": B, "points": N, "cutout_pts": CUTOUT_KW["num_cutout_pts"], "window": WINDOW,
+        "config": {"workload": "DR-SPAAM streaming inference, %s %s-shaped sequences (%d pts), "
+                               "cutout+backbone+attention memory+heads+NMS per scan"
+                               % ("%d independent sequences in total, sharded round-robin over %d GPU(s)," % (total_seqs, world)
+                                  if args.scaling == "strong" else "%d independent sequences per GPU," % B, args.shape.upper(), N),
+                   "sequences_per_gpu": B, "sequences_total": total_seqs, "cuda_graph": use_graph, "points": N, "cutout_pts": CUTOUT_KW["num_cutout_pts"], "window": WINDOW,
                    "alpha": ALPHA, "precision": args.precision, "weights": "random-init",
                    "l2_policy": "inputs larger than L2: per step the path streams %.1f GB of attention memory "
                                 "and features (L2 = 126 MB)" % (3 * B * N * 3584 * 4 / 1e9)},
-        "e2e": {"value": world * B * K / (ms_e2e / 1e3), "unit": "scans/s", "h2d_bytes_per_step": h2d,
+        "e2e": {"value": total_seqs * K / (ms_e2e / 1e3), "unit": "scans/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K, "detections_in_timed_region": n_det,
                 "api": "StreamingDetector.step(host ranges) -> host detections"},
         "gpu_launches": launches,
@@ -436,6 +475,11 @@ def run_ours(args):
                               "rest": ms_dev / K - (sum(cut_ms) + sum(gate_ms) + sum(nms_ms) + sum(sum(v) for v in conv_ms.values())) / K},
         "clocks": clocks,
     }
+    if use_graph:
+        out["latency"] = {"ms_per_step": ms_dev / K, "ms_per_scan_of_a_sequence": ms_dev / K, "e2e_ms_per_step": ms_e2e / K,
+                          "eager_ms_per_step": ms_eager / K, "launches_per_step_in_graph": launches / K,
+                          "note": "each step = one scan of each of the %d sequence(s), replayed as one CUDA graph per memory parity; "
+                                  "eager = the same steps issued launch by launch from Python" % B}
     if extra:
         out["other_precisions"] = extra
     if out["roofline"] is None:          # library-convolution modes: the attention kernel is the dominant libpof kernel
@@ -453,6 +497,163 @@ def run_ours(args):
                                                "SpatialDROW (dense attention) on cuda in strict fp32, NumPy NMS; batch 1 as in "
                                                "depracted_scripts/infer_person_flow.py" % (ng, args.shape.upper()),
                                      "stage_ms_per_scan": stage_g}
+    _JSON_OUT.write(json.dumps(out) + "\n")
+    _JSON_OUT.flush()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- training workload (configs[3])
+TRAIN_METRIC = "DR-SPAAM training samples/sec (DROW 450-pt, 11 scans per sample)"
+
+
+def run_train(args):
+    """BASELINE.json configs[3]: the step of bin/train_dr_spaam.py with config/dr_spaam.yaml - SpatialDROW, per-GPU batch 8,
+    11 scans x 450 points per sample, cutouts on the device, fused attention-memory forward/backward, detector loss, Adam;
+    DistributedDataParallel (one 7.9 MB bucket, NCCL over NVLink) when N > 1.  `value`: batches resident on the device;
+    `e2e`: every step takes a fresh host batch through the loader's pinned staging buffers (H2D inside the timed region)
+    and reads the loss back."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import yaml
+    from torch import optim
+
+    from planar_optical_flow_b200 import parallel
+    from planar_optical_flow_b200.dataset_dr_spaam import DeviceBatches, create_dataloader
+    from planar_optical_flow_b200.eval_utils import make_model_fn_obj_det
+    from planar_optical_flow_b200.model import SpatialDROW
+
+    rank, local, world = parallel.env_rank_world()
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    parallel.init(device=dev)
+    with open(os.path.join(ROOT, "config", "dr_spaam.yaml")) as f:
+        cfg = yaml.safe_load(f)
+    bs, K, W = cfg["batch_size"], args.steps, max(args.warmup, 3)
+    n_batches = 4
+    loader, _ = create_dataloader(data_path=os.path.join(ROOT, "no-such-dir"), num_scans=cfg["num_scans"], batch_size=bs, num_workers=0,
+                                  network_type=cfg["network"], use_data_augumentation=cfg["use_data_augumentation"],
+                                  cutout_kwargs=cfg["cutout_kwargs"], polar_grid_kwargs=cfg["polar_grid_kwargs"],
+                                  pedestrian_only=cfg["pedestrian_only"], num_samples=bs * n_batches * max(world, 1))
+    host_batches = [b for b in loader][:n_batches]
+
+    class _Replay:                                         # the loader's batches, again and again (synthesis is not the measured path)
+        sampler = dataset = None
+
+        def __len__(self):
+            return 1 << 30
+
+        def __iter__(self):
+            while True:
+                yield from host_batches
+
+    staged = DeviceBatches(_Replay(), dev)
+    dev_batches = []
+    it = iter(staged)
+    for _ in range(n_batches):
+        b = next(it)
+        dev_batches.append({k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in b.items()})
+    torch.manual_seed(0)
+    net = SpatialDROW(num_scans=cfg["num_scans"], num_pts=cfg["cutout_kwargs"]["num_cutout_pts"],
+                      focal_loss_gamma=cfg["focal_loss_gamma"], alpha=cfg["similarity_kwargs"]["alpha"],
+                      window_size=cfg["similarity_kwargs"]["window_size"], pedestrian_only=cfg["pedestrian_only"]).to(dev)
+    opt = optim.Adam(net.parameters(), lr=0.01)
+    n_params = sum(p.numel() for p in net.parameters())
+    net = parallel.wrap_ddp(net, dev)
+    fn = make_model_fn_obj_det(cfg["cutout_kwargs"])
+    net.train()
+
+    def one(batch):
+        opt.zero_grad(set_to_none=True)
+        loss = fn(net, batch)[0]
+        loss.backward()
+        opt.step()
+        return loss
+
+    def timed(source, read_loss):
+        for i in range(W):
+            one(source(i))
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = 0.0
+        for i in range(K):
+            loss = one(source(W + i))
+            if read_loss:
+                last = float(loss.item())                 # the D2H read of the step's result
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), last if read_loss else float(loss.item())
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_dev, loss_dev = timed(lambda i: dev_batches[i % n_batches], read_loss=False)
+    staged.h2d_bytes = 0
+    ms_e2e, loss_e2e = timed(lambda i: next(it), read_loss=True)
+    h2d = staged.h2d_bytes // (W + K)
+    clocks = sampler.stop() if sampler else None
+
+    # the gate's backward in isolation at the training shape (HBM bound): g_out and the memory are read once, g_x and g_tmpl written
+    gate_roof = None
+    if rank == 0:
+        from planar_optical_flow_b200 import ops
+
+        Bn, N, CL, E, Wn = bs, 450, 3584, 128, int(2 * int(cfg["similarity_kwargs"]["window_size"] / 2) + 1)
+        g = torch.Generator(device=dev).manual_seed(0)
+        tmpl = torch.randn(Bn, N, CL, device=dev, generator=g)
+        ex, et = torch.randn(Bn, N, E, device=dev, generator=g) * 0.2, torch.randn(Bn, N, E, device=dev, generator=g) * 0.2
+        _, _, attn = ops.gate_forward(tmpl, tmpl.clone(), ex, et, 0.5, Wn, want_weights=True)
+        g_out, g_feat = torch.randn(Bn, N, CL, device=dev, generator=g), torch.randn(Bn, N, Wn, device=dev, generator=g)
+        for _ in range(5):
+            ops.gate_backward(tmpl, ex, et, attn, g_out, g_feat, 0.5, Wn)
+        torch.cuda.synchronize(dev)
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ev.record()
+        for _ in range(20):
+            ops.gate_backward(tmpl, ex, et, attn, g_out, g_feat, 0.5, Wn)
+        e_ev.record()
+        torch.cuda.synchronize(dev)
+        bwd_ms = s_ev.elapsed_time(e_ev) / 20
+        bwd_bytes = Bn * N * (4 * CL * 4 + 4 * E * 4 + 3 * Wn * 4)        # read g_out, tmpl; write g_x, g_tmpl; embeddings and their gradients; weights, g_feat, g_s
+        peak, peak_src = measured_hbm_peak()
+        gbs = bwd_bytes / (bwd_ms * 1e-3) / 1e9
+        gate_roof = {"kernel": "pof_spaam_gate_bwd (gate_bwd_scores + gate_bwd_embed + gate_stream_kernel<11,1>), per-GPU training batch "
+                               "(%d x %d points), isolated launches" % (Bn, N),
+                     "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                     "avg_launch_ms": bwd_ms, "algorithmic_bytes_per_launch": bwd_bytes, "peak_source": peak_src,
+                     "note": "small launch (%.0f MB): latency matters as much as bandwidth; 10 such calls per training step" % (bwd_bytes / 1e6)}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    out = {"metric": TRAIN_METRIC, "value": world * bs * K / (ms_dev / 1e3), "unit": "samples/s", "n_gpus": world, "steps": K,
+           "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32 parameters and activations; cuDNN convolutions with TF32 tensor-core products (PyTorch's training default, "
+                    "as the reference trains); attention memory forward/backward in fp32 (libpof)",
+           "data": "synthetic", "impl": "ours",
+           "config": {"workload": "DR-SPAAM training step (bin/train_dr_spaam.py, config/dr_spaam.yaml): SpatialDROW, per-GPU batch %d x %d scans x "
+                                  "450 points, device cutouts, fused gate fwd/bwd, Adam%s" % (bs, cfg["num_scans"] + 1,
+                                                                                            ", DDP all-reduce over NCCL" if world > 1 else ""),
+                      "per_gpu_batch": bs, "scans_per_sample": cfg["num_scans"] + 1, "points": 450, "parameters": n_params,
+                      "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
+                      "l2_policy": "activations of a step (several GB) are far larger than L2"},
+           "e2e": {"value": world * bs * K / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                   "ms_per_step": ms_e2e / K, "api": "model_fn_obj_det(model, host batch through DeviceBatches) + backward + Adam, loss.item()"},
+           "gpu_launches": K * (2 + cfg["num_scans"] + 3 * cfg["num_scans"]),
+           "gpu_launches_note": "libpof launches per step: the cutout call (2 kernels) + %d gate forwards + %d gate backwards of 3 kernels; "
+                                "the convolutions are cuDNN" % (cfg["num_scans"], cfg["num_scans"]),
+           "roofline": gate_roof, "last_loss": {"device_batches": loss_dev, "e2e": loss_e2e}, "clocks": clocks}
     _JSON_OUT.write(json.dumps(out) + "\n")
     _JSON_OUT.flush()
     if world > 1:
@@ -495,5 +696,7 @@ if __name__ == "__main__":
     _JSON_OUT = _claim_stdout()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "train":
+        run_train(a)
     else:
         run_ours(a)

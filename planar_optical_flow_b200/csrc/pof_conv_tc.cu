@@ -153,6 +153,35 @@ __device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity, int* st
     }
 }
 
+// Whole-warp form of the bounded wait: every lane polls, the votes make the outcome (and the time-out) WARP-UNIFORM, so
+// the compiler keeps the loop counters, ring addresses and matrix descriptors that depend on it in uniform registers.
+// (With a single-lane role - `lane == 0` around the whole loop - nothing is provably uniform and every tcgen05.mma /
+// TMA instruction is wrapped in a R2UR waterfall loop: 353 SASS instructions per k-block for 12 MMAs, and that one
+// thread's issue rate, not the tensor pipe, bounded every layer.)
+__device__ __forceinline__ bool mbar_wait_warp(unsigned bar, unsigned parity, int* status, int code) {
+    if (__all_sync(0xffffffffu, mbar_try(bar, parity))) return true;
+    const long long t0 = clock64();
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 256; ++i)
+            if (__all_sync(0xffffffffu, mbar_try(bar, parity))) return true;
+        if (__any_sync(0xffffffffu, clock64() - t0 > kWaitLimit)) {
+            if ((threadIdx.x & 31) == 0) atomicCAS(status, 0, code);
+            return false;
+        }
+    }
+}
+// One lane of a converged warp (the same lane every time for the same mask).
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
@@ -342,14 +371,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        if (warp == 0 && lane == 0) {
-            // ------------------------------------------------------------------ TMA producer
+        if (warp == 0) {
+            // ------------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
             const unsigned tx = CG * (2u * (unsigned)rows_tile * kRowBytes + (p.w_resident ? 0u : 2u * (unsigned)C::kBTile));   // both CTAs' loads land on the leader's barrier
-            long long it = 0;
             int s = 0;
             unsigned ph = 0;
             bool ok = true;
-            if (p.w_resident && first_tile < n_tiles) {          // every weight k-block of this CTA's columns, once
+            if (p.w_resident && first_tile < n_tiles && elect_one()) {          // every weight k-block of this CTA's columns, once
                 const int n0 = (int)rank * (BN / CG);
                 if (rank == 0) mbar_expect_tx(wfull, CG * (unsigned)n_kb * 2u * (unsigned)C::kBTile);
                 for (int kb = 0; kb < n_kb; ++kb) {
@@ -364,84 +392,95 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
             }
+            __syncwarp();
             for (long long tile = first_tile; tile < n_tiles && ok; tile += tile_stride) {
                 const int nt = (int)(tile % p.tiles_n);
-                const long long m0 = ((tile / p.tiles_n) * CG + rank) * p.mt;
+                const int m0 = (int)(((tile / p.tiles_n) * CG + rank) * p.mt);
                 // the rows this CTA loads next (first column tile only: the others find them in L2 anyway)
                 const long long tile_nx = tile + tile_stride;
                 const bool warm = tile_nx < n_tiles && tile_nx % p.tiles_n == 0;
-                const long long m0_nx = ((tile_nx / p.tiles_n) * CG + rank) * p.mt;
-                for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                    if (!(ok = mbar_wait(empty(s), ph ^ 1u, p.status, 1))) break;
-                    const int tap = kb / kb_per_tap, c0 = (kb - tap * kb_per_tap) * kKBlock;
-#ifndef POF_CONV_NO_PREFETCH
-                    if (warm && tap == p.pad) {                      // the unshifted tap covers every row of the tile
-                        tma_prefetch_3d(&map_a, c0, 0, (int)m0_nx);
-                        tma_prefetch_3d(&map_a, p.Cin + c0, 0, (int)m0_nx);
-                    }
-#else
-                    (void)warm; (void)m0_nx;
-#endif
+                const int m0_nx = (int)(((tile_nx / p.tiles_n) * CG + rank) * p.mt);
+                const int n0 = nt * BN + (int)rank * (BN / CG);          // my share of the weight tile's rows (CG = 1: all of them)
+                int tap = 0, c0 = 0;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    if (!(ok = mbar_wait_warp(empty(s), ph ^ 1u, p.status, 1))) break;
                     const unsigned dst = ring + (unsigned)s * stage_bytes;
-                    if (CG == 1) {
-                        mbar_expect_tx(full(s), tx);
-                        tma_load_3d(dst, &map_a, c0, tap - p.pad, (int)m0, full(s));
-                        tma_load_3d(dst + kATile, &map_a, p.Cin + c0, tap - p.pad, (int)m0, full(s));
-                        if (!p.w_resident) {
-                            tma_load_2d(dst + 2 * kATile, &map_w, c0, (tap * 2 + 0) * p.Cout + nt * BN, full(s));
-                            tma_load_2d(dst + 2 * kATile + C::kBTile, &map_w, c0, (tap * 2 + 1) * p.Cout + nt * BN, full(s));
+                    if (elect_one()) {
+#ifndef POF_CONV_NO_PREFETCH
+                        if (warm && tap == p.pad) {                      // the unshifted tap covers every row of the tile
+                            tma_prefetch_3d(&map_a, c0, 0, m0_nx);
+                            tma_prefetch_3d(&map_a, p.Cin + c0, 0, m0_nx);
                         }
-                    } else {
-                        const int n0 = nt * BN + (int)rank * (BN / CG);          // my half of the weight tile's rows
-                        if (rank == 0) mbar_expect_tx(full(s), tx);
-                        tma_load_3d_pair(dst, &map_a, c0, tap - p.pad, (int)m0, full(s));
-                        tma_load_3d_pair(dst + kATile, &map_a, p.Cin + c0, tap - p.pad, (int)m0, full(s));
-                        if (!p.w_resident) {
-                            tma_load_2d_pair(dst + 2 * kATile, &map_w, c0, (tap * 2 + 0) * p.Cout + n0, full(s));
-                            tma_load_2d_pair(dst + 2 * kATile + C::kBTile, &map_w, c0, (tap * 2 + 1) * p.Cout + n0, full(s));
+#else
+                        (void)warm; (void)m0_nx;
+#endif
+                        if (CG == 1) {
+                            mbar_expect_tx(full(s), tx);
+                            tma_load_3d(dst, &map_a, c0, tap - p.pad, m0, full(s));
+                            tma_load_3d(dst + kATile, &map_a, p.Cin + c0, tap - p.pad, m0, full(s));
+                            if (!p.w_resident) {
+                                tma_load_2d(dst + 2 * kATile, &map_w, c0, (tap * 2 + 0) * p.Cout + n0, full(s));
+                                tma_load_2d(dst + 2 * kATile + C::kBTile, &map_w, c0, (tap * 2 + 1) * p.Cout + n0, full(s));
+                            }
+                        } else {
+                            if (rank == 0) mbar_expect_tx(full(s), tx);
+                            tma_load_3d_pair(dst, &map_a, c0, tap - p.pad, m0, full(s));
+                            tma_load_3d_pair(dst + kATile, &map_a, p.Cin + c0, tap - p.pad, m0, full(s));
+                            if (!p.w_resident) {
+                                tma_load_2d_pair(dst + 2 * kATile, &map_w, c0, (tap * 2 + 0) * p.Cout + n0, full(s));
+                                tma_load_2d_pair(dst + 2 * kATile + C::kBTile, &map_w, c0, (tap * 2 + 1) * p.Cout + n0, full(s));
+                            }
                         }
                     }
+                    __syncwarp();
                     if (++s == n_stages) { s = 0; ph ^= 1u; }
+                    c0 += kKBlock;
+                    if (c0 == p.Cin) { c0 = 0; ++tap; }
                 }
             }
-        } else if (warp == 1 && lane == 0 && rank == 0) {
-            // ------------------------------------------------------------------ MMA issuer (the pair's leader only)
+        } else if (warp == 1 && rank == 0) {
+            // ------------------------------------------------------------------ MMA issuer (the pair's leader only; whole warp, one elected lane issues)
             const unsigned idesc = umma_idesc(BN, kTileM * CG, F16);
-            long long ic = 0;                                          // chains issued so far
-            int s = 0;
+            constexpr int kSteps = kRowBytes / 32;                          // one MMA consumes 32 B of the row: K = 8 (tf32) or 16 (f16)
+            const unsigned long long desc_hi = umma_desc(0);                 // everything but the 14-bit start address
+            unsigned ic = 0;                                               // chains issued so far
+            int s = 0, in_chain = 0;
             unsigned ph = 0;
             bool ok = true;
-            if (p.w_resident && first_tile < n_tiles) ok = mbar_wait(wfull, 0u, p.status, 5);
+            if (p.w_resident && first_tile < n_tiles) ok = mbar_wait_warp(wfull, 0u, p.status, 5);
             for (long long tile = first_tile; tile < n_tiles && ok; tile += tile_stride) {
                 for (int kb = 0; kb < n_kb; ++kb) {
-                    const int buf = (int)(ic & 1);
-                    const bool first = kb % p.chain == 0, last = (kb + 1) % p.chain == 0 || kb + 1 == n_kb;
-                    if (first && !(ok = mbar_wait(tempty(buf), (unsigned)((ic >> 1) & 1) ^ 1u, p.status, 2))) break;   // chain ic-2 promoted
-                    if (!(ok = mbar_wait(full(s), ph, p.status, 3))) break;                // operands landed
+                    const unsigned buf = ic & 1u;
+                    const bool first = in_chain == 0, last = in_chain + 1 == p.chain || kb + 1 == n_kb;
+                    if (first && !(ok = mbar_wait_warp(tempty(buf), ((ic >> 1) & 1u) ^ 1u, p.status, 2))) break;   // chain ic-2 promoted
+                    if (!(ok = mbar_wait_warp(full(s), ph, p.status, 3))) break;                // operands landed
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const unsigned st = ring + (unsigned)s * stage_bytes;
                     const unsigned wst = p.w_resident ? base + (unsigned)kb * 2u * C::kBTile : st + 2 * kATile;
-                    const unsigned long long a_hi = umma_desc(st), a_lo = umma_desc(st + kATile);
-                    const unsigned long long b_hi = umma_desc(wst), b_lo = umma_desc(wst + C::kBTile);
-                    const unsigned d = tmem_base + (unsigned)(buf * BN);
-                    constexpr int kSteps = kRowBytes / 32;                                  // one MMA consumes 32 B of the row: K = 8 (tf32) or 16 (f16)
-                    auto mma = [&](unsigned long long a, unsigned long long b, unsigned acc) {
-                        if (CG == 1) { if (F16) umma_f16(d, a, b, idesc, acc); else umma_tf32(d, a, b, idesc, acc); }
-                        else { if (F16) umma_f16_pair(d, a, b, idesc, acc); else umma_tf32_pair(d, a, b, idesc, acc); }
-                    };
+                    if (elect_one()) {
+                        const unsigned long long a_hi = desc_hi | ((st >> 4) & 0x3fffu), a_lo = desc_hi | (((st + kATile) >> 4) & 0x3fffu);
+                        const unsigned long long b_hi = desc_hi | ((wst >> 4) & 0x3fffu), b_lo = desc_hi | (((wst + C::kBTile) >> 4) & 0x3fffu);
+                        const unsigned d = tmem_base + buf * BN;
+                        auto mma = [&](unsigned long long a, unsigned long long b, unsigned acc) {
+                            if (CG == 1) { if (F16) umma_f16(d, a, b, idesc, acc); else umma_tf32(d, a, b, idesc, acc); }
+                            else { if (F16) umma_f16_pair(d, a, b, idesc, acc); else umma_tf32_pair(d, a, b, idesc, acc); }
+                        };
 #pragma unroll
-                    for (int k = 0; k < kSteps; ++k) mma(a_lo + 2 * k, b_hi + 2 * k, k > 0 || !first);   // corrections first
+                        for (int k = 0; k < kSteps; ++k) mma(a_lo + 2 * k, b_hi + 2 * k, k > 0 || !first);   // corrections first
 #pragma unroll
-                    for (int k = 0; k < kSteps; ++k) mma(a_hi + 2 * k, b_lo + 2 * k, 1);
+                        for (int k = 0; k < kSteps; ++k) mma(a_hi + 2 * k, b_lo + 2 * k, 1);
 #pragma unroll
-                    for (int k = 0; k < kSteps; ++k) mma(a_hi + 2 * k, b_hi + 2 * k, 1);                 // main product last
-                    if (CG == 1) {
-                        umma_commit(empty(s));
-                        if (last) { umma_commit(tfull(buf)); ++ic; }
-                    } else {
-                        umma_commit_pair(empty(s));                      // both CTAs' producers may refill their slot
-                        if (last) { umma_commit_pair(tfull(buf)); ++ic; }  // both CTAs' epilogues may read their rows
+                        for (int k = 0; k < kSteps; ++k) mma(a_hi + 2 * k, b_hi + 2 * k, 1);                 // main product last
+                        if (CG == 1) {
+                            umma_commit(empty(s));
+                            if (last) umma_commit(tfull(buf));
+                        } else {
+                            umma_commit_pair(empty(s));                      // both CTAs' producers may refill their slot
+                            if (last) umma_commit_pair(tfull(buf));          // both CTAs' epilogues may read their rows
+                        }
                     }
+                    __syncwarp();
+                    if (last) { ++ic; in_chain = 0; } else ++in_chain;
                     if (++s == n_stages) { s = 0; ph ^= 1u; }
                 }
             }

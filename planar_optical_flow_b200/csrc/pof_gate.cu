@@ -329,7 +329,13 @@ constexpr size_t gate_smem_bytes() {
 template <int W, int MODE>
 int launch_gate_stream(const GateArgs& a, dim3 grid, int threads, cudaStream_t stream) {
     constexpr size_t smem = gate_smem_bytes<W>();
-    POF_CUDA(cudaFuncSetAttribute(gate_stream_kernel<W, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool attr_set[64] = {false};          // once per device (and never inside a stream capture after the first call)
+    int dev = 0;
+    POF_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_set[dev]) {
+        POF_CUDA(cudaFuncSetAttribute(gate_stream_kernel<W, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev < 64) attr_set[dev] = true;
+    }
     gate_stream_kernel<W, MODE><<<grid, threads, smem, stream>>>(a);
     POF_CUDA(cudaGetLastError());
     return POF_OK;

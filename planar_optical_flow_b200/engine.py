@@ -230,7 +230,7 @@ class StreamingDetector:
     """
 
     def __init__(self, model, scan_phi, cutout_kwargs, num_sequences, device=None, precision="fp32",
-                 min_dist=0.5, seq_chunk=None, record_events=False, cutout_fast=False):
+                 min_dist=0.5, seq_chunk=None, record_events=False, cutout_fast=False, cuda_graph=False):
         if not torch.cuda.is_available():
             raise RuntimeError("StreamingDetector needs a CUDA device; there is no CPU path")
         if precision not in ("fp32", "fp32-tf32", "fp32-simt", "tf32x3", "tf32"):
@@ -308,6 +308,15 @@ class StreamingDetector:
         self.h_status = torch.zeros(1, dtype=torch.int32).pin_memory()
         if self.channels_last:
             self.net.status = self.status
+        # cuda_graph=True: from the third step on, the whole chain of a step (~70 launches per chunk of sequences) is
+        # replayed as ONE CUDA graph per memory parity instead of being issued launch by launch from Python - what a
+        # small batch (a robot's single scanner: B = 1) is bound by
+        self.cuda_graph = bool(cuda_graph)
+        if self.cuda_graph and record_events:
+            raise ValueError("record_events places CUDA events between the launches; it cannot be combined with cuda_graph")
+        self._graphs = {}
+        self._graph_pool = None
+        self.g_scans = torch.empty((self.B, self.N), dtype=torch.float32, device=self.device) if self.cuda_graph else None
         self.record_events = record_events
         self.events = {"cutout": [], "gate": [], "nms": []}
         self.event_work = {}               # stage -> algorithmic FLOPs of each recorded launch (tcgen05 convolutions)
@@ -319,6 +328,7 @@ class StreamingDetector:
     def reset(self):
         self.has_memory = False
         self.steps_done = 0
+        self.cur = 0
 
     @contextlib.contextmanager
     def _precision(self):
@@ -415,11 +425,39 @@ class StreamingDetector:
         """One scan per sequence, all on the device.  scans: [B, N] float32 CUDA tensor.
 
         Returns a dict of device tensors: pred_cls [B, N] (post-sigmoid), pred_reg [B, N, 2],
-        feat_fused [B, N, W] and the NMS outputs of `ops.nms_centers`.
+        feat_fused [B, N, W] and the NMS outputs of `ops.nms_centers`.  With cuda_graph=True the tensors belong to the
+        graph of the step's memory parity: they are overwritten two steps later.
         """
         B, N = self.B, self.N
         if tuple(scans.shape) != (B, N):
             raise ValueError("scans must be [%d, %d]" % (B, N))
+        if self.cuda_graph and self.steps_done >= 2:           # steps 0 and 1 run eagerly: first-frame branch, lazy set-up
+            if scans.data_ptr() != self.g_scans.data_ptr():
+                self.g_scans.copy_(scans)
+            entry = self._graphs.get(self.cur)
+            if entry is None:
+                graph = torch.cuda.CUDAGraph()
+                before = self.kernel_launches
+                torch.cuda.current_stream(self.device).synchronize()
+                with torch.cuda.graph(graph, pool=self._graph_pool):
+                    res = self._step_body(self.g_scans)
+                if self._graph_pool is None:
+                    self._graph_pool = graph.pool()
+                entry = self._graphs[self.cur] = (graph, res, self.kernel_launches - before)
+                self.kernel_launches = before
+            graph, res, launches = entry
+            graph.replay()
+            self.kernel_launches += launches
+        else:
+            res = self._step_body(scans)
+        self.cur = 1 - self.cur
+        self.has_memory = True
+        self.steps_done += 1
+        self._last = res
+        return res
+
+    def _step_body(self, scans):
+        B, N = self.B, self.N
         prev, nxt = self.memory[self.cur], self.memory[1 - self.cur]
         pred_cls = torch.empty((B, N), dtype=torch.float32, device=self.device)
         pred_reg = torch.empty((B, N, 2), dtype=torch.float32, device=self.device)
@@ -436,11 +474,7 @@ class StreamingDetector:
             with self._timed("nms"):
                 res = ops.nms_centers(scans, self.phi, pred_cls, pred_reg, min_dist=self.min_dist)
             self.kernel_launches += 3
-        self.cur = 1 - self.cur
-        self.has_memory = True
-        self.steps_done += 1
         res.update(pred_cls=pred_cls, pred_reg=pred_reg, feat_fused=feat_fused)
-        self._last = res
         return res
 
     def _raise_status(self, code):
@@ -467,8 +501,9 @@ class StreamingDetector:
         buffers) out.  Includes the H2D copy of the ranges and the D2H copy of the results."""
         src = torch.as_tensor(scans_host, dtype=torch.float32)
         self.h_scans.copy_(src)
-        self.d_scans.copy_(self.h_scans, non_blocking=True)
-        res = self.step_device(self.d_scans)
+        d_scans = self.g_scans if self.cuda_graph else self.d_scans        # the graphs read their own input buffer
+        d_scans.copy_(self.h_scans, non_blocking=True)
+        res = self.step_device(d_scans)
         for k, h in self.h_out.items():
             h.copy_(res[k], non_blocking=True)
         self.h_status.copy_(self.status, non_blocking=True)

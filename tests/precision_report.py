@@ -1,6 +1,10 @@
-"""Relative error (vs the CPU oracle, magnitude-relative) of every engine precision mode, per output and step.
+"""Relative error (magnitude-relative) of every engine precision mode, per output and step, against BOTH the CPU
+oracle's float32 reference loop and a float64 evaluation of the same network on the same cutouts (the arbiter: it
+tells how far the float32 oracle itself is from the exact result).
 
-    python tests/precision_report.py [steps] [sequences] [points]        (needs a B200; reads nothing outside the repo)
+    python tests/precision_report.py [steps] [sequences] [points] [modes] [chains]     (needs a B200; reads nothing outside the repo)
+
+`modes`: comma list of engine precisions; a mode written `fp32@64` runs with POF_CONV_TC_CHAIN=64 (tensor-core chain length).
 """
 import os
 import sys
@@ -31,31 +35,40 @@ def main():
     phi = synth.drow_phi(n)
     scans = np.stack([synth.structured_sequence(steps, n, seed=40 + k, phi=phi) for k in range(b)], axis=1)
     sd = omodel.randomize_bn_stats(omodel.init_state_dict(56, True, seed=9))
-    want = []
-    tmpl = [None] * b
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    want, want64 = [], []
+    tmpl, tmpl64 = [None] * b, [None] * b
     with torch.no_grad():
         for t in range(steps):
-            row = []
+            row, row64 = [], []
             for k in range(b):
                 ct = ocut.scans_to_cutout(scans[t, k][None], phi, **CFG)
                 cls, reg, tmpl[k], ff = omodel.spatial_drow_stream(torch.from_numpy(ct)[None], sd, 0.5, 11, tmpl[k])
                 row.append((torch.sigmoid(cls[0, :, 0]).numpy(), reg[0].numpy(), ff[0].numpy(), tmpl[k][0].numpy()))
+                cls, reg, tmpl64[k], ff = omodel.spatial_drow_stream(torch.from_numpy(ct)[None].double(), sd64, 0.5, 11, tmpl64[k])
+                row64.append((torch.sigmoid(cls[0, :, 0]).numpy(), reg[0].numpy(), ff[0].numpy(), tmpl64[k][0].numpy()))
             want.append(row)
-    print("max |got - oracle| / max |oracle|, %d sequences x %d points, per step" % (b, n))
-    for prec in modes:
+            want64.append(row64)
+    names = ("scores", "votes", "similarities", "memory")
+    print("max |a - b| / max |b|, %d sequences x %d points, per step; 'o32' = vs the float32 oracle, 'f64' = vs the float64 evaluation" % (b, n))
+    for t in range(steps):
+        e = [max(rel(want[t][k][i], want64[t][k][i]) for k in range(b)) for i in range(4)]
+        print("  %-10s step %d  " % ("oracle32", t) + "  ".join("%s f64 %.2e" % (nm, v) for nm, v in zip(names, e)))
+    for spec in modes:
+        prec, _, chain = spec.partition("@")
+        os.environ["POF_CONV_TC_CHAIN"] = chain or "0"
         m = SpatialDROW(num_scans=10, num_pts=56, alpha=0.5, window_size=11, pedestrian_only=True)
         m.load_state_dict(sd, strict=True)
         det = StreamingDetector(m.cuda(), phi, CFG, b, precision=prec)
         for t in range(steps):
             det.step(scans[t])
-            e = {"scores": 0.0, "votes": 0.0, "similarities": 0.0, "memory": 0.0}
-            for k in range(b):
-                c, r, f, mem = want[t][k]
-                e["scores"] = max(e["scores"], rel(det._last["pred_cls"][k].cpu().numpy(), c))
-                e["votes"] = max(e["votes"], rel(det._last["pred_reg"][k].cpu().numpy(), r))
-                e["similarities"] = max(e["similarities"], rel(det._last["feat_fused"][k].cpu().numpy(), f))
-                e["memory"] = max(e["memory"], rel(det.template[k].cpu().numpy(), mem))
-            print("  %-7s step %d  " % (prec, t) + "  ".join("%s %.2e" % kv for kv in e.items()))
+            got = lambda k: (det._last["pred_cls"][k].cpu().numpy(), det._last["pred_reg"][k].cpu().numpy(),      # noqa: E731
+                             det._last["feat_fused"][k].cpu().numpy(), det.template[k].cpu().numpy())
+            g = [got(k) for k in range(b)]
+            e32 = [max(rel(g[k][i], want[t][k][i]) for k in range(b)) for i in range(4)]
+            e64 = [max(rel(g[k][i], want64[t][k][i]) for k in range(b)) for i in range(4)]
+            print("  %-10s step %d  " % (spec, t) + "  ".join("%s o32 %.2e f64 %.2e" % (nm, a, c) for nm, a, c in zip(names, e32, e64)))
+    os.environ.pop("POF_CONV_TC_CHAIN", None)
 
 
 main()

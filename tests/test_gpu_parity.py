@@ -738,3 +738,24 @@ def c_full(det, k):
 
 def r_full(det, k):
     return det._last["pred_reg"][k].cpu().numpy()
+
+
+def test_cuda_graph_replay_equals_eager_steps():
+    """StreamingDetector(cuda_graph=True): from the third step on every step is one graph replay; results bit-equal to eager."""
+    from planar_optical_flow_b200.engine import StreamingDetector
+
+    n, b, steps = 90, 2, 7
+    phi = synth.drow_phi(n)
+    scans = np.stack([synth.structured_sequence(steps, n, seed=20 + k, phi=phi) for k in range(b)], axis=1)
+    sd = omodel.randomize_bn_stats(omodel.init_state_dict(56, True, seed=4))
+    eager = StreamingDetector(_product_model(sd), phi, CFG, b)
+    graph = StreamingDetector(_product_model(sd), phi, CFG, b, cuda_graph=True)
+    for t in range(steps):
+        he = {k: v.copy() for k, v in eager.step(scans[t]).items()}
+        hg = graph.step(scans[t])
+        for k in he:
+            assert np.array_equal(he[k], hg[k]), (t, k)
+        assert torch.equal(eager.template, graph.template)
+        assert torch.equal(eager._last["pred_reg"], graph._last["pred_reg"])
+    assert len(graph._graphs) == 2 and graph.kernel_launches == eager.kernel_launches
+    graph.check()
