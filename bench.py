@@ -110,8 +110,27 @@ def build_model(seed=0):
 
 
 # ----------------------------------------------------------------------------- CPU reference path
+def reference_modules():
+    """(utils module, dr_spaam module) of the UNMODIFIED reference (baseline/_ref, installed by baseline/install_reference.py
+    from the build container's read-only mount), or None when it is not there (then the oracle port is timed)."""
+    try:
+        from oracle import ref_shim
+
+        if ref_shim.available():
+            return ref_shim.load()
+    except Exception as e:      # noqa: BLE001
+        sys.stderr.write("reference tree not usable (%r): timing the oracle port\n" % (e,))
+    return None
+
+
+def cpu_reference_kind():
+    return "reference" if reference_modules() is not None else "port"
+
+
 def cpu_reference_scans_per_s(shape, n_scans, warmup=2, sequences=1, model_device="cpu"):
-    """The reference's algorithm on the host cores (oracle/, all threads torch can use).
+    """The reference's own code on the host cores when baseline/_ref holds it (its `scans_to_cutout`, its `SpatialDROW`
+    module, its `nms_predicted_center`, driven like depracted_scripts/infer_person_flow.py:101-139), else the oracle port of
+    the same algorithm (oracle/); all threads torch can use.
 
     Streams `sequences` independent sequences one scan at a time exactly like the reference loop
     (depracted_scripts/infer_person_flow.py:101-139): NumPy cutout -> torch SpatialDROW with
@@ -131,6 +150,29 @@ def cpu_reference_scans_per_s(shape, n_scans, warmup=2, sequences=1, model_devic
     model = build_model()
     sd = {k: v.detach().clone().to(model_device) for k, v in model.state_dict().items()}
     on_gpu = model_device != "cpu"
+    ref = reference_modules()
+    if ref is not None:
+        ref_utils, ref_net = ref
+        ref_model = ref_net.SpatialDROW(num_scans=10, num_pts=CUTOUT_KW["num_cutout_pts"], alpha=ALPHA, window_size=WINDOW,
+                                        pedestrian_only=True)
+        ref_model.load_state_dict(model.state_dict(), strict=True)
+        ref_model = ref_model.to(model_device).eval()
+
+        def cutout_fn(scan, phi):
+            return ref_utils.scans_to_cutout(scan[None], phi, stride=1, **CUTOUT_KW)
+
+        def model_fn(ct, tmpl):
+            return ref_model(torch.from_numpy(ct)[None].to(model_device), testing=True, fea_template=tmpl)
+
+        nms_fn = ref_utils.nms_predicted_center
+    else:
+        def cutout_fn(scan, phi):
+            return ocut.scans_to_cutout(scan[None], phi, stride=1, **CUTOUT_KW)
+
+        def model_fn(ct, tmpl):
+            return omodel.spatial_drow_stream(torch.from_numpy(ct)[None].to(model_device), sd, ALPHA, WINDOW, tmpl)
+
+        nms_fn = onms.nms_predicted_center
     if on_gpu:
         tf32_was = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
         torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
@@ -146,13 +188,13 @@ def cpu_reference_scans_per_s(shape, n_scans, warmup=2, sequences=1, model_devic
                     t0 = time.perf_counter()
                     stage = {k: 0.0 for k in stage}
                 a = time.perf_counter()
-                ct = ocut.scans_to_cutout(scans[t, b][None], phi, stride=1, **CUTOUT_KW)
+                ct = cutout_fn(scans[t, b], phi)
                 c = time.perf_counter()
-                cls, reg, tmpl[b], _ = omodel.spatial_drow_stream(torch.from_numpy(ct)[None].to(model_device), sd, ALPHA, WINDOW, tmpl[b])
+                cls, reg, tmpl[b], _ = model_fn(ct, tmpl[b])
                 conf = torch.sigmoid(cls[0]).cpu().numpy()
                 reg_h = reg[0].cpu().numpy()
                 d = time.perf_counter()
-                onms.nms_predicted_center(scans[t, b], phi, conf, reg_h)
+                nms_fn(scans[t, b], phi, conf, reg_h)
                 e = time.perf_counter()
                 stage["cutout"] += c - a
                 stage["model"] += d - c
@@ -486,16 +528,19 @@ def run_ours(args):
         out["roofline"] = out["roofline_gate"]
     if not args.no_cpu_baseline and world == 1:
         v, cores, n, stage = cpu_reference_scans_per_s(args.shape, args.cpu_scans)
-        out["cpu_baseline"] = {"value": v, "unit": "scans/s", "cores": cores, "kind": "port",
-                               "sample": "%d scans of one %s-shaped sequence streamed through the oracle "
-                                         "(NumPy cutout, torch-CPU SpatialDROW with dense attention, NumPy NMS)" % (n, args.shape.upper()),
+        kind = cpu_reference_kind()
+        out["cpu_baseline"] = {"value": v, "unit": "scans/s", "cores": cores, "kind": kind,
+                               "sample": "%d scans of one %s-shaped sequence streamed through %s "
+                                         "(NumPy cutout, torch-CPU SpatialDROW with dense attention, NumPy NMS)"
+                                         % (n, args.shape.upper(), "the unmodified reference (baseline/_ref)" if kind == "reference" else "the oracle port"),
                                "stage_ms_per_scan": stage}
         # the reference's PyTorch-GPU path (north_star's second bar): same loop, the network on this GPU
         vg, _, ng, stage_g = cpu_reference_scans_per_s(args.shape, 4 * args.cpu_scans, warmup=4, model_device="cuda")
-        out["torch_gpu_baseline"] = {"value": vg, "unit": "scans/s", "kind": "port",
-                                     "sample": "%d scans of one %s-shaped sequence: NumPy cutout on the host, the oracle's "
+        out["torch_gpu_baseline"] = {"value": vg, "unit": "scans/s", "kind": kind,
+                                     "sample": "%d scans of one %s-shaped sequence: NumPy cutout on the host, the %s "
                                                "SpatialDROW (dense attention) on cuda in strict fp32, NumPy NMS; batch 1 as in "
-                                               "depracted_scripts/infer_person_flow.py" % (ng, args.shape.upper()),
+                                               "depracted_scripts/infer_person_flow.py" % (ng, args.shape.upper(),
+                                                                                         "reference's own" if kind == "reference" else "oracle's"),
                                      "stage_ms_per_scan": stage_g}
     _JSON_OUT.write(json.dumps(out) + "\n")
     _JSON_OUT.flush()
@@ -668,15 +713,18 @@ def run_reference(args):
     seqs_per_step = 4                      # bounded sample: one step = one scan of 4 sequences
     n = args.steps * seqs_per_step
     v, cores, timed, stage = cpu_reference_scans_per_s(args.shape, n, warmup=args.warmup, sequences=seqs_per_step)
-    sample = ("each step = one scan of %d of the %d %s-shaped sequences, streamed through the oracle port of the "
-              "reference's CPU path" % (seqs_per_step, args.sequences, args.shape.upper()))
+    kind = cpu_reference_kind()
+    sample = ("each step = one scan of %d of the %d %s-shaped sequences, streamed through %s"
+              % (seqs_per_step, args.sequences, args.shape.upper(),
+                 "the unmodified reference's CPU path (baseline/_ref: its scans_to_cutout, SpatialDROW module and nms_predicted_center)"
+                 if kind == "reference" else "the oracle port of the reference's CPU path"))
     _JSON_OUT.write(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * seqs_per_step / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "DR-SPAAM streaming inference, %s-shaped sequences, CPU reference path" % args.shape.upper(),
                    "sample_sequences_per_step": seqs_per_step},
-        "cpu_baseline": {"value": v, "unit": "scans/s", "cores": cores, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": v, "unit": "scans/s", "cores": cores, "kind": kind, "sample": sample,
                          "stage_ms_per_scan": stage},
         "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }) + "\n")

@@ -18,7 +18,19 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("POF_REFERENCE_ROOT", "/root/reference")
+_INSTALLED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def _pick_root():
+    """The read-only mount in the build container; on the GPU box the unmodified copy that baseline/install_reference.py
+    placed under the git-ignored baseline/_ref/ (used by `bench.py --impl reference` only)."""
+    for cand in (os.environ.get("POF_REFERENCE_ROOT"), "/root/reference", _INSTALLED):
+        if cand and os.path.isfile(os.path.join(cand, "src", "utils", "utils.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available() -> bool:

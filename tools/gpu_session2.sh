@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_timed_config.py tests/test_gpu_parity.py -m gpu -x -q -k "conv_tc or gate or head or status" > gpurun_out/s2_pytest_conv.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s2_pytest_conv.log
-tail -4 gpurun_out/s2_pytest_conv.log
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/s2_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s2_pytest.log
+tail -15 gpurun_out/s2_pytest.log
 for shape in "56 64 64 3 1 1" "56 64 128 3 1 2" "28 128 128 3 1 1" "28 128 256 3 1 2" "14 256 256 3 1 1" "14 256 512 3 1 2" "7 512 256 3 1 1" "7 256 128 3 1 1" "14 256 128 14 0 1"; do
   python tools/conv_layer_run.py $shape 69824 5 >> gpurun_out/s2_layers.txt 2>&1
 done
@@ -18,3 +18,8 @@ python tools/conv_layer_run.py 14 256 512 3 1 2 69824 2 > gpurun_out/s2_plain.lo
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 1 -c 1 -f -o gpurun_out/s2_conv256 python tools/conv_layer_run.py 14 256 512 3 1 2 69824 2 > gpurun_out/s2_ncu.log 2>&1
 python tools/conv_layer_run.py 56 64 64 3 1 1 69824 2 > gpurun_out/s2_plain.log 2>&1 && \
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 1 -c 1 -f -o gpurun_out/s2_conv64 python tools/conv_layer_run.py 56 64 64 3 1 1 69824 2 > gpurun_out/s2_ncu.log 2>&1
+
+timeout 300 python bench.py --no-cpu-baseline --sequences 1 --steps 50 > gpurun_out/s2_bench_b1.json 2> gpurun_out/s2_bench_b1.err; echo "b1 rc=$?"; tail -3 gpurun_out/s2_bench_b1.err
+timeout 300 python bench.py --no-cpu-baseline --sequences 8 --steps 50 > gpurun_out/s2_bench_b8.json 2> gpurun_out/s2_bench_b8.err; echo "b8 rc=$?"; tail -3 gpurun_out/s2_bench_b8.err
+timeout 300 python bench.py --workload train --steps 10 > gpurun_out/s2_bench_train.json 2> gpurun_out/s2_bench_train.err; echo "train rc=$?"; tail -3 gpurun_out/s2_bench_train.err
+cat gpurun_out/s2_bench_b1.json gpurun_out/s2_bench_b8.json gpurun_out/s2_bench_train.json | cut -c1-1500
