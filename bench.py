@@ -219,30 +219,42 @@ def parity_spot(det, phi, scans, picks):
     from oracle import model as omodel
     from oracle import nms as onms
 
+    from planar_optical_flow_b200 import ops
+
     sd = {k: v.detach().cpu() for k, v in build_model().state_dict().items()}
     worst = {"scores": 0.0, "votes": 0.0, "memory": 0.0, "similarities": 0.0}
+    worst_same = dict(worst)
     mask_self = mask_ref = True
+    phi_d = torch.from_numpy(np.ascontiguousarray(phi)).to(det.device)
     for b in picks:
-        tmpl = None
+        tmpl = tmpl_s = None
+        ct_dev = ops.cutout(torch.from_numpy(np.ascontiguousarray(scans[:, b])).to(det.device).unsqueeze(1), phi_d,
+                            **CUTOUT_KW).cpu()                       # [T, N, 1, P]: the cutouts the detector computed for this sequence
         with torch.no_grad():
             for t in range(scans.shape[0]):
                 ct = ocut.scans_to_cutout(scans[t, b][None], phi, stride=1, **CUTOUT_KW)
                 cls, reg, tmpl, ff = omodel.spatial_drow_stream(torch.from_numpy(ct)[None], sd, ALPHA, WINDOW, tmpl)
+                cls_s, reg_s, tmpl_s, ff_s = omodel.spatial_drow_stream(ct_dev[t][None], sd, ALPHA, WINDOW, tmpl_s)
         conf = torch.sigmoid(cls[0]).numpy()
         got = {"scores": det._last["pred_cls"][b].cpu().numpy().reshape(-1, 1), "votes": det._last["pred_reg"][b].cpu().numpy(),
                "memory": det.template[b].cpu().numpy(), "similarities": det._last["feat_fused"][b].cpu().numpy()}
         want = {"scores": conf, "votes": reg[0].numpy(), "memory": tmpl[0].numpy(), "similarities": ff[0].numpy()}
+        same = {"scores": torch.sigmoid(cls_s[0]).numpy(), "votes": reg_s[0].numpy(), "memory": tmpl_s[0].numpy(), "similarities": ff_s[0].numpy()}
         for k in worst:
             worst[k] = max(worst[k], float(np.abs(got[k].astype(np.float64) - want[k]).max() / np.abs(want[k]).max()))
+            worst_same[k] = max(worst_same[k], float(np.abs(got[k].astype(np.float64) - same[k]).max() / np.abs(same[k]).max()))
         mask = det._last["instance_mask"][b].cpu().numpy()
         mine = onms.nms_sweep_spec(scans[-1, b], phi, got["scores"], got["votes"])       # NMS spec on the detector's own scores
         ref = onms.nms_predicted_center(scans[-1, b], phi, conf, reg[0].numpy())[2]       # the reference loop end to end
         mask_self = mask_self and bool(np.array_equal(mask, mine["instance_mask"]))
         mask_ref = mask_ref and bool(np.array_equal(mask, ref))
     return {"sequences": list(picks), "steps_replayed": int(scans.shape[0]), "max_rel": max(worst.values()), "per_tensor": worst,
+            "max_rel_network_on_same_cutouts": max(worst_same.values()), "per_tensor_network_on_same_cutouts": worst_same,
             "mask_equal": mask_self, "mask_equal_reference_loop": mask_ref,
-            "note": "max_rel: detector vs the oracle's float32 reference loop on the same ranges after the same history, relative "
-                    "to each tensor's magnitude (bar 1e-5; tests/test_gpu_timed_config.py arbitrates with float64); mask_equal: "
+            "note": "max_rel: detector vs the oracle's float32 reference loop (NumPy cutout included) on the same ranges after the same "
+                    "history, relative to each tensor's magnitude (bar 1e-5; tests/test_gpu_timed_config.py arbitrates with float64); "
+                    "network_on_same_cutouts: the same with the oracle network fed the cutout kernel's own output, i.e. without the "
+                    "<= 2-ulp difference between NumPy's float32 arctan and the device's in the window half-angles; mask_equal: "
                     "device NMS == the NMS specification on the detector's own scores (bit-exact bar); "
                     "mask_equal_reference_loop: == the reference loop's masks (differs only if two scores or a distance "
                     "sit within float32 noise of each other)"}

@@ -87,31 +87,52 @@ __global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ y, c
 }
 
 // out[m, l, c] = lrelu(b[c] + sum_k w[c, k] * x[m, l + k - 1]),  x = cutouts [M, P], zero padded.
-// A thread keeps ONE group of four channels for all the rows it visits (C/4 divides the block size), so its twelve
-// weights and four biases live in registers; the first version re-read them from shared memory for every row with
-// an 8-way bank conflict and ran at 30 % of the write bandwidth.
+// A thread keeps ONE group of G adjacent channels for all the rows it visits (C/G divides the block size), so its
+// weights and biases live in registers; the first version re-read them from shared memory for every row with
+// an 8-way bank conflict and ran at 30 % of the write bandwidth.  G = 8 for the float16 split (what the engine
+// uses): a thread then stores 16 bytes of hi and 16 bytes of lo per row, and the 8 threads of a 64-channel row write
+// two full 128-byte lines; G = 4 (8-byte stores) measured 3.6 TB/s.
+template <int G>
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float slope, int P, int C,
                                                          long long rows /* M*P */, float* plain, void* split, int parts, int* status) {
     float amax = 0.f;
-    const unsigned c4n = (unsigned)C >> 2;
-    const unsigned rpb = blockDim.x / c4n;             // rows per block and pass
-    const int c = (int)(threadIdx.x % c4n) << 2;
-    float w0[4], w1[4], w2[4], bb[4];
+    const unsigned cgn = (unsigned)C / G;
+    const unsigned rpb = blockDim.x / cgn;             // rows per block and pass
+    const int c = (int)(threadIdx.x % cgn) * G;
+    float w0[G], w1[G], w2[G], bb[G];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < G; ++j) {
         w0[j] = __ldg(w + 3 * (c + j)); w1[j] = __ldg(w + 3 * (c + j) + 1); w2[j] = __ldg(w + 3 * (c + j) + 2);
         bb[j] = __ldg(bias + c + j);
     }
-    for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / c4n; row < rows; row += (long long)gridDim.x * rpb) {
+    for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / cgn; row < rows; row += (long long)gridDim.x * rpb) {
         const int l = rows < (1ll << 32) ? (int)((unsigned)row % (unsigned)P) : (int)(row % P);
         const float xc = __ldg(x + row);
         const float xl = l > 0 ? __ldg(x + row - 1) : 0.f;
         const float xr = l < P - 1 ? __ldg(x + row + 1) : 0.f;
-        float o[4];
+        float o[G];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = lrelu(fmaf(w2[j], xr, fmaf(w1[j], xc, fmaf(w0[j], xl, bb[j]))), slope);
-        emit(make_float4(o[0], o[1], o[2], o[3]), (size_t)row, c, C, plain, split, parts, amax);
+        for (int j = 0; j < G; ++j) o[j] = lrelu(fmaf(w2[j], xr, fmaf(w1[j], xc, fmaf(w0[j], xl, bb[j]))), slope);
+        if (G == 8 && parts == POF_SPLIT_F16 && split && !plain) {
+            unsigned hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const __half2 h2 = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+                const float2 hf = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(o[2 * j] - hf.x, o[2 * j + 1] - hf.y);
+                amax = fmaxf(amax, fmaxf(fabsf(o[2 * j]), fabsf(o[2 * j + 1])));
+                hi[j] = *reinterpret_cast<const unsigned*>(&h2);
+                lo[j] = *reinterpret_cast<const unsigned*>(&l2);
+            }
+            __half* base = reinterpret_cast<__half*>(split) + (size_t)row * 2 * (size_t)C + c;
+            st_stream_f4(reinterpret_cast<float4*>(base), make_float4(__uint_as_float(hi[0]), __uint_as_float(hi[1]), __uint_as_float(hi[2]), __uint_as_float(hi[3])));
+            st_stream_f4(reinterpret_cast<float4*>(base + C), make_float4(__uint_as_float(lo[0]), __uint_as_float(lo[1]), __uint_as_float(lo[2]), __uint_as_float(lo[3])));
+        } else {
+#pragma unroll
+            for (int j = 0; j < G; j += 4)
+                emit(make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]), (size_t)row, c + j, C, plain, split, parts, amax);
+        }
     }
     if (status && !(amax <= 65504.f)) atomicCAS(status, 0, 16);
 }
@@ -208,8 +229,13 @@ int pof_conv_first_fwd(const float* cutouts, const float* weight, const float* b
                 "pof_conv_first_fwd: split_parts must be 2, 3 or POF_SPLIT_F16");
     const long long rows = M * P;
     POF_REQUIRE(256 % (C >> 2) == 0, POF_ERR_BAD_SHAPE, "pof_conv_first_fwd: C / 4 must divide 256 (got C = %d)", C);
-    const unsigned grid = stream_grid(rows * (C >> 2), 256);
-    conv_first_kernel<<<grid, 256, 0, stream>>>(cutouts, weight, bias, slope, P, C, rows, out_plain, out_split, split_parts, status);
+    if (C % 8 == 0 && 256 % (C >> 3) == 0 && split_parts == POF_SPLIT_F16 && out_split && !out_plain) {
+        const unsigned grid = stream_grid(rows * (C >> 3), 256);
+        conv_first_kernel<8><<<grid, 256, 0, stream>>>(cutouts, weight, bias, slope, P, C, rows, out_plain, out_split, split_parts, status);
+    } else {
+        const unsigned grid = stream_grid(rows * (C >> 2), 256);
+        conv_first_kernel<4><<<grid, 256, 0, stream>>>(cutouts, weight, bias, slope, P, C, rows, out_plain, out_split, split_parts, status);
+    }
     POF_CUDA(cudaGetLastError());
     return POF_OK;
 }

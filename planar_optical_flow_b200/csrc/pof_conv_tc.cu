@@ -577,9 +577,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int i = 0; i < 4; ++i) {
                         float v = acc[g * 32 + k + i];
                         if (p.pool == 2) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-                        // out_scale is a positive power of two: v * out_scale is exact, so the fused form rounds once
-                        // like the separate bias add, and it commutes with the max above
-                        v = F16 ? fmaf(v, p.out_scale, bb[i]) : v + bb[i];
+                        // out_scale > 0 (the inverse of the weights' power of two, times the truncation compensation):
+                        // the fused form rounds once, like a separate bias add, and it commutes with the max above
+                        v = fmaf(v, p.out_scale, bb[i]);
                         o[k + i] = fmaxf(v, v * p.slope);               // LeakyReLU for 0 <= slope <= 1
                     }
                 }
@@ -684,7 +684,7 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
     POF_REQUIRE(Cin >= kb && Cin % kb == 0, POF_ERR_BAD_SHAPE, "pof_conv_tc_fwd: Cin must be a multiple of %d (got %d)", kb, Cin);
     const int chain_flags = chain_channels;
     const int cg = (chain_channels & POF_CONV_TC_SINGLE_CTA) ? 1 : 2;      // high flag bits: tuning / tests only
-    chain_channels &= ~(POF_CONV_TC_SINGLE_CTA | POF_CONV_TC_STREAM_W);
+    chain_channels &= ~(POF_CONV_TC_SINGLE_CTA | POF_CONV_TC_STREAM_W | POF_CONV_TC_NO_DEBIAS);
     // binary16 chains have half as many accumulation steps per channel: 128 channels cost what 64 TF32 channels do
     // (6-7e-7 of the fp64 result per layer; cuDNN's fp32 kernels: 1-2e-6)
     if (chain_channels == 0) chain_channels = f16 ? 128 : 64;
@@ -713,6 +713,18 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
     p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.pad = pad; p.pool = pool; p.slope = slope;
     p.chain = chain_channels / kb;
     p.out_scale = out_scale;
+    if (!(chain_flags & POF_CONV_TC_NO_DEBIAS)) {
+        // The tensor core adds each MMA's 16-deep sum to the running fp32 accumulator with TRUNCATION, so a chain's
+        // partial sum comes out short: measured on every layer shape of the network (tools/conv_bias_probe.py,
+        // profiles/r2_conv_truncation_bias.txt) the mean signed relative error of the outputs is -0.9e-7 / -2.8e-7 /
+        // -6.8e-7 for chains of 4 / 8 / 16 main-product MMAs, i.e. -4.9e-8 per MMA beyond the first two, with a
+        // spread (0.75e-7 / 1.6e-7 / 3.1e-7) smaller than the mean.  A one-sided error adds up coherently through the
+        // eleven layers; the expected shortfall is therefore folded into the scale the epilogue applies anyway
+        // (fma(sum, out_scale, bias): still one rounding).  What remains is zero-mean.
+        // (TF32 parts: K = 8 per MMA, so a 64-channel chain has the 8 main MMAs of a 128-channel binary16 chain.)
+        const float n_main = (float)chain_channels / (f16 ? 16.0f : 8.0f);
+        p.out_scale = out_scale * (1.0f + 4.9e-8f * (n_main - 2.2f));
+    }
     p.bias = bias; p.out_plain = out_plain; p.out_split = out_split; p.status = status;
     {   // narrow layers: this CTA's share of ALL weight k-blocks fits next to a deep ring of activation stages, so the
         // weights are loaded once per launch instead of once per tile (they are 35-55 % of those layers' L2->SM traffic)

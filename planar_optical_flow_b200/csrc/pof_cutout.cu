@@ -673,25 +673,35 @@ __device__ __forceinline__ float div_taps(float acc, float taps_f, float taps_rc
 // with a single chunk per row there is nothing to rotate
 __device__ __forceinline__ unsigned nchunks_rot(int P, int lane) { return P >= 8 ? ((unsigned)lane >> 2) & 1u : 0u; }
 
-template <typename PhiT>
+// MULTI = false: S == 1, one CTA per sample; the scan's own span reduction happens here and the 32 rows of a group
+// leave as one bulk store.  MULTI = true: S > 1 (training samples), one CTA per scan (b, s); the oversampling factor
+// is a property of the whole sample (utils.py:308) and comes from cutout_span_kernel through `span_max`; a row's
+// reference range is the newest scan's unless `fixed` (:274-278); the rows of one scan are S*P floats apart in the
+// output, so a finished group is written with coalesced 16-byte stores, 14 lanes per 224-byte row.
+template <typename PhiT, bool MULTI>
 __global__ void __launch_bounds__(POF_SCAN_LB_THREADS, POF_SCAN_LB_BLOCKS) cutout_scan_kernel(const CutoutArgs a) {
-    extern __shared__ __align__(16) float smem_f[];          // pairs [N+1] float2 | arctangent table | ranges [N] | per-warp tiles [32][P]
+    extern __shared__ __align__(16) float smem_f[];          // pairs [N+1] float2 | arctangent table | ranges [N] | per-warp tiles [32][P] | (MULTI, !fixed) reference ranges [N]
     __shared__ double warp_span[kScanWarpsMax];
     __shared__ float warp_min[kScanWarpsMax];
     const Consts c = make_consts<PhiT>(a);
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
-    const int b = blockIdx.x;                                // S == 1: scan == sample
+    const int b = MULTI ? blockIdx.x / a.S : blockIdx.x;     // S == 1: scan == sample
+    const int sc = MULTI ? blockIdx.x - b * a.S : 0;
     const int nm1 = a.N - 1;
     const int P = a.P;
     float2* pairs = reinterpret_cast<float2*>(smem_f);
     double* atab = reinterpret_cast<double*>(smem_f + 2 * ((a.N + 2) & ~1));
     float* vals = reinterpret_cast<float*>(atab + kAtanDeg * kAtanCells);
     float* tile = vals + ((a.N + 3) & ~3) + (size_t)warp * 32 * P;
-    const float* scan = a.scans + (size_t)b * a.N;
+    const bool other_ref = MULTI && !a.fixed && sc != a.S - 1;
+    float* dvals_w = other_ref ? vals + ((a.N + 3) & ~3) + (size_t)nwarps * 32 * P : vals;      // reference ranges d of the rows
+    const float* dvals = dvals_w;
+    const float* scan = a.scans + ((size_t)b * a.S + sc) * a.N;
     const float scale = a.centered ? (float)c.inv_depth : 1.0f;
     const PhiT* phi = reinterpret_cast<const PhiT*>(a.phi);
-    const float* ha_in = a.half_alpha_in ? a.half_alpha_in + (size_t)b * a.M : nullptr;
-    float* ha_out = a.half_alpha_out ? a.half_alpha_out + (size_t)b * a.M : nullptr;
+    const size_t row0 = ((size_t)b * a.S + sc) * a.M;        // [B, S, M] half-angle tables
+    const float* ha_in = a.half_alpha_in ? a.half_alpha_in + row0 : nullptr;
+    float* ha_out = a.half_alpha_out ? a.half_alpha_out + row0 : nullptr;
 
     // ---- stage the scan as (C, D) pairs; entry N repeats beam N-1 so index N-1 + 0 reads in bounds ---
     float dmin = 3.0e38f;
@@ -702,9 +712,13 @@ __global__ void __launch_bounds__(POF_SCAN_LB_THREADS, POF_SCAN_LB_BLOCKS) cutou
         const float D = (v1 - v0) * scale;
         pairs[i] = make_float2(v0 * scale, D);
         if (i < a.N) vals[i] = r0;
-        if (a.stride == 1) dmin = fminf(dmin, fmaxf(r0, 1e-2f));     // every beam is a row (entry N repeats beam N-1)
+        if (!MULTI && a.stride == 1) dmin = fminf(dmin, fmaxf(r0, 1e-2f));     // every beam is a row (entry N repeats beam N-1)
     }
-    if (a.stride != 1)
+    if (other_ref) {
+        const float* ref = a.scans + ((size_t)b * a.S + (a.S - 1)) * a.N;
+        for (int i = tid; i < a.N; i += T) dvals_w[i] = __ldg(ref + i);
+    }
+    if (!MULTI && a.stride != 1)
         for (int m = tid; m < a.M; m += T) dmin = fminf(dmin, fmaxf(__ldg(scan + m * a.stride), 1e-2f));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
@@ -713,7 +727,10 @@ __global__ void __launch_bounds__(POF_SCAN_LB_THREADS, POF_SCAN_LB_BLOCKS) cutou
 
     // ---- the scan's maximal index span, from the rows nearest to the sensor -----------------------------
     int s_area = 0;
-    if (a.area_mode || a.s_area_out) {
+    if (MULTI) {                                             // the sample's span was reduced over all its scans by cutout_span_kernel
+        const double best = a.span_max[b];
+        if (a.area_mode && best > (double)P) s_area = (int)ceil(__ddiv_rn(best, (double)P));
+    } else if (a.area_mode || a.s_area_out) {
         dmin = warp_min[0];
         for (int w = 1; w < nwarps; ++w) dmin = fminf(dmin, warp_min[w]);
         const float near = a.half_alpha_in ? 3.0e38f : dmin * 1.001f;
@@ -754,7 +771,7 @@ __global__ void __launch_bounds__(POF_SCAN_LB_THREADS, POF_SCAN_LB_BLOCKS) cutou
     const int nchunks = P >> 2;
     const unsigned long long limit = ((unsigned long long)(unsigned)nm1 << 32) + 0x100ull;
     const double span_unit = (double)(P - 1) * c.inv_pitch;
-    float* out_b = a.out + (size_t)b * a.M * P;
+    float* out_b = a.out + (MULTI ? ((size_t)b * a.M * a.S + sc) * P : (size_t)b * a.M * P);
     const float taps_f = (float)s_area, taps_rcp = s_area > 0 ? 1.0f / (float)s_area : 0.f;
     bool store_pending = false;
 
@@ -766,7 +783,7 @@ __global__ void __launch_bounds__(POF_SCAN_LB_THREADS, POF_SCAN_LB_BLOCKS) cutou
         float lo_f = 0.f, hi_f = 0.f, pad_f = 0.f, bias = 0.f;
         if (valid) {                                          // :274-285, from the staged scan
             const int m = m0 + lane, i = m * a.stride;
-            const float d = vals[i];
+            const float d = dvals[i];
             const float ratio = __fdiv_rn(a.half_width, fmaxf(d, 1e-2f));
             const float ha = ha_in ? __ldg(ha_in + m) : atan_f32_tab(ratio, atab);             // :279
             if (ha_out) ha_out[m] = ha;
@@ -796,7 +813,7 @@ __global__ void __launch_bounds__(POF_SCAN_LB_THREADS, POF_SCAN_LB_BLOCKS) cutou
                 pad_f = fminf(fmaxf((float)a.pad, lo_f), hi_f);
             }
         }
-        if (store_pending) {                                  // the previous group's tile must have been read by the TMA
+        if (!MULTI && store_pending) {                        // the previous group's tile must have been read by the TMA
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
         }
@@ -845,16 +862,28 @@ __global__ void __launch_bounds__(POF_SCAN_LB_THREADS, POF_SCAN_LB_BLOCKS) cutou
             }
         }
 
-        // ---- the group's rows are adjacent in the output (S == 1): one bulk store ------------------------
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-            bulk_s2g(out_b + (unsigned)(m0 * P), tile, (unsigned)(rows_here * P) * 4u);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (MULTI) {
+            // ---- S > 1: the rows of this scan are S*P floats apart; 16-byte pieces, consecutive lanes along a row ----
+            __syncwarp();
+            const int q = P >> 2;                                 // pieces per row
+            for (int t = lane; t < rows_here * q; t += 32) {
+                const int r = t / q, c4 = t - r * q;
+                st_stream_f4(reinterpret_cast<float4*>(out_b + ((size_t)(m0 + r) * a.S) * P + 4 * c4),
+                             *reinterpret_cast<const float4*>(tile + r * P + 4 * c4));
+            }
+            __syncwarp();                                         // the tile is free for the next group
+        } else {
+            // ---- the group's rows are adjacent in the output (S == 1): one bulk store ------------------------
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(out_b + (unsigned)(m0 * P), tile, (unsigned)(rows_here * P) * 4u);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            store_pending = true;
         }
-        store_pending = true;
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (!MULTI && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 int scan_warps_for(int M) {
@@ -870,21 +899,22 @@ int scan_warps_for(int M) {
     return 4;
 }
 
-template <typename PhiT>
+template <typename PhiT, bool MULTI>
 bool launch_cutout_scan(const CutoutArgs& a, cudaStream_t stream, int* status) {
     const int warps = scan_warps_for(a.M);
-    const size_t smem = ((size_t)2 * ((a.N + 2) & ~1) + (size_t)((a.N + 3) & ~3) + (size_t)warps * 32 * a.P) * sizeof(float) +
+    const size_t smem = ((size_t)2 * ((a.N + 2) & ~1) + (size_t)((a.N + 3) & ~3) + (size_t)warps * 32 * a.P +
+                         (MULTI && !a.fixed ? (size_t)((a.N + 3) & ~3) : 0)) * sizeof(float) +
                         sizeof(double) * kAtanDeg * kAtanCells;
     if (smem > 110 * 1024) return false;
-    static bool attr_set[2][64] = {{false}};
+    static bool attr_set[2][2][64] = {{{false}}};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return false;
     const int which = sizeof(PhiT) == 8;
-    if (dev < 64 && !attr_set[which][dev]) {
-        if (cudaFuncSetAttribute(cutout_scan_kernel<PhiT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess) return false;
-        attr_set[which][dev] = true;
+    if (dev < 64 && !attr_set[which][MULTI][dev]) {
+        if (cudaFuncSetAttribute(cutout_scan_kernel<PhiT, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess) return false;
+        attr_set[which][MULTI][dev] = true;
     }
-    cutout_scan_kernel<PhiT><<<a.B, warps * 32, smem, stream>>>(a);
+    cutout_scan_kernel<PhiT, MULTI><<<MULTI ? a.B * a.S : a.B, warps * 32, smem, stream>>>(a);
     const cudaError_t e = cudaGetLastError();
     *status = e == cudaSuccess ? POF_OK : cuda_fail(e, "cutout_scan_kernel launch");
     return true;
@@ -973,12 +1003,16 @@ int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64, int B, i
     const bool coarse = !scale_pow2 && 1.5 * ldexp(1.0, mag_exp - 1 - 23) > 6.0e-6;             // 1.5 float32 ulps of padding_val * scale
     if (numerics == POF_CUTOUT_FAST && S == 1 && !coarse) {        // one CTA per scan: span reduction, half-angles and samples in one launch
         int status = POF_OK;
-        if (phi_is_f64 ? launch_cutout_scan<double>(a, stream, &status) : launch_cutout_scan<float>(a, stream, &status)) return status;
+        if (phi_is_f64 ? launch_cutout_scan<double, false>(a, stream, &status) : launch_cutout_scan<float, false>(a, stream, &status)) return status;
     }
     if (area_mode || s_area_out) {
         if (phi_is_f64) cutout_span_kernel<double, false><<<B, kThreads, 0, stream>>>(a);
         else cutout_span_kernel<float, false><<<B, kThreads, 0, stream>>>(a);
         POF_CUDA(cudaGetLastError());
+    }
+    if (numerics == POF_CUTOUT_FAST && S > 1 && !coarse && N < kMaxStagedPts) {      // one CTA per scan (b, s) of the training samples
+        int status = POF_OK;
+        if (phi_is_f64 ? launch_cutout_scan<double, true>(a, stream, &status) : launch_cutout_scan<float, true>(a, stream, &status)) return status;
     }
     if (numerics == POF_CUTOUT_FAST) return phi_is_f64 ? launch_cutout<double, true>(a, stream) : launch_cutout<float, true>(a, stream);
     return phi_is_f64 ? launch_cutout<double, false>(a, stream) : launch_cutout<float, false>(a, stream);

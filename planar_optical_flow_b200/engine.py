@@ -157,7 +157,7 @@ class _ChannelsLastBackbone:
                        status=self.status)
         if plain and plain_out is not None:
             plain_out.view(p.shape).copy_(p)
-            p = plain_out
+            p = plain_out.view(p.shape)
         return p, (s if self.split else p)
 
     @property

@@ -106,7 +106,12 @@ def test_streaming_engine_jrdb_shape_across_chunks():
     precision and chunking) with B = 130 sequences, which spans two backbone chunks, over 4 steps.  Three sequences
     (first, the one either side of the chunk boundary, last) are replayed through the oracle's reference loop in
     float32 AND in float64: the engine must be within 1e-5 of the float32 oracle, or - where the float32 oracle itself
-    is further than that from the float64 truth - at least as close to the truth as the oracle is."""
+    is further than that from the float64 truth - at least as close to the truth as the oracle is.
+    The network is compared on identical inputs (the oracle is fed the cutout kernel's output for the same ranges; the
+    kernel's own parity is tests/test_gpu_parity.py's subject); the whole chain from the oracle's NumPy cutouts is
+    checked too for every sequence whose device cutouts have matched NumPy's at every sample so far (a <= 2-ulp
+    half-angle difference can flip the nearest beam of an area-resampled sample, which changes that sample by up to the
+    clip range and everything downstream of it)."""
     from planar_optical_flow_b200.engine import StreamingDetector
 
     B, steps = 130, 4
@@ -126,12 +131,18 @@ def test_streaming_engine_jrdb_shape_across_chunks():
     sd64 = f64_state_dict(sd)
     tmpl32 = {k: None for k in picks}
     tmpl64 = {k: None for k in picks}
+    tmpl_np = {k: None for k in picks}
+    same_input, n_e2e = {k: True for k in picks}, 0
     report = {}
+    phi_d = torch.from_numpy(phi).cuda()
     for t in range(steps):
         host = det.step(scans[t])
-        for k in picks:
-            ct = ocut.scans_to_cutout(scans[t, k][None], phi, **CFG)
+        ct_dev = ops.cutout(torch.from_numpy(scans[t, picks]).cuda().unsqueeze(1), phi_d, **CFG).cpu().numpy()     # what the engine saw
+        for j, k in enumerate(picks):
+            ct = ct_dev[j]
             with torch.no_grad():
+                ct_np = ocut.scans_to_cutout(scans[t, k][None], phi, **CFG)
+                c_np, r_np, tmpl_np[k], _ = omodel.spatial_drow_stream(torch.from_numpy(ct_np)[None], sd, 0.5, 11, tmpl_np[k])
                 c32, r32, tmpl32[k], f32 = omodel.spatial_drow_stream(torch.from_numpy(ct)[None], sd, 0.5, 11, tmpl32[k])
                 c64, r64, tmpl64[k], f64 = omodel.spatial_drow_stream(torch.from_numpy(ct)[None].double(), sd64, 0.5, 11, tmpl64[k])
             got = {"scores": det._last["pred_cls"][k].cpu().numpy().reshape(-1, 1),
@@ -142,6 +153,13 @@ def test_streaming_engine_jrdb_shape_across_chunks():
                       "memory": tmpl32[k][0].numpy()}
             want64 = {"scores": torch.sigmoid(c64[0]).numpy(), "votes": r64[0].numpy(), "similarities": f64[0].numpy(),
                       "memory": tmpl64[k][0].numpy()}
+            same_input[k] = same_input[k] and float(np.abs(ct - ct_np).max()) <= REL_TOL
+            if same_input[k]:        # no nearest-beam flip from a 1-ulp half-angle so far: the whole chain from NumPy's cutouts agrees too
+                n_e2e += 1
+                for name, w_np in (("scores", torch.sigmoid(c_np[0]).numpy()), ("votes", r_np[0].numpy()), ("memory", tmpl_np[k][0].numpy())):
+                    e = rel_err(got[name], w_np)
+                    assert e <= 2 * REL_TOL or rel_err(got[name], want64[name]) <= max(REL_TOL, rel_err(w_np, want64[name])), \
+                        "end-to-end %s step %d seq %d: %.3g" % (name, t, k, e)
             for name in got:
                 e_ref = rel_err(got[name], want32[name])              # engine vs the reference's own float32 path
                 e_true = rel_err(got[name], want64[name])             # engine vs float64 truth
@@ -159,4 +177,5 @@ def test_streaming_engine_jrdb_shape_across_chunks():
             if np.array_equal(mine["order"], want["order"]) and want["margin"] > 1e-4:
                 assert np.array_equal(mask, want["instance_mask"])
     det.check()
-    print("engine parity at the bench shape (engine-vs-oracle32, engine-vs-fp64, oracle32-vs-fp64):", report)
+    print("engine parity at the bench shape (engine-vs-oracle32, engine-vs-fp64, oracle32-vs-fp64):", report,
+          "; end-to-end checks on identical cutouts: %d of %d" % (n_e2e, steps * len(picks)))

@@ -16,7 +16,9 @@ from planar_optical_flow_b200.engine import _ChannelsLastBackbone        # noqa:
 
 dev = torch.device("cuda")
 holder = _ChannelsLastBackbone.__new__(_ChannelsLastBackbone)
-holder.f16 = True
+F16 = os.environ.get("POF_PROBE_TF32", "0") != "1"          # POF_PROBE_TF32=1: TF32 parts (kind::tf32, K = 8 per MMA)
+holder.f16 = F16
+print("operand parts:", "binary16 (kind::f16)" if F16 else "TF32 (kind::tf32)")
 for LA, Cin, Cout in ((56, 64, 64), (28, 128, 128), (14, 256, 256), (14, 256, 512), (7, 512, 256)):
     g = torch.Generator(device="cuda").manual_seed(1)
     M = 2048
@@ -24,16 +26,16 @@ for LA, Cin, Cout in ((56, 64, 64), (28, 128, 128), (14, 256, 256), (14, 256, 51
     x = torch.where(x > 0, x, 0.1 * x)                                   # post-LeakyReLU statistics
     w = torch.randn(Cout, Cin, 3, generator=g, device=dev) * (2.0 / (Cin * 3)) ** 0.5
     ws, out_scale = holder._tc_weight(w)
-    _, a = ops.act(x.view(M * LA, Cin), None, pool=1, slope=1.0, want_plain=False, want_split=True, parts=ops.SPLIT_F16)
+    _, a = ops.act(x.view(M * LA, Cin), None, pool=1, slope=1.0, want_plain=False, want_split=True, parts=ops.SPLIT_F16 if F16 else 2)
     want = F.conv1d(x.permute(0, 2, 1).double(), w.double(), None, padding=1).permute(0, 2, 1).reshape(-1, Cout)
-    for chain in (64, 128, 256):
+    for chain, flag in ((64, 0x40000), (128, 0x40000), (256, 0x40000), (64, 0), (128, 0)):      # 0x40000 = POF_CONV_TC_NO_DEBIAS
         if chain > Cin:
             continue
         plain, _ = ops.conv_tc(a, ws, None, M, LA, LA, 3, 1, pool=1, slope=1.0, want_plain=True, want_split=False,
-                               out_scale=out_scale, chain_channels=chain)
+                               out_scale=out_scale, chain_channels=chain | flag)
         err = plain.double() - want
         scale = want.abs().max()
         big = want.abs() > 0.25 * scale                                   # outputs with a meaningful magnitude
         signed = (err * want.sign())[big] / want.abs()[big]
-        print("LA=%-2d %3d->%3d chain=%-3d  max|err|/max|out| %.2e   mean signed rel err of large outputs %+.2e  (std %.2e)  rms rel %.2e" % (
-            LA, Cin, Cout, chain, float(err.abs().max() / scale), float(signed.mean()), float(signed.std()), float((err[big] / want[big]).pow(2).mean().sqrt())))
+        print("LA=%-2d %3d->%3d chain=%-3d %s max|err|/max|out| %.2e   mean signed rel err of large outputs %+.2e  (std %.2e)  rms rel %.2e" % (
+            LA, Cin, Cout, chain, "raw     " if flag else "debiased", float(err.abs().max() / scale), float(signed.mean()), float(signed.std()), float((err[big] / want[big]).pow(2).mean().sqrt())))
