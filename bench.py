@@ -302,6 +302,17 @@ def measured_hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of a hot-path kernel, from the `ncu --set full` capture of the
+    CURRENT build summarised in profiles/r2_ncu_traffic.json (tools/ncu_traffic.py); None when that launch shape was not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")) as f:
+            e = json.load(f).get(key)
+        return None if e is None else {"bytes": e["traffic_bytes"], "source": "profiles/r2_ncu_traffic.json:%s (%s)" % (key, e["report"])}
+    except Exception:      # noqa: BLE001
+        return None
+
+
 def measured_tensor_peak():
     """Dense bf16 TFLOP/s sustained inside a long step (MEASURED_PEAKS.json), else the recipe's fallback."""
     try:
@@ -477,7 +488,10 @@ def run_ours(args):
         conv_roof = {"kernel": "conv_tc_kernel<256,2,%s> (tcgen05 3x%s split convolution, SM pairs; layers with >= 256 output channels)"
                                % (("true", "F16") if f16 else ("false", "TF32")),
                      "bound": "tensor", "achieved": ach, "peak": pipe_peak, "unit": "TFLOP/s", "frac": ach / pipe_peak,
-                     "traffic": None, "peak_source": tsrc + (" (kind::f16 runs at the bf16 rate)" if f16 else " / 2 (TF32 runs at half the bf16 rate)"),
+                     "traffic": (ncu_traffic("conv_tc_256_layer_256to512_M%d" % (chunk_seqs * N)) or {}).get("bytes"),
+                     "traffic_note": "ncu dram bytes of the 256->512 layer's launch at this launch size (the largest of the BN = 256 launches; "
+                                     "algorithmic: 1.00 GB of split activations in, 0.50 GB out + 0.50 GB of weights and re-reads served by L2)",
+                     "peak_source": tsrc + (" (kind::f16 runs at the bf16 rate)" if f16 else " / 2 (TF32 runs at half the bf16 rate)"),
                      "avg_launch_ms": t_ms / len(conv_ms["conv256"]), "launches_timed": len(conv_ms["conv256"]),
                      "algorithmic_flops_per_launch": fl / len(conv_ms["conv256"]),
                      "note": "achieved = fp32 convolution FLOPs (2*rows*Cin*Cout*taps) / CUDA-event time; the kernel issues THREE "
@@ -509,15 +523,23 @@ def run_ours(args):
         "parity_spot": spot,
         "roofline": conv_roof,
         "roofline_gate": {"kernel": "gate_stream_kernel<11,0> (attention memory update)", "bound": "hbm",
-                     "achieved": gate_gbs, "peak": peak, "unit": "GB/s", "frac": gate_gbs / peak, "traffic": None,
+                     "achieved": gate_gbs, "peak": peak, "unit": "GB/s", "frac": gate_gbs / peak,
+                     "traffic": (ncu_traffic("gate_stream_split_B%d" % chunk_seqs) or {}).get("bytes"),
                      "peak_source": peak_src, "avg_launch_ms": gate_avg_ms, "launches_timed": len(gate_ms),
                      "algorithmic_bytes_per_launch": gate_bytes_per_seq * seqs_per_launch,
-                     "frac_of_nominal_8TBs": gate_gbs / 8000.0},
+                     "frac_of_nominal_8TBs": gate_gbs / 8000.0,
+                     "with_operand_split": {
+                         "bytes_per_launch": (gate_bytes_per_seq + (N * 3584 * 4 if args.precision == "fp32" else 0)) * seqs_per_launch,
+                         "achieved": (gate_bytes_per_seq + (N * 3584 * 4 if args.precision == "fp32" else 0)) * seqs_per_launch / (gate_avg_ms * 1e-3) / 1e9,
+                         "frac": (gate_bytes_per_seq + (N * 3584 * 4 if args.precision == "fp32" else 0)) * seqs_per_launch / (gate_avg_ms * 1e-3) / 1e9 / peak,
+                         "note": "in the engine's default precision the same launch also writes the new memory as the float16 [hi | lo] operand of the "
+                                 "convolutions that consume it (N*3584*4 B per sequence-step on top of SURVEY 8d's N*44,076 B; it replaced a separate "
+                                 "read-and-split pass): `achieved` / `frac` above count the SURVEY bytes only"}},
         "roofline_cutout": {"kernel": "cutout_scan_kernel (one CTA per scan, FAST numerics), cutout-only sweep at batch %d "
                                       "(BASELINE.json configs[1])" % cut_sweep["batch"],
                             "bound": "hbm", "achieved": sweep_gbs["fast"], "peak": peak, "unit": "GB/s",
                             "frac": sweep_gbs["fast"] / peak, "avg_launch_ms": cut_sweep["fast"],
-                            "traffic": 961529088,    # dram read + write of one launch, profiles/r1_cutout_scan_kernel_ncu.txt
+                            "traffic": (ncu_traffic("cutout_scan_B%d" % cut_sweep["batch"]) or {}).get("bytes"),
                             "algorithmic_bytes_per_launch": sweep_bytes,
                             "exact_arithmetic": {"achieved": sweep_gbs["exact"], "frac": sweep_gbs["exact"] / peak,
                                                  "avg_launch_ms": cut_sweep["exact"]},

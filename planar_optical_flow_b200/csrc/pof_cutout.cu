@@ -170,6 +170,55 @@ __global__ void __launch_bounds__(kThreads) cutout_span_kernel(const CutoutArgs 
     }
 }
 
+// The same reduction with one CTA per SCAN (b, s) and an atomic max per sample (non-negative doubles order like
+// their bit patterns; `span_max` is zeroed first): B*S CTAs instead of B, and - the half-angle being a monotone
+// function of the range - only the rows within 0.1 % of the scan's smallest reference range are evaluated (every other
+// row has a strictly smaller float32 half-angle, hence a smaller span), as in cutout_scan_kernel.  Used when the caller
+// wants neither `s_area_out` nor the half-angle tables from this pass and supplies no half-angles of its own.
+template <typename PhiT>
+__global__ void __launch_bounds__(kThreads) cutout_span_scan_kernel(const CutoutArgs a) {
+    __shared__ double warp_max[kThreads / 32];
+    __shared__ float warp_min[kThreads / 32];
+    const Consts c = make_consts<PhiT>(a);
+    const int b = blockIdx.x / a.S, sc = blockIdx.x - b * a.S;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* ref = a.scans + ((size_t)b * a.S + (a.fixed ? sc : a.S - 1)) * a.N;
+    const PhiT* phi = reinterpret_cast<const PhiT*>(a.phi);
+    float dmin = 3.0e38f;
+    for (int m = threadIdx.x; m < a.M; m += kThreads) dmin = fminf(dmin, fmaxf(__ldg(ref + m * a.stride), 1e-2f));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    if (lane == 0) warp_min[warp] = dmin;
+    __syncthreads();
+    dmin = warp_min[0];
+    for (int w = 1; w < kThreads / 32; ++w) dmin = fminf(dmin, warp_min[w]);
+    const float near = dmin * 1.001f;
+    double best = 0.0;
+    for (int m = threadIdx.x; m < a.M; m += kThreads) {
+        const int i = m * a.stride;
+        const float dc = fmaxf(__ldg(ref + i), 1e-2f);
+        if (dc <= near) {
+            const float ha = atan_f32(__fdiv_rn(a.half_width, dc));
+            const float step = __fdiv_rn(2.0f * ha, (float)(a.P - 1));
+            const double start = (double)(phi[i] - (PhiT)ha);
+            const double span = __dsub_rn(sample_index(start, step, a.P - 1, c), sample_index(start, step, 0, c));
+            if (span > best) best = span;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, best, o);
+        if (other > best) best = other;
+    }
+    if (lane == 0) warp_max[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kThreads / 32; ++w)
+            if (warp_max[w] > best) best = warp_max[w];
+        if (best > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(a.span_max + b), (unsigned long long)__double_as_longlong(best));
+    }
+}
+
 // ---- per-sample arithmetic --------------------------------------------------------------------
 // EXACT: the reference's roundings, operation by operation.  `in_scan` (:289) is evaluated by the
 // caller from the same idx.
@@ -1006,8 +1055,15 @@ int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64, int B, i
         if (phi_is_f64 ? launch_cutout_scan<double, false>(a, stream, &status) : launch_cutout_scan<float, false>(a, stream, &status)) return status;
     }
     if (area_mode || s_area_out) {
-        if (phi_is_f64) cutout_span_kernel<double, false><<<B, kThreads, 0, stream>>>(a);
-        else cutout_span_kernel<float, false><<<B, kThreads, 0, stream>>>(a);
+        if (!s_area_out && !half_alpha_in && !half_alpha_out) {       // one CTA per scan, nearest rows only, atomic max per sample
+            POF_CUDA(cudaMemsetAsync(a.span_max, 0, (size_t)B * sizeof(double), stream));
+            if (phi_is_f64) cutout_span_scan_kernel<double><<<B * S, kThreads, 0, stream>>>(a);
+            else cutout_span_scan_kernel<float><<<B * S, kThreads, 0, stream>>>(a);
+        } else if (phi_is_f64) {
+            cutout_span_kernel<double, false><<<B, kThreads, 0, stream>>>(a);
+        } else {
+            cutout_span_kernel<float, false><<<B, kThreads, 0, stream>>>(a);
+        }
         POF_CUDA(cudaGetLastError());
     }
     if (numerics == POF_CUTOUT_FAST && S > 1 && !coarse && N < kMaxStagedPts) {      // one CTA per scan (b, s) of the training samples

@@ -782,3 +782,23 @@ def test_cuda_graph_replay_equals_eager_steps():
         assert torch.equal(eager._last["pred_reg"], graph._last["pred_reg"])
     assert len(graph._graphs) == 2 and graph.kernel_launches == eager.kernel_launches
     graph.check()
+
+
+@pytest.mark.parametrize("fast", [False, True])
+@pytest.mark.parametrize("fixed", [True, False])
+def test_cutout_span_reduction_paths_agree(fast, fixed):
+    """The per-scan span reduction (nearest rows only, atomic max per sample; what a plain call uses) and the per-sample
+    one that also reports `s_area` give bit-equal cutouts: structured, adversarial and edge ranges, S = 1 and S = 4."""
+    phi = synth.phi_for("jrdb")
+    n = len(phi)
+    kw = dict(CFG, fixed=fixed)
+    phi_d = torch.from_numpy(phi).cuda()
+    for S in (1, 4):
+        rows = [synth.structured_sequence(S, n, seed=3, phi=phi), synth.adversarial_scans(S, n, seed=4),
+                np.full((S, n), 0.004, np.float32), np.full((S, n), 29.99, np.float32)]
+        rows[2][:, ::7] = 3.0
+        scans = torch.from_numpy(np.stack(rows)).cuda()                     # [B = 4, S, N]
+        plain = ops.cutout(scans, phi_d, fast=fast, **kw)
+        full, s_area = ops.cutout(scans, phi_d, fast=fast, return_s_area=True, **kw)
+        assert torch.equal(plain, full), (S, int((plain != full).sum()))
+        assert int(s_area.max()) >= 4 and int(s_area.min()) >= 0

@@ -27,7 +27,7 @@ for path in variants + [_lib.LIB_PATH]:
     fn.restype = ctypes.c_int
     fn.argtypes = _lib.SIGNATURES["pof_spaam_gate_fwd"][1]
     args = [ctypes.c_void_p(v.data_ptr()) for v in (x, t, ex, et)] + [B, N, CL, E, W, 0.5,
-            ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ff.data_ptr()), None, None]
+            ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ff.data_ptr()), None, None, 0, None, None]
     for _ in range(3):
         rc = fn(*args)
     torch.cuda.synchronize()
