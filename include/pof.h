@@ -254,6 +254,25 @@ POF_API int pof_conv_tc_f16_fwd(const void* a_split, const void* w_split, const 
                                 int pool, float slope, float out_scale, float* out_plain, void* out_split,
                                 int* status, int chain_channels, void* stream);
 
+/*    Training-mode BatchNorm + LeakyReLU (+ max-pool over row pairs) of one conv layer (dr_spaam.py:8-12 `_conv`, :81-97
+ *    max_pool1d(2)) on channels-last activations y [rows, C] (the convolution's output), as one operator with its own
+ *    backward - what the training step of bin/train_dr_spaam.py spends most of its time on (profiles/r2_train_launch_summary.txt).
+ *      pof_bn_act_stats  sums [2, C] double <- per-channel sum and sum of squares of y (zeroed by the call)
+ *      pof_bn_act_fwd    z [rows / pool, C] = max over `pool` consecutive rows of lrelu((y - mean) * invstd * gamma + beta),
+ *                        batch statistics from `sums` (biased variance); writes mean / invstd [C] (saved for the backward) and,
+ *                        when given, updates running_mean / running_var with `momentum` (unbiased variance), as
+ *                        torch.nn.functional.batch_norm(training=True) does
+ *      pof_bn_act_bwd    dz [rows / pool, C] -> dx [rows, C], dgamma [C], dbeta [C]; recomputes the pre-activations from y
+ *                        (nothing else is saved); a pooled pair's gradient goes to its first maximum; `sums` [2, C] double scratch
+ *    C % 4 == 0 with C / 4 dividing 256; pool in {1, 2}.                                                                   */
+POF_API int pof_bn_act_stats(const float* y, long long rows, int C, double* sums, void* stream);
+POF_API int pof_bn_act_fwd(const float* y, const double* sums, const float* gamma, const float* beta,
+                           long long rows, int C, int pool, float eps, float slope, float momentum,
+                           float* z, float* mean, float* invstd, float* running_mean, float* running_var, void* stream);
+POF_API int pof_bn_act_bwd(const float* y, const float* dz, const float* mean, const float* invstd,
+                           const float* gamma, const float* beta, long long rows, int C, int pool, float slope,
+                           double* sums, float* dx, float* dgamma, float* dbeta, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * 5. Windowed patch correlation of the scan-pair flow prototype
  *    replaces Prototype._fusion, src/depracted/model/prototype.py:118-156 (dense [N, N] patch

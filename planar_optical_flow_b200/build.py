@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_PATH = os.path.join(PKG_DIR, "libpof.so")
 
-SOURCES = ["pof_api.cu", "pof_cutout.cu", "pof_gate.cu", "pof_nms.cu", "pof_backbone.cu", "pof_conv_tc.cu", "pof_corr.cu", "pof_cutout_legacy.cu"]
+SOURCES = ["pof_api.cu", "pof_cutout.cu", "pof_gate.cu", "pof_nms.cu", "pof_backbone.cu", "pof_conv_tc.cu", "pof_corr.cu", "pof_cutout_legacy.cu", "pof_bnact.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -37,16 +37,28 @@ class _ConvBnAct(nn.Sequential):
     its per-channel NCHW batch-norm kernels, which took 45 % + 16 % of the training step (profiles/r1_train_step.txt).
     """
 
-    def forward(self, x):
+    fused = True        # batch-norm + LeakyReLU (+ pool) of the training branch as libpof's one operator (False: cuDNN + PyTorch kernels)
+
+    def forward(self, x, pool=1):
+        """`pool` = 2 applies the block's max_pool1d(2) (dr_spaam.py:81) here, so it can be fused with the activation."""
         if x.dim() != 4:
-            return super().forward(x)
+            y = super().forward(x)
+            return F.max_pool1d(y, kernel_size=pool) if pool > 1 else y
+        y = self._forward_4d(x, pool)
+        return y
+
+    def _forward_4d(self, x, pool):
         conv, bn = self[0], self[1]
         w4, pad = conv.weight.unsqueeze(2), (0, conv.padding[0])
         track = bn.track_running_stats
+
+        def pooled(t):
+            return F.max_pool2d(t, kernel_size=(1, pool)) if pool > 1 else t
+
         if not (bn.training or not track):                      # eval: running statistics
             y = F.batch_norm(F.conv2d(x, w4, conv.bias, padding=pad), bn.running_mean, bn.running_var, bn.weight, bn.bias,
                              False, 0.0, bn.eps)
-            return F.leaky_relu_(y, _SLOPE)
+            return pooled(F.leaky_relu_(y, _SLOPE))
         # Batch statistics: the convolution's bias cancels in (y + b) - mean(y + b), so it is left out of the forward
         # pass (no bias-add pass, and no reduction of the output gradient for a bias gradient that is zero in exact
         # arithmetic - 27 % of the step).  It still belongs to the running mean, and it still gets its (zero) gradient.
@@ -59,9 +71,15 @@ class _ConvBnAct(nn.Sequential):
             # the same layer in this step (the gate embeds every scan) saved the buffer, and a version bump would make
             # autograd refuse their backward although batch-statistics backward never reads it.
             bn.running_mean.data.add_(conv.bias.detach(), alpha=factor / (1.0 - factor))
-        y = F.batch_norm(F.conv2d(x, w4, None if skip_bias else conv.bias, padding=pad), bn.running_mean if track else None,
-                         bn.running_var if track else None, bn.weight, bn.bias, True, factor, bn.eps)
-        y = F.leaky_relu_(y, _SLOPE)
+        y = F.conv2d(x, w4, None if skip_bias else conv.bias, padding=pad)
+        c = y.shape[1]
+        if self.fused and y.is_cuda and bn.affine and c % 4 == 0 and 256 % (c // 4) == 0 and (pool == 1 or y.shape[3] % 2 == 0):
+            y = ops.bn_act_pool(y, bn.weight, bn.bias, bn.running_mean if track else None, bn.running_var if track else None,
+                                momentum=factor, eps=bn.eps, slope=_SLOPE, pool=pool)
+        else:
+            y = F.batch_norm(y, bn.running_mean if track else None, bn.running_var if track else None, bn.weight, bn.bias,
+                             True, factor, bn.eps)
+            y = pooled(F.leaky_relu_(y, _SLOPE))
         return _ZeroGradOperand.apply(y, conv.bias) if skip_bias else y
 
 
@@ -135,17 +153,15 @@ class DROW(nn.Module):
         b, n, p = scan_cutouts.shape
         y = scan_cutouts.reshape(b * n, 1, 1, p).contiguous(memory_format=torch.channels_last)
         for blk in (self.conv_block_1, self.conv_block_2):
-            for layer in blk:
-                y = layer(y)
-            y = F.max_pool2d(y, kernel_size=(1, 2))
+            for k, layer in enumerate(blk):
+                y = layer(y, pool=2 if k == len(blk) - 1 else 1)          # the block's max_pool1d(2), fused into its last layer
         return y
 
     def _votes_cl(self, t, b, n):
         """[B*N, 256, 1, L] channels-last fused features -> ([B, N, C], [B, N, 2])."""
         y = t
-        for layer in self.conv_block_3:
-            y = layer(y)
-        y = F.max_pool2d(y, kernel_size=(1, 2))
+        for k, layer in enumerate(self.conv_block_3):
+            y = layer(y, pool=2 if k == len(self.conv_block_3) - 1 else 1)
         for layer in self.conv_block_4:
             y = layer(y)
         y = y.mean(dim=3)                                      # avg_pool1d over the whole length: [M, 128, 1]

@@ -328,6 +328,62 @@ def head(y, bias, M, L, w_head, b_head, n_sigmoid, slope=0.1, out=None, out_rest
     return out if out_rest is None else (out, out_rest)
 
 
+# --------------------------------------------------------------------------- training: batch-norm + LeakyReLU (+ pool)
+class _BnActPoolFn(torch.autograd.Function):
+    """y [M, C, 1, L] (channels-last memory: rows = M * L, C contiguous) -> [M, C, 1, L / pool]."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, running_mean, running_var, momentum, eps, slope, pool):
+        require_cuda_tensor(gamma, "gamma", torch.float32)
+        require_cuda_tensor(beta, "beta", torch.float32)
+        if y.dim() != 4 or y.shape[2] != 1 or y.dtype != torch.float32 or not y.is_cuda:
+            raise ValueError("bn_act_pool takes float32 CUDA activations [M, C, 1, L]")
+        if not y.is_contiguous(memory_format=torch.channels_last):
+            y = y.contiguous(memory_format=torch.channels_last)
+        M, C, _, Lr = y.shape
+        if pool not in (1, 2) or Lr % pool:
+            raise ValueError("pool must be 1, or 2 with an even length (got pool=%d, L=%d)" % (pool, Lr))
+        rows = M * Lr
+        dev = y.device
+        with torch.cuda.device(dev):
+            sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
+            z = torch.empty((M, C, 1, Lr // pool), dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last)
+            mean = torch.empty(C, dtype=torch.float32, device=dev)
+            invstd = torch.empty(C, dtype=torch.float32, device=dev)
+            L = _lib.lib()
+            stream = current_stream_ptr(dev)
+            check(L.pof_bn_act_stats(_ptr(y), rows, C, _ptr(sums), stream), "pof_bn_act_stats")
+            check(L.pof_bn_act_fwd(_ptr(y), _ptr(sums), _ptr(gamma), _ptr(beta), rows, C, int(pool), float(eps), float(slope),
+                                   float(momentum), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(running_mean), _ptr(running_var), stream),
+                  "pof_bn_act_fwd")
+        ctx.save_for_backward(y, gamma, beta, mean, invstd)
+        ctx.cfg = (float(slope), int(pool))
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        y, gamma, beta, mean, invstd = ctx.saved_tensors
+        slope, pool = ctx.cfg
+        M, C, _, Lr = y.shape
+        dev = y.device
+        dz = dz.contiguous(memory_format=torch.channels_last)
+        with torch.cuda.device(dev):
+            dx = torch.empty_like(y)                       # channels-last like y
+            dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+            dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+            sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
+            check(_lib.lib().pof_bn_act_bwd(_ptr(y), _ptr(dz), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), M * Lr, C, pool,
+                                            slope, _ptr(sums), _ptr(dx), _ptr(dgamma), _ptr(dbeta), current_stream_ptr(dev)),
+                  "pof_bn_act_bwd")
+        return dx, dgamma, dbeta, None, None, None, None, None, None
+
+
+def bn_act_pool(y, gamma, beta, running_mean=None, running_var=None, momentum=0.1, eps=1e-5, slope=0.1, pool=1):
+    """Training-mode BatchNorm (batch statistics, running statistics updated in place) + LeakyReLU + max-pool over `pool`
+    consecutive positions, as one differentiable operator on channels-last activations y [M, C, 1, L] (csrc/pof_bnact.cu)."""
+    return _BnActPoolFn.apply(y, gamma, beta, running_mean, running_var, momentum, eps, slope, pool)
+
+
 # --------------------------------------------------------------------------- patch correlation (prototype)
 class _PatchCorrFn(torch.autograd.Function):
     @staticmethod

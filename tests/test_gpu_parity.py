@@ -802,3 +802,68 @@ def test_cutout_span_reduction_paths_agree(fast, fixed):
         full, s_area = ops.cutout(scans, phi_d, fast=fast, return_s_area=True, **kw)
         assert torch.equal(plain, full), (S, int((plain != full).sum()))
         assert int(s_area.max()) >= 4 and int(s_area.min()) >= 0
+
+
+@pytest.mark.parametrize("M,L,C,pool", [(37, 56, 64, 1), (37, 56, 128, 2), (11, 28, 256, 2), (9, 14, 512, 2), (300, 1, 128, 1)])
+def test_bn_act_pool_forward_backward_matches_float64_autograd(M, L, C, pool):
+    """libpof's training-mode BatchNorm + LeakyReLU (+ pool) operator against torch autograd in float64."""
+    g = torch.Generator().manual_seed(M + C)
+    y = (torch.randn(M, C, 1, L, generator=g) * 1.5 + 0.3)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
+    rm, rv = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    w = torch.randn(M, C, 1, L // pool, generator=g)
+    # float64 reference
+    y64 = y.double().requires_grad_(True)
+    g64, b64 = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rm64, rv64 = rm.double().clone(), rv.double().clone()
+    z64 = F.leaky_relu(F.batch_norm(y64, rm64, rv64, g64, b64, True, 0.1, 1e-5), 0.1)
+    if pool == 2:
+        z64 = F.max_pool2d(z64, kernel_size=(1, 2))
+    (z64 * w.double()).sum().backward()
+    # the operator
+    yc = y.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    gc, bc = gamma.cuda().requires_grad_(True), beta.cuda().requires_grad_(True)
+    rmc, rvc = rm.cuda().clone(), rv.cuda().clone()
+    z = ops.bn_act_pool(yc, gc, bc, rmc, rvc, momentum=0.1, eps=1e-5, slope=0.1, pool=pool)
+    assert z.is_contiguous(memory_format=torch.channels_last) and tuple(z.shape) == (M, C, 1, L // pool)
+    (z * w.cuda()).sum().backward()
+    assert_rel(z.detach().cpu(), z64.detach(), tol=2e-6, what="forward")
+    assert_rel(rmc.cpu(), rm64, tol=2e-6, what="running mean")
+    assert_rel(rvc.cpu(), rv64, tol=2e-6, what="running variance")
+    assert_rel(yc.grad.cpu(), y64.grad, tol=5e-6, what="grad input")
+    assert_rel(gc.grad.cpu(), g64.grad, tol=5e-6, what="grad gamma")
+    assert_rel(bc.grad.cpu(), b64.grad, tol=5e-6, what="grad beta")
+
+
+def test_fused_training_layers_equal_the_cudnn_path():
+    """SpatialDROW's training branch with the fused operator vs the same module on cuDNN batch-norm + PyTorch's LeakyReLU
+    and max-pool kernels: outputs, running statistics and every gradient."""
+    from planar_optical_flow_b200.model.dr_spaam import _ConvBnAct
+
+    torch.manual_seed(3)
+    sd = omodel.randomize_bn_stats(omodel.init_state_dict(56, True, seed=12))
+    x = torch.randn(2, 23, 3, 56).cuda()
+    res = {}
+    try:
+        for fused in (True, False):
+            _ConvBnAct.fused = fused
+            m = _product_model(sd).train()
+            cls, reg, ff = m(x)
+            (cls.square().mean() + reg.square().mean() + 1e-3 * ff.square().mean()).backward()
+            res[fused] = (cls.detach(), reg.detach(), ff.detach(), {k: p.grad.clone() for k, p in m.named_parameters()},
+                          {k: b.clone() for k, b in m.named_buffers() if "running" in k})
+    finally:
+        _ConvBnAct.fused = True
+    a, b = res[True], res[False]
+    for i, name in enumerate(("cls", "reg", "feat_fused")):
+        assert_rel(a[i].cpu(), b[i].cpu(), tol=1e-4, what=name)          # two TF32-free fp32 paths through 11 train-mode BN layers
+    for k in b[4]:
+        assert_rel(a[4][k].cpu(), b[4][k].cpu(), tol=1e-4, what=k)
+    for k in b[3]:
+        if k.endswith(".0.bias") or k == "gate.conv.0.bias":
+            continue                                                      # zero in exact arithmetic (a bias in front of train-mode BN)
+        # where the two values of a pooled pair agree to the last bits, the two paths may route the gradient to different
+        # rows (and a pre-activation next to zero may take the other slope): isolated elements differ, the direction agrees
+        ga, gb = a[3][k].flatten().double().cpu(), b[3][k].flatten().double().cpu()
+        cos = float((ga @ gb) / (ga.norm() * gb.norm() + 1e-300))
+        assert cos > 0.9999 and rel_err(ga, gb) < 0.2, (k, cos, rel_err(ga, gb))
