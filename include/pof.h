@@ -264,13 +264,21 @@ POF_API int pof_conv_tc_f16_fwd(const void* a_split, const void* w_split, const 
  *                        torch.nn.functional.batch_norm(training=True) does
  *      pof_bn_act_bwd    dz [rows / pool, C] -> dx [rows, C], dgamma [C], dbeta [C]; recomputes the pre-activations from y
  *                        (nothing else is saved); a pooled pair's gradient goes to its first maximum; `sums` [2, C] double scratch
- *    C % 4 == 0 with C / 4 dividing 256; pool in {1, 2}.                                                                   */
-POF_API int pof_bn_act_stats(const float* y, long long rows, int C, double* sums, void* stream);
+ *    `groups`: the rows are G consecutive blocks of rows / G rows (the S scans of a training sample, whose layers the
+ *    reference runs as S separate batch_norm calls, dr_spaam.py:264-273); each block is normalised with ITS OWN batch
+ *    statistics, the running statistics receive one update per block in block order, gamma / beta gradients add up.
+ *    sums [G, 2, C], mean / invstd [G, C].  C % 4 == 0 with C / 4 dividing 256; pool in {1, 2}.                              */
+POF_API int pof_bn_act_stats(const float* y, long long rows, int C, int groups, double* sums, void* stream);
+/*    pof_conv_first_wgrad   weight gradient of the first layer, Conv1d(1 -> C, k = 3, p = 1) (dr_spaam.py:49), from
+ *                        dy [M * P, C] (channels last) and the cutouts [M, P]: dw [C, 3]; `sums` [3, C] double scratch.
+ *                        (The forward of that layer in training is pof_conv_first_fwd with slope = 1 and a zero bias.)      */
+POF_API int pof_conv_first_wgrad(const float* dy, const float* cutouts, long long M, int P, int C,
+                                 double* sums, float* dw, void* stream);
 POF_API int pof_bn_act_fwd(const float* y, const double* sums, const float* gamma, const float* beta,
-                           long long rows, int C, int pool, float eps, float slope, float momentum,
+                           long long rows, int C, int groups, int pool, float eps, float slope, float momentum,
                            float* z, float* mean, float* invstd, float* running_mean, float* running_var, void* stream);
 POF_API int pof_bn_act_bwd(const float* y, const float* dz, const float* mean, const float* invstd,
-                           const float* gamma, const float* beta, long long rows, int C, int pool, float slope,
+                           const float* gamma, const float* beta, long long rows, int C, int groups, int pool, float slope,
                            double* sums, float* dx, float* dgamma, float* dbeta, void* stream);
 
 /* ------------------------------------------------------------------------- *

@@ -52,10 +52,11 @@ SIGNATURES = {
     "pof_cutout_original_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_double, c_double, c_double,
                                         c_int, c_int, c_void_p, c_void_p]),
     "pof_polar_grid_fwd": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_int, c_void_p, c_void_p]),
-    "pof_bn_act_stats": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p]),
-    "pof_bn_act_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_float, c_float, c_float,
+    "pof_bn_act_stats": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_void_p]),
+    "pof_conv_first_wgrad": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "pof_bn_act_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_float, c_float, c_float,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "pof_bn_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_float,
+    "pof_bn_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_int, c_float,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pof_nms_ws_bytes": (c_size_t, [c_int, c_int]),
     "pof_nms_centers": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_double,

@@ -39,15 +39,24 @@ class _ConvBnAct(nn.Sequential):
 
     fused = True        # batch-norm + LeakyReLU (+ pool) of the training branch as libpof's one operator (False: cuDNN + PyTorch kernels)
 
-    def forward(self, x, pool=1):
-        """`pool` = 2 applies the block's max_pool1d(2) (dr_spaam.py:81) here, so it can be fused with the activation."""
+    def forward(self, x, pool=1, groups=1):
+        """`pool` = 2 applies the block's max_pool1d(2) (dr_spaam.py:81) here, so it can be fused with the activation.
+        `groups` > 1 (4-D training path only): x holds `groups` equal consecutive blocks of cutouts - the scans of the training
+        samples - that the reference pushes through this layer in `groups` separate calls (dr_spaam.py:264-273); the
+        convolution runs once over all of them and the batch norm keeps per-block statistics (`can_group`)."""
         if x.dim() != 4:
             y = super().forward(x)
             return F.max_pool1d(y, kernel_size=pool) if pool > 1 else y
-        y = self._forward_4d(x, pool)
-        return y
+        return self._forward_4d(x, pool, groups)
 
-    def _forward_4d(self, x, pool):
+    def can_group(self, x):
+        """True if this layer can take several scans at once with per-scan batch statistics (the fused CUDA operator)."""
+        conv, bn = self[0], self[1]
+        c = conv.out_channels
+        return bool(self.fused and x.is_cuda and bn.training and bn.track_running_stats and bn.affine and bn.momentum is not None
+                    and conv.bias is not None and c % 4 == 0 and 256 % (c // 4) == 0)
+
+    def _forward_4d(self, x, pool, groups=1):
         conv, bn = self[0], self[1]
         w4, pad = conv.weight.unsqueeze(2), (0, conv.padding[0])
         track = bn.track_running_stats
@@ -64,18 +73,30 @@ class _ConvBnAct(nn.Sequential):
         # arithmetic - 27 % of the step).  It still belongs to the running mean, and it still gets its (zero) gradient.
         if bn.training and track:
             bn.num_batches_tracked.add_(1)
+        if groups > 1:
+            if not self.can_group(x):
+                raise RuntimeError("this layer cannot take several scans at once; call it per scan")
+            if bn.training and track:
+                bn.num_batches_tracked.add_(groups - 1)           # one more call per extra scan
         factor = bn.momentum if bn.momentum is not None else 1.0 / max(float(bn.num_batches_tracked), 1.0)
         skip_bias = conv.bias is not None and factor < 1.0
         if skip_bias and bn.training and track:
             # rm <- (1 - f) rm + f (mean(y) + b): fold f b in before batch_norm's own update.  Through .data: earlier calls of
             # the same layer in this step (the gate embeds every scan) saved the buffer, and a version bump would make
             # autograd refuse their backward although batch-statistics backward never reads it.
-            bn.running_mean.data.add_(conv.bias.detach(), alpha=factor / (1.0 - factor))
-        y = F.conv2d(x, w4, None if skip_bias else conv.bias, padding=pad)
+            # For G grouped calls the bias enters every one of the G updates: rm_G = (1-f)^G rm_0 + sum_g f (1-f)^(G-1-g) (m_g + b),
+            # and the b terms sum to (1 - (1-f)^G) b, which is what adding b (1 - (1-f)^G) / (1-f)^G up front gives.
+            keep = (1.0 - factor) ** groups
+            bn.running_mean.data.add_(conv.bias.detach(), alpha=(1.0 - keep) / keep)
+        if (self.fused and skip_bias and x.is_cuda and conv.in_channels == 1 and conv.kernel_size == (3,) and pad == (0, 1)
+                and not x.requires_grad and x.dtype == torch.float32 and conv.out_channels % 4 == 0 and 256 % (conv.out_channels // 4) == 0):
+            y = ops.conv_first_train(x.reshape(x.shape[0], x.shape[3]), conv.weight)      # cuDNN has no fast engine for one input channel
+        else:
+            y = F.conv2d(x, w4, None if skip_bias else conv.bias, padding=pad)
         c = y.shape[1]
         if self.fused and y.is_cuda and bn.affine and c % 4 == 0 and 256 % (c // 4) == 0 and (pool == 1 or y.shape[3] % 2 == 0):
             y = ops.bn_act_pool(y, bn.weight, bn.bias, bn.running_mean if track else None, bn.running_var if track else None,
-                                momentum=factor, eps=bn.eps, slope=_SLOPE, pool=pool)
+                                momentum=factor, eps=bn.eps, slope=_SLOPE, pool=pool, groups=groups)
         else:
             y = F.batch_norm(y, bn.running_mean if track else None, bn.running_var if track else None, bn.weight, bn.bias,
                              True, factor, bn.eps)
@@ -148,14 +169,18 @@ class DROW(nn.Module):
         return torch.sum(x, dim=2)
 
     # -- the same two halves on channels-last 4-D activations [M, C, 1, L] (see _ConvBnAct) ------------------
-    def _features_cl(self, scan_cutouts):
-        """[B, N, P] cutouts of one scan -> [B*N, 256, 1, P/4], channels-last memory."""
+    def _features_cl(self, scan_cutouts, groups=1):
+        """[B, N, P] cutouts of one scan -> [B*N, 256, 1, P/4], channels-last memory.  With `groups` = S the input is
+        [S * B, N, P] (scan-major): all scans of the samples in one pass, batch statistics per scan."""
         b, n, p = scan_cutouts.shape
         y = scan_cutouts.reshape(b * n, 1, 1, p).contiguous(memory_format=torch.channels_last)
         for blk in (self.conv_block_1, self.conv_block_2):
             for k, layer in enumerate(blk):
-                y = layer(y, pool=2 if k == len(blk) - 1 else 1)          # the block's max_pool1d(2), fused into its last layer
+                y = layer(y, pool=2 if k == len(blk) - 1 else 1, groups=groups)   # the block's max_pool1d(2), fused into its last layer
         return y
+
+    def _can_group_features(self, x):
+        return all(layer.can_group(x) for blk in (self.conv_block_1, self.conv_block_2) for layer in blk)
 
     def _votes_cl(self, t, b, n):
         """[B*N, 256, 1, L] channels-last fused features -> ([B, N, C], [B, N, 2])."""
@@ -237,10 +262,24 @@ class SpatialDROW(DROW):
         def embed(t4):
             return self.gate.conv(t4).view(b, n, -1)
 
-        tmpl = self._features_cl(x[:, :, 0, :])
+        # The per-scan features do not depend on the recurrence: with the fused operator all S scans go through conv blocks
+        # 1-2 in ONE pass (one convolution and one weight gradient per layer instead of S, no S-fold gradient accumulation),
+        # the batch norm keeping the per-scan statistics and running-statistics updates of the reference's S separate calls.
+        feats = None
+        if n_scan > 1 and self.training and self._can_group_features(x):
+            allscans = x.permute(2, 0, 1, 3).reshape(n_scan * b, n, x.shape[3])            # scan-major
+            feats = self._features_cl(allscans, groups=n_scan)                               # [S*B*N, 256, 1, L]
+            feats = feats.view(n_scan, b * n, feats.shape[1], 1, feats.shape[3])
+
+        def scan_features(s):
+            if feats is not None:
+                return feats[s]
+            return self._features_cl(x[:, :, s, :])
+
+        tmpl = scan_features(0)
         feat_fused = None
         for s in range(1, max(n_scan, 2)):          # a single-scan input gates scan 0 with itself (:271-273)
-            cur = self._features_cl(x[:, :, min(s, n_scan - 1), :])
+            cur = scan_features(min(s, n_scan - 1))
             out_rows, feat_fused = ops.gate(rows(cur), rows(tmpl), embed(cur), embed(tmpl), self.gate._alpha, self.gate.window)
             tmpl = out_rows.view(b * n, 1, out_rows.shape[2], out_rows.shape[3]).permute(0, 3, 1, 2)
         pred_cls, pred_reg = self._votes_cl(tmpl, b, n)

@@ -333,7 +333,7 @@ class _BnActPoolFn(torch.autograd.Function):
     """y [M, C, 1, L] (channels-last memory: rows = M * L, C contiguous) -> [M, C, 1, L / pool]."""
 
     @staticmethod
-    def forward(ctx, y, gamma, beta, running_mean, running_var, momentum, eps, slope, pool):
+    def forward(ctx, y, gamma, beta, running_mean, running_var, momentum, eps, slope, pool, groups):
         require_cuda_tensor(gamma, "gamma", torch.float32)
         require_cuda_tensor(beta, "beta", torch.float32)
         if y.dim() != 4 or y.shape[2] != 1 or y.dtype != torch.float32 or not y.is_cuda:
@@ -344,38 +344,76 @@ class _BnActPoolFn(torch.autograd.Function):
         if pool not in (1, 2) or Lr % pool:
             raise ValueError("pool must be 1, or 2 with an even length (got pool=%d, L=%d)" % (pool, Lr))
         rows = M * Lr
+        if groups < 1 or M % groups:
+            raise ValueError("the %d cutouts do not split into %d groups" % (M, groups))
         dev = y.device
         with torch.cuda.device(dev):
-            sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
-            z = torch.empty((M, C, 1, Lr // pool), dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last)
-            mean = torch.empty(C, dtype=torch.float32, device=dev)
-            invstd = torch.empty(C, dtype=torch.float32, device=dev)
+            sums = torch.empty(2 * groups * C, dtype=torch.float64, device=dev)
+            z = torch.empty((M, C, 1, Lr // pool), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+            mean = torch.empty(groups * C, dtype=torch.float32, device=dev)
+            invstd = torch.empty(groups * C, dtype=torch.float32, device=dev)
             L = _lib.lib()
             stream = current_stream_ptr(dev)
-            check(L.pof_bn_act_stats(_ptr(y), rows, C, _ptr(sums), stream), "pof_bn_act_stats")
-            check(L.pof_bn_act_fwd(_ptr(y), _ptr(sums), _ptr(gamma), _ptr(beta), rows, C, int(pool), float(eps), float(slope),
+            check(L.pof_bn_act_stats(_ptr(y), rows, C, int(groups), _ptr(sums), stream), "pof_bn_act_stats")
+            check(L.pof_bn_act_fwd(_ptr(y), _ptr(sums), _ptr(gamma), _ptr(beta), rows, C, int(groups), int(pool), float(eps), float(slope),
                                    float(momentum), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(running_mean), _ptr(running_var), stream),
                   "pof_bn_act_fwd")
         ctx.save_for_backward(y, gamma, beta, mean, invstd)
-        ctx.cfg = (float(slope), int(pool))
+        ctx.cfg = (float(slope), int(pool), int(groups))
         return z
 
     @staticmethod
     def backward(ctx, dz):
         y, gamma, beta, mean, invstd = ctx.saved_tensors
-        slope, pool = ctx.cfg
+        slope, pool, groups = ctx.cfg
         M, C, _, Lr = y.shape
         dev = y.device
         dz = dz.contiguous(memory_format=torch.channels_last)
         with torch.cuda.device(dev):
-            dx = torch.empty_like(y)                       # channels-last like y
+            dx = torch.empty_like(y, memory_format=torch.channels_last)
             dgamma = torch.empty(C, dtype=torch.float32, device=dev)
             dbeta = torch.empty(C, dtype=torch.float32, device=dev)
-            sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
-            check(_lib.lib().pof_bn_act_bwd(_ptr(y), _ptr(dz), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), M * Lr, C, pool,
+            sums = torch.empty(2 * groups * C, dtype=torch.float64, device=dev)
+            check(_lib.lib().pof_bn_act_bwd(_ptr(y), _ptr(dz), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), M * Lr, C, groups, pool,
                                             slope, _ptr(sums), _ptr(dx), _ptr(dgamma), _ptr(dbeta), current_stream_ptr(dev)),
                   "pof_bn_act_bwd")
         return dx, dgamma, dbeta, None, None, None, None, None, None
+
+
+class _ConvFirstFn(torch.autograd.Function):
+    """Conv1d(1 -> C, k = 3, p = 1) without bias on cutouts [M, P] -> channels-last activations [M, C, 1, P]."""
+
+    @staticmethod
+    def forward(ctx, cutouts, weight):
+        require_cuda_tensor(cutouts, "cutouts", torch.float32)
+        M, P = cutouts.shape
+        C = weight.shape[0]
+        w = weight.detach().reshape(C, 3).contiguous()
+        zero = torch.zeros(C, dtype=torch.float32, device=cutouts.device)
+        plain, _ = conv_first(cutouts, w, zero, slope=1.0, want_plain=True, want_split=False)       # [M * P, C]
+        ctx.save_for_backward(cutouts)
+        ctx.w_shape = tuple(weight.shape)
+        return plain.view(M, 1, P, C).permute(0, 3, 1, 2)                                           # [M, C, 1, P], channels-last memory
+
+    @staticmethod
+    def backward(ctx, dy):
+        (cutouts,) = ctx.saved_tensors
+        M, P = cutouts.shape
+        C = ctx.w_shape[0]
+        dev = cutouts.device
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        with torch.cuda.device(dev):
+            sums = torch.empty(3 * C, dtype=torch.float64, device=dev)
+            dw = torch.empty((C, 3), dtype=torch.float32, device=dev)
+            check(_lib.lib().pof_conv_first_wgrad(_ptr(dy), _ptr(cutouts), M, P, C, _ptr(sums), _ptr(dw), current_stream_ptr(dev)),
+                  "pof_conv_first_wgrad")
+        return None, dw.view(ctx.w_shape)
+
+
+def conv_first_train(cutouts, weight):
+    """The first layer's convolution for the training branch (no bias: it cancels under batch statistics), differentiable in
+    the weight; the cutouts are data and get no gradient.  cutouts [M, P] float32 CUDA, weight [C, 1, 3]."""
+    return _ConvFirstFn.apply(cutouts, weight)
 
 
 def bn_act_pool(y, gamma, beta, running_mean=None, running_var=None, momentum=0.1, eps=1e-5, slope=0.1, pool=1):

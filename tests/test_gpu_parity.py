@@ -867,3 +867,21 @@ def test_fused_training_layers_equal_the_cudnn_path():
         ga, gb = a[3][k].flatten().double().cpu(), b[3][k].flatten().double().cpu()
         cos = float((ga @ gb) / (ga.norm() * gb.norm() + 1e-300))
         assert cos > 0.9999 and rel_err(ga, gb) < 0.2, (k, cos, rel_err(ga, gb))
+
+
+def test_first_layer_training_conv_and_weight_gradient():
+    """ops.conv_first_train (the 1 -> 64 layer of the training branch: forward kernel + pof_conv_first_wgrad) vs autograd in float64."""
+    g = torch.Generator().manual_seed(8)
+    M, P, C = 211, 56, 64
+    x = torch.randn(M, P, generator=g).clamp(-1, 1)
+    w = torch.randn(C, 1, 3, generator=g) * 0.5
+    gy = torch.randn(M, C, 1, P, generator=g)
+    w64 = w.double().requires_grad_(True)
+    y64 = F.conv1d(x.double().view(M, 1, P), w64, None, padding=1)                     # [M, C, P]
+    (y64 * gy.double().view(M, C, P)).sum().backward()
+    wc = w.cuda().requires_grad_(True)
+    y = ops.conv_first_train(x.cuda(), wc)
+    assert tuple(y.shape) == (M, C, 1, P) and y.is_contiguous(memory_format=torch.channels_last)
+    (y * gy.cuda()).sum().backward()
+    assert_rel(y.detach().cpu().view(M, C, P), y64.detach(), tol=1e-6, what="first layer forward")
+    assert_rel(wc.grad.cpu(), w64.grad, tol=2e-6, what="first layer weight gradient")

@@ -1,6 +1,6 @@
 // L2 -> SM bandwidth of TMA bulk loads on sm_100a: every CTA (one per SM) streams chunks of an L2-resident buffer
 // into shared memory through a ring of mbarriers, nothing else.  Upper bound for the tcgen05 convolution's operand feed.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/l2_bw tools/l2_bw.cu && tools/l2_bw
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o /tmp/l2_bw tools/l2_bw.cu   (build outside the tree: the binary is not part of the product) && /tmp/l2_bw
 #include <cstdio>
 #include <cuda_runtime.h>
 

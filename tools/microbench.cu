@@ -1,5 +1,5 @@
 // Instruction-throughput microbenchmarks that decide the cutout kernel's arithmetic plan.
-// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench tools/microbench.cu
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o /tmp/microbench tools/microbench.cu   (build outside the tree: the binary is not part of the product)
 #include <cstdio>
 #include <cuda_runtime.h>
 
