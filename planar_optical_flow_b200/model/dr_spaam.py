@@ -16,6 +16,7 @@ What changed underneath:
   * the 1-D conv backbone stays on PyTorch/cuDNN: it is the only dense contraction.
 The modules only run on CUDA tensors; there is no CPU path.
 """
+import os
 from math import ceil
 
 import torch
@@ -230,6 +231,13 @@ class _SpatialAttention(nn.Module):
 
 
 class SpatialDROW(DROW):
+    # Training branch: how many scans of a sample go through conv blocks 1-2 in one call (per-scan batch statistics are kept
+    # either way, ops.bn_act_pool(groups=...)).  Measured on B200 (bench.py --workload train, 8 x 11 scans x 450 points): 1 scan per
+    # call 30.5 ms per step, 2: 26.3, 4: 22.1, all 11: 32.3 - fewer, larger launches and no per-scan gradient accumulation up to
+    # a point; beyond it cuDNN answers the batch with a much slower (strided) dgrad engine and the activations of a call no
+    # longer stay in L2 between the passes of the batch-norm operator.
+    scans_per_call = int(os.environ.get("POF_TRAIN_SCANS_PER_CALL", "4"))
+
     def __init__(self, dropout=0.5, num_scans=5, num_pts=48, focal_loss_gamma=0.0, alpha=0.5, window_size=7,
                  pedestrian_only=False):
         super().__init__(dropout=dropout, num_scans=num_scans, num_pts=num_pts,
@@ -266,10 +274,14 @@ class SpatialDROW(DROW):
         # 1-2 in ONE pass (one convolution and one weight gradient per layer instead of S, no S-fold gradient accumulation),
         # the batch norm keeping the per-scan statistics and running-statistics updates of the reference's S separate calls.
         feats = None
-        if n_scan > 1 and self.training and self._can_group_features(x):
-            allscans = x.permute(2, 0, 1, 3).reshape(n_scan * b, n, x.shape[3])            # scan-major
-            feats = self._features_cl(allscans, groups=n_scan)                               # [S*B*N, 256, 1, L]
-            feats = feats.view(n_scan, b * n, feats.shape[1], 1, feats.shape[3])
+        per_call = max(1, min(int(self.scans_per_call), n_scan))
+        if per_call > 1 and self.training and self._can_group_features(x):
+            feats = []
+            for s0 in range(0, n_scan, per_call):                 # consecutive scans, in scan order: the running statistics see the
+                g = min(per_call, n_scan - s0)                    # same sequence of updates as the reference's per-scan calls
+                block = x[:, :, s0:s0 + g, :].permute(2, 0, 1, 3).reshape(g * b, n, x.shape[3])      # scan-major
+                f = self._features_cl(block, groups=g)                                             # [g*B*N, 256, 1, L]
+                feats.extend(f.view(g, b * n, f.shape[1], 1, f.shape[3]).unbind(0))
 
         def scan_features(s):
             if feats is not None:

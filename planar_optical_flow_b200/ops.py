@@ -377,7 +377,7 @@ class _BnActPoolFn(torch.autograd.Function):
             check(_lib.lib().pof_bn_act_bwd(_ptr(y), _ptr(dz), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), M * Lr, C, groups, pool,
                                             slope, _ptr(sums), _ptr(dx), _ptr(dgamma), _ptr(dbeta), current_stream_ptr(dev)),
                   "pof_bn_act_bwd")
-        return dx, dgamma, dbeta, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None
 
 
 class _ConvFirstFn(torch.autograd.Function):
@@ -416,10 +416,12 @@ def conv_first_train(cutouts, weight):
     return _ConvFirstFn.apply(cutouts, weight)
 
 
-def bn_act_pool(y, gamma, beta, running_mean=None, running_var=None, momentum=0.1, eps=1e-5, slope=0.1, pool=1):
+def bn_act_pool(y, gamma, beta, running_mean=None, running_var=None, momentum=0.1, eps=1e-5, slope=0.1, pool=1, groups=1):
     """Training-mode BatchNorm (batch statistics, running statistics updated in place) + LeakyReLU + max-pool over `pool`
-    consecutive positions, as one differentiable operator on channels-last activations y [M, C, 1, L] (csrc/pof_bnact.cu)."""
-    return _BnActPoolFn.apply(y, gamma, beta, running_mean, running_var, momentum, eps, slope, pool)
+    consecutive positions, as one differentiable operator on channels-last activations y [M, C, 1, L] (csrc/pof_bnact.cu).
+    `groups` > 1: the M cutouts are `groups` equal consecutive blocks (the scans of a training sample), each normalised with
+    its own batch statistics exactly as `groups` separate calls would, the running statistics updated once per block in order."""
+    return _BnActPoolFn.apply(y, gamma, beta, running_mean, running_var, momentum, eps, slope, pool, groups)
 
 
 # --------------------------------------------------------------------------- patch correlation (prototype)

@@ -885,3 +885,31 @@ def test_first_layer_training_conv_and_weight_gradient():
     (y * gy.cuda()).sum().backward()
     assert_rel(y.detach().cpu().view(M, C, P), y64.detach(), tol=1e-6, what="first layer forward")
     assert_rel(wc.grad.cpu(), w64.grad, tol=2e-6, what="first layer weight gradient")
+
+
+def test_bn_act_pool_groups_equal_separate_calls():
+    """groups = G on G stacked blocks == G separate calls in order: outputs, gradients and the running statistics after the
+    G sequential updates (the reference runs a layer once per scan, dr_spaam.py:264-273)."""
+    g = torch.Generator().manual_seed(21)
+    G, Mg, L, C, pool = 5, 23, 28, 128, 2
+    y = (torch.randn(G * Mg, C, 1, L, generator=g) * torch.linspace(0.5, 2.0, G).repeat_interleave(Mg)[:, None, None, None]).cuda()
+    y = y.contiguous(memory_format=torch.channels_last)
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).cuda(), (torch.randn(C, generator=g) * 0.2).cuda()
+    w = torch.randn(G * Mg, C, 1, L // pool, generator=g).cuda()
+    rm0, rv0 = (torch.randn(C, generator=g) * 0.1).cuda(), (torch.rand(C, generator=g) + 0.5).cuda()
+    # separate calls
+    ys = y.clone().requires_grad_(True)
+    gs, bs = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_s, rv_s = rm0.clone(), rv0.clone()
+    z_s = torch.cat([ops.bn_act_pool(ys[k * Mg:(k + 1) * Mg], gs, bs, rm_s, rv_s, momentum=0.1, pool=pool) for k in range(G)])
+    (z_s * w).sum().backward()
+    # one grouped call
+    yg = y.clone().requires_grad_(True)
+    gg, bg = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_g, rv_g = rm0.clone(), rv0.clone()
+    z_g = ops.bn_act_pool(yg, gg, bg, rm_g, rv_g, momentum=0.1, pool=pool, groups=G)
+    (z_g * w).sum().backward()
+    assert torch.equal(z_g, z_s) and torch.equal(yg.grad, ys.grad)
+    assert torch.equal(rm_g, rm_s) and torch.equal(rv_g, rv_s)
+    assert_rel(gg.grad.cpu(), gs.grad.cpu(), tol=1e-6, what="grad gamma")
+    assert_rel(bg.grad.cpu(), bs.grad.cpu(), tol=1e-6, what="grad beta")
