@@ -77,6 +77,8 @@ struct GateArgs {
     int B, N, CL, E;
     int chunk_len, n_chunks;
     float alpha, beta;   // beta = (float)(1.0 - alpha)
+    const float* g_feat; // MODE 2: gradient of feat_fused [B, N, W] or null
+    float* g_s;          // MODE 2: gradient of the similarities [B, N, W]
     void* out_split;     // forward only, optional: the new memory as binary16 [hi | lo] rows of split_c channels
     int split_c;         //   (operand of pof_conv_tc_f16_fwd: row r = point * (CL / split_c) + l is [hi(split_c) | lo(split_c)])
     int* status;         // optional device int: 32 = a ring wait timed out, 16 = a memory value left the binary16 range
@@ -195,6 +197,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // MODE 0 (forward):  out[i]  = alpha*x[i] + beta * sum_k w[i][k]  * tmpl[i-hw+k]
 // MODE 1 (backward): out[j]  = beta * sum_k wT[j][k] * g_out[j-hw+k]   (g_tmpl; `tmpl` = g_out)
 //                    out2[j] = alpha * g_out[j]                         (g_x)
+// MODE 2 (backward): g_w[i][k] = beta * <g_out[i], tmpl[i-hw+k]>  (`x` = g_out), then the soft-max Jacobian and the direct
+//                    feat_fused gradient: g_s[i][k] = w[i][k] * (g_w[i][k] - sum_k' w[i][k'] g_w[i][k']) + g_feat[i][k].
+//                    The template rows come through the same ring and register window as in the forward, so each is
+//                    fetched once per chunk (the first version of this pass - one warp per point, gate_bwd_scores_kernel -
+//                    re-read the W rows of every point out of L2).  A thread's four channels give W partial products per
+//                    point; a warp folds its 32 x W partials with a transposing butterfly (16 shuffles for up to 16 values
+//                    instead of 5 per value), the 28 warp sums of a point meet in shared memory, and warp 0 finishes the point
+//                    one stage later, behind the barrier the ring needs anyway.  Clamped duplicates at the sequence ends
+//                    have weight 0 in w, so their products never reach g_s.
 //
 // The chunk is consumed as a sequence of STAGES s = 0 .. len+W-2.  Stage s carries template row
 // clamp(i0-hw+s) and, once the window is full (s >= W-1), the x row of point p = s-(W-1).  One
@@ -202,6 +213,42 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // (completion on one mbarrier per slot); every thread then moves ITS 16 bytes of the new template
 // row into its register window, so shared memory is only a deep prefetch queue (1 write + 1 read
 // per element) and the W-fold neighbour re-use still costs no memory traffic.
+// floats of the per-chunk weight table; MODE 2 keeps two points' per-warp partial sums there instead
+template <int W>
+struct GateTable {
+    static constexpr size_t kWeights = (size_t)kMaxChunk * ((W + 3) & ~3), kPartials = (size_t)2 * (kGateThreads / 32) * 16;
+    static constexpr size_t kFloats = kWeights > kPartials ? kWeights : kPartials;
+};
+
+// Sum 16 per-lane values over the 32 lanes of a warp with a transposing butterfly: after the five steps lane L holds the
+// warp total of value index  ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1)  (both lanes of a pair hold it).
+__device__ __forceinline__ float warp_fold16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool up = (lane & 16) != 0;
+        const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool up = (lane & 8) != 0;
+        const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const bool up = (lane & 4) != 0;
+        const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        const bool up = (lane & 2) != 0;
+        const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 template <int W, int MODE>
 __global__ void __launch_bounds__(kGateThreads, kGateMinBlocks) gate_stream_kernel(const GateArgs a) {
     constexpr int HW = W / 2;
@@ -212,7 +259,7 @@ __global__ void __launch_bounds__(kGateThreads, kGateMinBlocks) gate_stream_kern
     float4* stage = reinterpret_cast<float4*>(smem_raw);
     float(*w_s)[WPAD] = reinterpret_cast<float(*)[WPAD]>(smem_raw + (size_t)R * 2 * kGateThreads * sizeof(float4));
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)R * 2 * kGateThreads * sizeof(float4) +
-                                                                     sizeof(float) * kMaxChunk * WPAD);
+                                                                     sizeof(float) * GateTable<W>::kFloats);
 
     const int tid = threadIdx.x;
     const int b = blockIdx.z;
@@ -231,7 +278,7 @@ __global__ void __launch_bounds__(kGateThreads, kGateMinBlocks) gate_stream_kern
 
     auto issue = [&](int s) {        // thread 0 only
         const int slot = s % R;
-        const bool with_x = (MODE == 0) && s >= W - 1;
+        const bool with_x = (MODE == 0 || MODE == 2) && s >= W - 1;
         mbar_expect_tx(&full[slot], with_x ? 2 * row_bytes : row_bytes);
         const int r = min(max(i0 - HW + s, 0), a.N - 1);              // clamped like the reference's table (:152)
         bulk_g2s(stage + (size_t)slot * 2 * kGateThreads, t_base + r * CL, row_bytes, &full[slot]);
@@ -247,8 +294,28 @@ __global__ void __launch_bounds__(kGateThreads, kGateMinBlocks) gate_stream_kern
         for (int s = 0; s < min(R, n_stages); ++s) issue(s);          // in flight while the weights are computed
     }
     if (MODE == 0) chunk_weights<W>(a, b, i0, len, blockIdx.y == 0, w_s);
-    else chunk_weights_transposed<W>(a, b, i0, len, w_s);
+    else if (MODE == 1) chunk_weights_transposed<W>(a, b, i0, len, w_s);
     __syncthreads();
+    // MODE 2: the weight table's memory holds the per-warp partial sums of two points in flight: red[parity][warp][16]
+    float* red = reinterpret_cast<float*>(w_s);
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kGateThreads / 32;
+    static_assert(W <= 16 && 2 * kWarps * 16 <= GateTable<W>::kFloats, "partial sums do not fit the weight table");
+    // MODE 2: warp 0 turns the warp sums of point p into g_s[p]
+    auto finish_point = [&](int p) {
+        const int i = i0 + p;
+        float gw = 0.f;
+        if (lane < W) {
+            const float* r = red + (size_t)(p & 1) * kWarps * 16 + lane;
+#pragma unroll 4
+            for (int w = 0; w < kWarps; ++w) gw += r[w * 16];
+            gw *= a.beta;
+        }
+        const size_t o = ((size_t)b * a.N + i) * W + lane;
+        const float wv = lane < W ? __ldg(a.attn_w + o) : 0.f;
+        const float mean = warp_sum(wv * gw);
+        if (lane < W) a.g_s[o] = wv * (gw - mean) + (a.g_feat ? __ldg(a.g_feat + o) : 0.f);
+    };
 
     float4 win[W];
 #pragma unroll
@@ -272,11 +339,30 @@ __global__ void __launch_bounds__(kGateThreads, kGateMinBlocks) gate_stream_kern
                 mbar_wait(&full[slot], (unsigned)(s / R) & 1u, a.status);
                 const float4 tv = stage[(size_t)slot * 2 * kGateThreads + tid];
                 float4 xv = f4_zero();
-                if (MODE == 0 && s >= W - 1) xv = stage[((size_t)slot * 2 + 1) * kGateThreads + tid];
+                if ((MODE == 0 || MODE == 2) && s >= W - 1) xv = stage[((size_t)slot * 2 + 1) * kGateThreads + tid];
                 __syncthreads();                                       // slot fully read: refill it
                 if (tid == 0 && s + R < n_stages) issue(s + R);
                 win[u] = tv;                                           // row s replaces row s-W
-                if (s >= W - 1) {
+                if (MODE == 2) {
+                    // the barrier above also published the warp sums of the previous point
+                    if (warp == 0 && s >= W) finish_point(s - W);
+                    if (s >= W - 1) {
+                        const int p = s - (W - 1);
+                        float part[16];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            if (k < W) {
+                                const float4 t = win[(u + 1 + k) % W];                       // template row i-hw+k
+                                part[k] = active ? fmaf(xv.x, t.x, fmaf(xv.y, t.y, fmaf(xv.z, t.z, xv.w * t.w))) : 0.f;
+                            } else {
+                                part[k] = 0.f;
+                            }
+                        }
+                        const float tot = warp_fold16(part, lane);
+                        const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                        if ((lane & 1) == 0) red[((size_t)(p & 1) * kWarps + warp) * 16 + idx] = tot;
+                    }
+                } else if (s >= W - 1) {
                     const int p = s - (W - 1);
                     const int i = i0 + p;
                     float wk[WPAD];
@@ -318,11 +404,15 @@ __global__ void __launch_bounds__(kGateThreads, kGateMinBlocks) gate_stream_kern
         }
     }
     if (MODE == 0 && s_col && !(amax <= 65504.f) && a.status) atomicCAS(a.status, 0, 16);   // beyond binary16 (or NaN)
+    if (MODE == 2) {                                                   // the last point of the chunk
+        __syncthreads();
+        if (warp == 0) finish_point(len - 1);
+    }
 }
 
 template <int W>
 constexpr size_t gate_smem_bytes() {
-    return (size_t)kGateRing * 2 * kGateThreads * sizeof(float4) + sizeof(float) * kMaxChunk * ((W + 3) & ~3) +
+    return (size_t)kGateRing * 2 * kGateThreads * sizeof(float4) + sizeof(float) * GateTable<W>::kFloats +
            kGateRing * sizeof(unsigned long long);
 }
 
@@ -459,8 +549,25 @@ int launch_gate_bwd_small(const GateArgs& a, const float* g_out, const float* g_
                           cudaStream_t stream) {
     const long long pts = (long long)a.B * a.N;
     const unsigned grid = (unsigned)((pts + 7) / 8);
+#ifdef POF_GATE_BWD_SCORES_PER_POINT          // the first version: one warp per point, template rows re-read from L2
     gate_bwd_scores_kernel<W><<<grid, 256, 0, stream>>>(a, g_out, g_feat, g_s);
     POF_CUDA(cudaGetLastError());
+#else
+    {
+        GateArgs sc = a;
+        sc.x = g_out;              // the "x row" of a stage carries g_out[i]
+        sc.g_feat = g_feat;
+        sc.g_s = g_s;
+        dim3 sgrid;
+        plan_chunks(a.B, a.N, a.CL, sc, sgrid);
+        if (sgrid.y != 1) {        // rows wider than one CTA's 3584 channels: the per-point kernel sums over the whole row
+            gate_bwd_scores_kernel<W><<<grid, 256, 0, stream>>>(a, g_out, g_feat, g_s);
+            POF_CUDA(cudaGetLastError());
+        } else if (int rc = launch_gate_stream<W, 2>(sc, sgrid, kGateThreads, stream)) {
+            return rc;
+        }
+    }
+#endif
     gate_bwd_embed_kernel<W><<<grid, 256, 0, stream>>>(a, g_s, g_ex, g_et);
     POF_CUDA(cudaGetLastError());
     return POF_OK;
@@ -501,6 +608,7 @@ int pof_spaam_gate_fwd(const float* x, const float* tmpl, const float* emb_x, co
     a.x = x; a.tmpl = tmpl; a.emb_x = emb_x; a.emb_t = emb_t;
     a.out = out_tmpl; a.feat_fused = feat_fused; a.attn_w = attn_w;
     a.out_split = out_split; a.split_c = out_split ? split_channels : 0; a.status = status;
+    a.g_feat = nullptr; a.g_s = nullptr;
     a.B = B; a.N = N; a.CL = CL; a.E = E;
     a.alpha = alpha;
     a.beta = (float)(1.0 - (double)alpha);
@@ -541,6 +649,7 @@ int pof_spaam_gate_bwd(const float* tmpl, const float* emb_x, const float* emb_t
     a.beta = (float)(1.0 - (double)alpha);
     a.chunk_len = 0; a.n_chunks = 0;
     a.out_split = nullptr; a.split_c = 0; a.status = nullptr;
+    a.g_feat = nullptr; a.g_s = nullptr;
     float* g_s = reinterpret_cast<float*>(ws);
 
     int rc = POF_ERR_UNSUPPORTED;
