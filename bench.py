@@ -30,8 +30,13 @@ One JSON line on stdout (rank 0):
   roofline_gate / roofline_cutout   the two HBM-bound hot-path kernels: algorithmic bytes (SURVEY.md
              §8d: N*44,076 B per sequence-step, N*228 B per scan row) / CUDA-event launch time,
              against the measured copy bandwidth (MEASURED_PEAKS.json)
-  cpu_baseline  the oracle (CPU restatement of the reference, NumPy + torch CPU) timed on this
-             box's host cores on a bounded sample of the same workload
+             (`traffic` = ncu dram bytes of one launch of the current build, profiles/r2_ncu_traffic.json; the gate line also
+             carries the figure that counts the float16 operand split the kernel writes in the same pass)
+  parity_spot   two of the timed sequences replayed through the oracle's reference loop AFTER the timed region: max error of
+             the last step's scores / votes / memory relative to each tensor's magnitude, NMS masks equal
+  cpu_baseline  the UNMODIFIED reference (baseline/_ref: its scans_to_cutout, SpatialDROW module, nms_predicted_center;
+             kind "reference") - or, if that directory is missing, the oracle port of the same algorithm (kind "port") -
+             timed on this box's host cores on a bounded sample of the same workload
 `--impl reference` times that CPU path alone, as the reference arm.
 """
 import argparse

@@ -17,7 +17,7 @@ for shape in ("jrdb", "drow") if not ONLY else ("jrdb",):
     n = len(phi)
     phi_d = torch.from_numpy(phi).to(dev)
     for kind in ("structured", "adversarial") if not ONLY else ("structured",):
-        for B, S in ((256, 1), (4096, 1), (64, 11)) if not ONLY else ((4096, 1),):
+        for B, S in ((256, 1), (4096, 1), (64, 11), (512, 11)) if not ONLY else ((4096, 1),):
             if kind == "structured":
                 base = np.stack([synth.structured_sequence(S, n, seed=k, phi=phi) for k in range(16)])
                 scans = np.tile(base, (B // 16 + 1, 1, 1))[:B]
