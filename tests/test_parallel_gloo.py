@@ -90,3 +90,26 @@ def test_ddp_gradients_identical_across_ranks_world2():
     out = _run("_ddp")
     assert out[0][0] and out[1][0]
     assert out[0][1] == out[1][1] > 0
+
+
+def _sharded_loader(rank, world, parallel):
+    """Under an initialised process group `create_dataloader` shards every epoch: the ranks' samples are disjoint, cover the
+    set, and the order changes with the epoch (Trainer.train calls sampler.set_epoch)."""
+    from planar_optical_flow_b200.dataset_dr_spaam import create_dataloader
+
+    loader, _ = create_dataloader("/no-such-dir", num_scans=2, batch_size=4, num_workers=0, num_samples=32,
+                                  cutout_kwargs=dict(num_cutout_pts=56))
+    seen = []
+    for epoch in (0, 1):
+        loader.sampler.set_epoch(epoch)
+        seen.append([i for b in loader for i in b["idx"]])
+    return seen, type(loader.sampler).__name__
+
+
+def test_training_loader_is_sharded_across_ranks_world2():
+    out = _run("_sharded_loader")
+    (a0, a1), name = out[0]
+    (b0, b1), _ = out[1]
+    assert name == "DistributedSampler"
+    assert len(a0) == len(b0) == 16 and not set(a0) & set(b0) and sorted(a0 + b0) == list(range(32))
+    assert not set(a1) & set(b1) and a0 != a1                     # re-shuffled, still disjoint
