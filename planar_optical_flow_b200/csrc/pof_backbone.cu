@@ -106,8 +106,10 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
         w0[j] = __ldg(w + 3 * (c + j)); w1[j] = __ldg(w + 3 * (c + j) + 1); w2[j] = __ldg(w + 3 * (c + j) + 2);
         bb[j] = __ldg(bias + c + j);
     }
-    for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / cgn; row < rows; row += (long long)gridDim.x * rpb) {
-        const int l = rows < (1ll << 32) ? (int)((unsigned)row % (unsigned)P) : (int)(row % P);
+    const long long row_first = (long long)blockIdx.x * rpb + threadIdx.x / cgn, row_step = (long long)gridDim.x * rpb;
+    int l = (int)(row_first % P);                          // position inside the cutout, advanced without a division per row
+    const int l_step = (int)(row_step % P);
+    for (long long row = row_first; row < rows; row += row_step, l = l + l_step >= P ? l + l_step - P : l + l_step) {
         const float xc = __ldg(x + row);
         const float xl = l > 0 ? __ldg(x + row - 1) : 0.f;
         const float xr = l < P - 1 ? __ldg(x + row + 1) : 0.f;

@@ -913,3 +913,44 @@ def test_bn_act_pool_groups_equal_separate_calls():
     assert torch.equal(rm_g, rm_s) and torch.equal(rv_g, rv_s)
     assert_rel(gg.grad.cpu(), gs.grad.cpu(), tol=1e-6, what="grad gamma")
     assert_rel(bg.grad.cpu(), bs.grad.cpu(), tol=1e-6, what="grad beta")
+
+
+def test_kernels_do_not_write_outside_their_outputs():
+    """compute-sanitizer is not available on the GPU pool: outputs are placed inside larger buffers filled with a canary value
+    and the bytes before and after them must come back untouched (multi-scan cutout kernel, attention kernel with the operand
+    split, tcgen05 convolution writing into a caller's view)."""
+    canary = 1234.5
+    pad = 4096
+
+    def guarded(shape, dtype=torch.float32):
+        n = int(np.prod(shape))
+        buf = torch.full((n + 2 * pad,), canary, dtype=dtype, device="cuda")
+        return buf, buf[pad:pad + n].view(shape)
+
+    def intact(buf, n):
+        return bool((buf[:pad] == canary).all()) and bool((buf[pad + n:] == canary).all())
+
+    phi = synth.phi_for("jrdb")
+    n = len(phi)
+    scans = torch.from_numpy(np.stack([synth.adversarial_scans(3, n, seed=k) for k in range(2)])).cuda()
+    for fast in (True, False):
+        buf, out = guarded((2, n, 3, 56))
+        ops.cutout(scans, torch.from_numpy(phi).cuda(), fast=fast, out=out, **CFG)
+        assert intact(buf, out.numel()) and bool(torch.isfinite(out).all()) and not bool((out == canary).any())
+    b, npts, L, C, E = 2, 23, 14, 256, 128
+    x, t = torch.randn(b, npts, L, C).cuda(), torch.randn(b, npts, L, C).cuda()
+    ex, et = torch.randn(b, npts, E).cuda() * 0.2, torch.randn(b, npts, E).cuda() * 0.2
+    b_out, o = guarded((b, npts, L, C))
+    b_ff, ff = guarded((b, npts, 11))
+    b_sp, sp = guarded((b * npts * L, 2 * C), torch.float16)
+    ops.gate_forward(x, t, ex, et, 0.5, 11, out=o, feat_out=ff, split_out=sp, split_channels=C)
+    assert intact(b_out, o.numel()) and intact(b_ff, ff.numel()) and intact(b_sp, sp.numel())
+    assert not bool((o == canary).any()) and not bool((sp == canary).any())
+    M, LA, Cin, Cout = 77, 14, 256, 256
+    a = torch.randn(M * LA, Cin).cuda()
+    _, a_split = ops.act(a, None, pool=1, slope=1.0, want_plain=False, want_split=True, parts=ops.SPLIT_F16)
+    ws, out_scale = _tc_weights((torch.randn(Cout, Cin, 3) * 0.05).cuda(), True)
+    b_pl, pl = guarded((M * LA // 2, Cout))
+    ops.conv_tc(a_split, ws, None, M, LA, LA, 3, 1, pool=2, want_plain=True, want_split=True, out_scale=out_scale, plain_out=pl)
+    torch.cuda.synchronize()
+    assert intact(b_pl, pl.numel()) and not bool((pl == canary).any())
