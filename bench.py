@@ -114,6 +114,20 @@ def build_model(seed=0):
     return m.eval()
 
 
+def stream_config(args, B, total_seqs, N, world, use_graph):
+    """The `config` object of the streaming workload: ONE definition for our arm and the reference arm (which times a bounded
+    sample of the same workload on the host cores and says so in `cpu_baseline.sample`)."""
+    return {"workload": "DR-SPAAM streaming inference, %s %s-shaped sequences (%d pts), "
+                        "cutout+backbone+attention memory+heads+NMS per scan"
+                        % ("%d independent sequences in total, sharded round-robin over %d GPU(s)," % (total_seqs, world)
+                           if args.scaling == "strong" else "%d independent sequences per GPU," % B, args.shape.upper(), N),
+            "sequences_per_gpu": B, "sequences_total": total_seqs, "cuda_graph": use_graph, "points": N,
+            "cutout_pts": CUTOUT_KW["num_cutout_pts"], "window": WINDOW, "alpha": ALPHA, "precision": args.precision,
+            "weights": "random-init",
+            "l2_policy": "inputs larger than L2: per step the path streams %.1f GB of attention memory "
+                         "and features (L2 = 126 MB)" % (3 * B * N * 3584 * 4 / 1e9)}
+
+
 # ----------------------------------------------------------------------------- CPU reference path
 def reference_modules():
     """(utils module, dr_spaam module) of the UNMODIFIED reference (baseline/_ref, installed by baseline/install_reference.py
@@ -513,14 +527,7 @@ def run_ours(args):
                                       "fp32-simt": "f32", "tf32x3": "f32 operands, TF32 tensor-core accumulation (1e-4)",
                                       "tf32": "tf32"}[args.precision], "data": "synthetic",
         "impl": "ours",
-        "config": {"workload": "DR-SPAAM streaming inference, %s %s-shaped sequences (%d pts), "
-                               "cutout+backbone+attention memory+heads+NMS per scan"
-                               % ("%d independent sequences in total, sharded round-robin over %d GPU(s)," % (total_seqs, world)
-                                  if args.scaling == "strong" else "%d independent sequences per GPU," % B, args.shape.upper(), N),
-                   "sequences_per_gpu": B, "sequences_total": total_seqs, "cuda_graph": use_graph, "points": N, "cutout_pts": CUTOUT_KW["num_cutout_pts"], "window": WINDOW,
-                   "alpha": ALPHA, "precision": args.precision, "weights": "random-init",
-                   "l2_policy": "inputs larger than L2: per step the path streams %.1f GB of attention memory "
-                                "and features (L2 = 126 MB)" % (3 * B * N * 3584 * 4 / 1e9)},
+        "config": stream_config(args, B, total_seqs, N, world, use_graph),
         "e2e": {"value": total_seqs * K / (ms_e2e / 1e3), "unit": "scans/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K, "detections_in_timed_region": n_det,
                 "api": "StreamingDetector.step(host ranges) -> host detections"},
@@ -749,7 +756,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    seqs_per_step = 4                      # bounded sample: one step = one scan of 4 sequences
+    from planar_optical_flow_b200 import synth
+
+    # the workload is the other arm's (same `config`); what is TIMED is a bounded sample of it: one step = one scan of 4 sequences
+    world_ref = max(args.gpus, 1)
+    B_ref = len(range(0, args.sequences, world_ref)) if args.scaling == "strong" else args.sequences
+    total_ref = args.sequences if args.scaling == "strong" else world_ref * args.sequences
+    n_pts = len(synth.phi_for(args.shape))
+    seqs_per_step = 4
     n = args.steps * seqs_per_step
     v, cores, timed, stage = cpu_reference_scans_per_s(args.shape, n, warmup=args.warmup, sequences=seqs_per_step)
     kind = cpu_reference_kind()
@@ -761,8 +775,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * seqs_per_step / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DR-SPAAM streaming inference, %s-shaped sequences, CPU reference path" % args.shape.upper(),
-                   "sample_sequences_per_step": seqs_per_step},
+        "config": stream_config(args, B_ref, total_ref, n_pts, world_ref, B_ref <= 16 or args.graph),
         "cpu_baseline": {"value": v, "unit": "scans/s", "cores": cores, "kind": kind, "sample": sample,
                          "stage_ms_per_scan": stage},
         "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
