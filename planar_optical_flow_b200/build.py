@@ -59,21 +59,36 @@ def build_variant(name, defines):
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source of the package into libpof.so.  Returns its path."""
+    """Compile every CUDA source of the package into libpof.so.  Returns its path.
+
+    Safe under several processes at once (the ranks of a torchrun job importing the package together): the build is
+    serialised by a lock file, staleness is re-checked under the lock, and the binary is replaced atomically."""
     if not force and not _stale():
         return LIB_PATH
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH + ".tmp"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    log = os.path.join(PKG_DIR, "build.log")
-    with open(log, "w") as f:
-        f.write(" ".join(cmd) + "\n" + proc.stdout)
-    if proc.returncode != 0:
-        sys.stderr.write(proc.stdout)
-        raise RuntimeError("nvcc failed (exit %d); see %s" % (proc.returncode, log))
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
-    if verbose:
-        sys.stdout.write(proc.stdout)
+    import fcntl
+
+    with open(os.path.join(PKG_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():          # another process built it while this one waited
+                return LIB_PATH
+            tmp = "%s.tmp.%d" % (LIB_PATH, os.getpid())
+            cmd = [find_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-o", tmp]
+            cmd += [os.path.join(CSRC, s) for s in SOURCES]
+            proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            log = os.path.join(PKG_DIR, "build.log")
+            with open(log, "w") as f:
+                f.write(" ".join(cmd) + "\n" + proc.stdout)
+            if proc.returncode != 0:
+                sys.stderr.write(proc.stdout)
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed (exit %d); see %s" % (proc.returncode, log))
+            os.replace(tmp, LIB_PATH)
+            if verbose:
+                sys.stdout.write(proc.stdout)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
