@@ -13,8 +13,12 @@ What changed underneath:
     (csrc/pof_gate.cu) through `ops.gate`, differentiable via its own backward kernels;
   * no neighbour table is cached on the module, so one instance serves any N
     (the reference locks an instance to its first N, SURVEY.md D9);
-  * the 1-D conv backbone stays on PyTorch/cuDNN: it is the only dense contraction.
-The modules only run on CUDA tensors; there is no CPU path.
+  * the convolutions themselves stay on PyTorch/cuDNN (the only dense contraction; the streaming engine has its own tcgen05
+    kernel for inference, engine.py); in the training branch what runs between them - batch-norm with batch statistics,
+    LeakyReLU, the block's max-pool - is libpof's one fused operator (`ops.bn_act_pool`, csrc/pof_bnact.cu), the first
+    layer (one input channel) has its own forward / weight-gradient kernels, and `scans_per_call` scans of a sample share
+    one call per layer with per-scan batch statistics.
+The gate only runs on CUDA tensors; there is no CPU path for it.
 """
 import os
 from math import ceil
