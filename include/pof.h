@@ -91,6 +91,7 @@ POF_API int pof_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * ------------------------------------------------------------------------- */
 #define POF_CUTOUT_EXACT 0   /* every rounding of the reference reproduced (modulo the arctangent) */
 #define POF_CUTOUT_FAST 1    /* fixed-point index line + float32 blend: within ~3e-6 of EXACT        */
+#define POF_CUTOUT_EXACT_PIECES 2   /* EXACT on the first (piece-per-thread) kernel: same bits, kept as a cross-check */
 
 POF_API size_t pof_cutout_ws_bytes(int B);
 

@@ -31,6 +31,7 @@
 //
 // Area mode needs `s_area = ceil(max_span / P)` over a whole reference call (utils.py:308) =
 // over one sample b here: cutout_span_kernel (one CTA per b) reduces it into `ws` first.
+#include <math_constants.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -118,10 +119,29 @@ __device__ __forceinline__ Consts make_consts(const CutoutArgs& a) {
 }
 
 // (v - d) / window_depth, or v itself when not centred, rounded to float  (:328-334)
+// An infinite range (no return) is in the reference's domain: (inf - d) / depth = inf, where the three-operation division
+// would produce inf - inf.
+__device__ __forceinline__ double div_depth(double x, const Consts& c) {
+    const double q = div_by(x, c.depth, c.inv_depth);
+    return fabs(x) == CUDART_INF ? x : q;
+}
 __device__ __forceinline__ float finish(double v, float range, const Consts& c, int centered) {
-    if (centered) v = div_by(__dsub_rn(v, (double)range), c.depth, c.inv_depth);
+    if (centered) v = div_depth(__dsub_rn(v, (double)range), c);
     return (float)v;
 }
+// np.clip = minimum(maximum(x, lo), hi) propagates a NaN from ANY of its operands (an infinite reference range makes
+// both bounds NaN after centring; inf - inf inside a blend makes the sample NaN): max.NaN / min.NaN, not fmaxf / fminf.
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float fmin_nan(float a, float b) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float clip_nan(float v, float lo, float hi) { return fmin_nan(fmax_nan(v, lo), hi); }
 
 // Range, half-angle, step and start angle of row (b, s, m)   (:274-285)
 // FAST_ATAN (float32 arctangent, 1-2 ulp) was measured: it saves 9 % of the FAST kernel's instructions but the
@@ -238,7 +258,7 @@ __device__ __forceinline__ float linear_exact(const RowGeom& g, const float* src
     const float v_lo = src[lo];
     const float v_hi = src[min(lo + 1, nm1)];
     const double v = __dadd_rn((double)v_lo, __dmul_rn(ratio, (double)__fsub_rn(v_hi, v_lo)));
-    return clip_final(finish(v, g.range, c, centered), g);
+    return clip_nan(finish(v, g.range, c, centered), g.lo_f, g.hi_f);
 }
 
 __device__ __forceinline__ float area_exact(const RowGeom& g, const float* src, int k, const Consts& c, int nm1, int centered) {
@@ -253,7 +273,7 @@ __device__ __forceinline__ float area_exact(const RowGeom& g, const float* src, 
         const int j = min(max(__double2int_rn(ia), 0), nm1);
         acc = (t == 0) ? src[j] : __fadd_rn(acc, src[j]);
     }
-    return clip_final(finish((double)__fdiv_rn(acc, (float)g.s_area), g.range, c, centered), g);
+    return clip_nan(finish((double)__fdiv_rn(acc, (float)g.s_area), g.range, c, centered), g.lo_f, g.hi_f);
 }
 
 // FAST: `fx` is the sample's index in 32.32 fixed point; out = clip(v*scale + bias) with
@@ -325,7 +345,8 @@ __global__ void __launch_bounds__(kThreads) cutout_kernel(const CutoutArgs a) {
         // FINAL float against the final values of the two bounds is the same function  (:327-334)
         g.lo_f = finish((double)(g.range - a.depth_f), g.range, c, a.centered);
         g.hi_f = finish((double)(g.range + a.depth_f), g.range, c, a.centered);
-        g.pad_f = fminf(fmaxf(finish(a.pad, g.range, c, a.centered), g.lo_f), g.hi_f);      // :326
+        g.pad_f = FAST ? fminf(fmaxf(finish(a.pad, g.range, c, a.centered), g.lo_f), g.hi_f)      // :326
+                       : clip_nan(finish(a.pad, g.range, c, a.centered), g.lo_f, g.hi_f);
         if (FAST) {
             g.fx_base = to_fixed(i0);
             g.fx_slope = to_fixed((double)g.step * c.inv_pitch);
@@ -935,6 +956,254 @@ __global__ void __launch_bounds__(POF_SCAN_LB_THREADS, POF_SCAN_LB_BLOCKS) cutou
     if (!MULTI && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// ---- EXACT numerics, one CTA per scan (round 2) ---------------------------------------------------------------
+// The piece-per-thread EXACT kernel above issues ~60 instructions per sample: 14 double operations, five 64-bit
+// conversions (F2I/I2F/F2F run at a quarter of the double rate) and ~40 slots of per-piece bookkeeping.  This is the
+// same arithmetic, operation for operation, in the scan kernel's shape - a lane owns a row and walks its samples, a
+// finished 32-row group leaves as one bulk store - with the conversions taken out of the sample loop:
+//   * the scan is staged as DOUBLE pairs (v[i], (double)(v[i+1] - v[i])): one LDS.128 per sample, no F2F;
+//   * floor(idx) is the low word of RD(idx + 1.5 * 2^52) and its double is that sum minus the constant (both exact for
+//     0 <= idx < 2^31): no F2I / I2F.  Only rows whose first and last index lie inside the scan take this loop (the index
+//     is monotone along a row); rows that leave the scan and area-resampled rows call linear_exact / area_exact;
+//   * (double)k comes from a P-entry table in shared memory;
+//   * for a power-of-two window_depth the correctly rounded division is one product.
+// 12 double operations and one F2F.F32.F64 per sample remain.
+constexpr double kFloorMagic = 6755399441055744.0;      // 1.5 * 2^52
+
+struct ExactRow {
+    double start, step_d, range_d;
+    float lo_f, hi_f;
+};
+
+// MODE 0: not centred; 1: centred, window_depth a power of two; 2: centred, any window_depth
+template <int MODE>
+__device__ __forceinline__ void exact_row_inside(const ExactRow& r, const Consts& c, const double2* dpairs, const double* ktab,
+                                                 unsigned rot, int nchunks, float* dst) {
+#pragma unroll 1
+    for (int j = 0; j < nchunks; ++j) {
+        int ch = j + (int)rot;
+        if (ch >= nchunks) ch = 0;                            // rotated chunk order: conflict-free 16-byte stores
+        const int k0 = ch << 2;
+        float res[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double ang = fma(ktab[k0 + u], r.step_d, r.start);                                     // :286-288
+            const double idx = div_by(__dsub_rn(ang, c.origin), c.pitch, c.inv_pitch);
+            const double t = __dadd_rd(idx, kFloorMagic);
+            const double ratio = __dsub_rn(idx, __dsub_rn(t, kFloorMagic));                              // :292-294
+            const double2 vd = dpairs[__double2loint(t)];
+            double v = __dadd_rn(vd.x, __dmul_rn(ratio, vd.y));                                          // :300
+            if (MODE != 0) {
+                v = __dsub_rn(v, r.range_d);                                                             // :329-330
+                v = MODE == 1 ? __dmul_rn(v, c.inv_depth) : div_depth(v, c);
+            }
+            res[u] = clip_nan((float)v, r.lo_f, r.hi_f);
+        }
+        *reinterpret_cast<float4*>(dst + k0) = make_float4(res[0], res[1], res[2], res[3]);
+    }
+}
+
+template <typename PhiT, bool MULTI>
+__global__ void __launch_bounds__(kScanWarpsMax * 32, 4) cutout_scan_exact_kernel(const CutoutArgs a, const int mode) {
+    extern __shared__ __align__(16) float smem_f[];          // pairs [N+1] double2 | (double)k [P] | ranges [N] | per-warp tiles [32][P] | (MULTI, !fixed) reference ranges [N]
+    __shared__ double warp_span[kScanWarpsMax];
+    __shared__ float warp_min[kScanWarpsMax];
+    const Consts c = make_consts<PhiT>(a);
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const int b = MULTI ? blockIdx.x / a.S : blockIdx.x;
+    const int sc = MULTI ? blockIdx.x - b * a.S : 0;
+    const int nm1 = a.N - 1;
+    const int P = a.P;
+    double2* dpairs = reinterpret_cast<double2*>(smem_f);
+    double* ktab = reinterpret_cast<double*>(dpairs + (a.N + 1));
+    float* vals = reinterpret_cast<float*>(ktab + P);
+    float* tile = vals + ((a.N + 3) & ~3) + (size_t)warp * 32 * P;
+    const bool other_ref = MULTI && !a.fixed && sc != a.S - 1;
+    float* dvals_w = other_ref ? vals + ((a.N + 3) & ~3) + (size_t)nwarps * 32 * P : vals;
+    const float* dvals = dvals_w;
+    const float* scan = a.scans + ((size_t)b * a.S + sc) * a.N;
+    const PhiT* phi = reinterpret_cast<const PhiT*>(a.phi);
+    const size_t row0 = ((size_t)b * a.S + sc) * a.M;
+    const float* ha_in = a.half_alpha_in ? a.half_alpha_in + row0 : nullptr;
+    float* ha_out = a.half_alpha_out ? a.half_alpha_out + row0 : nullptr;
+    const double Pd = (double)P;
+
+    // ---- stage the scan; entry N repeats beam N-1 (inds_ct_high is clipped at N-1, :293) -----------------
+    float dmin = 3.0e38f;
+    for (int k = tid; k < P; k += T) ktab[k] = (double)k;
+    for (int i = tid; i <= a.N; i += T) {
+        const float v0 = __ldg(scan + min(i, nm1)), v1 = __ldg(scan + min(i + 1, nm1));
+        dpairs[i] = make_double2((double)v0, (double)__fsub_rn(v1, v0));
+        if (i < a.N) vals[i] = v0;
+        if (!MULTI && a.stride == 1) dmin = fminf(dmin, fmaxf(v0, 1e-2f));
+    }
+    if (other_ref) {
+        const float* ref = a.scans + ((size_t)b * a.S + (a.S - 1)) * a.N;
+        for (int i = tid; i < a.N; i += T) dvals_w[i] = __ldg(ref + i);
+    }
+    if (!MULTI && a.stride != 1)
+        for (int m = tid; m < a.M; m += T) dmin = fminf(dmin, fmaxf(__ldg(scan + m * a.stride), 1e-2f));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    if (lane == 0) warp_min[warp] = dmin;
+    __syncthreads();
+
+    // ---- the sample's oversampling factor (:304-308) ---------------------------------------------------------
+    int s_area = 0;
+    if (MULTI) {                                             // reduced over all scans of the sample by the span kernels
+        const double best = a.span_max[b];
+        if (a.area_mode && best > Pd) s_area = (int)ceil(__ddiv_rn(best, Pd));
+    } else if (a.area_mode || a.s_area_out) {                // S == 1: from the rows nearest to the sensor (see cutout_span_scan_kernel)
+        dmin = warp_min[0];
+        for (int w = 1; w < nwarps; ++w) dmin = fminf(dmin, warp_min[w]);
+        const float near = ha_in ? 3.0e38f : dmin * 1.001f;
+        double best = 0.0;
+        for (int m = tid; m < a.M; m += T) {
+            const int i = m * a.stride;
+            const float dc = fmaxf(vals[i], 1e-2f);
+            if (dc <= near) {
+                const float ha = ha_in ? __ldg(ha_in + m) : atan_f32(__fdiv_rn(a.half_width, dc));
+                const float step = __fdiv_rn(2.0f * ha, (float)(P - 1));
+                const double start = (double)(phi[i] - (PhiT)ha);
+                const double span = __dsub_rn(sample_index(start, step, P - 1, c), sample_index(start, step, 0, c));
+                if (span > best) best = span;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double other = __shfl_xor_sync(0xffffffffu, best, o);
+            if (other > best) best = other;
+        }
+        if (lane == 0) warp_span[warp] = best;
+        __syncthreads();
+        best = lane < nwarps ? warp_span[lane] : 0.0;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            const double other = __shfl_xor_sync(0xffffffffu, best, o);
+            if (other > best) best = other;
+        }
+        best = __shfl_sync(0xffffffffu, best, 0);
+        if (a.area_mode && best > Pd) s_area = (int)ceil(__ddiv_rn(best, Pd));
+        if (tid == 0) {
+            a.span_max[b] = best;
+            if (a.s_area_out) a.s_area_out[b] = s_area;
+        }
+    }
+
+    const unsigned rot = nchunks_rot(P, lane);
+    const int nchunks = P >> 2;
+    float* out_b = a.out + (MULTI ? ((size_t)b * a.M * a.S + sc) * P : (size_t)b * a.M * P);
+    bool store_pending = false;
+
+    for (int m0 = warp * 32; m0 < a.M; m0 += T) {
+        const int rows_here = min(32, a.M - m0);
+        const bool valid = lane < rows_here;
+        bool is_area = false, inside = false;
+        RowGeom g;
+        g.start = 0.0; g.step = g.step_a = g.range = g.lo_f = g.hi_f = g.pad_f = 0.f; g.s_area = 0;
+        if (valid) {                                          // :274-285, as in cutout_kernel's phase 1
+            const int m = m0 + lane, i = m * a.stride;
+            g.range = dvals[i];
+            const float ratio = __fdiv_rn(a.half_width, fmaxf(g.range, 1e-2f));
+            const float ha = ha_in ? __ldg(ha_in + m) : atan_f32(ratio);                       // :279
+            if (ha_out) ha_out[m] = ha;
+            const float two_ha = 2.0f * ha;
+            g.step = __fdiv_rn(two_ha, (float)(P - 1));                                        // :282
+            g.start = (double)(phi[i] - (PhiT)ha);                                             // :284-285
+            const double i0 = sample_index(g.start, g.step, 0, c);
+            const double i1 = sample_index(g.start, g.step, P - 1, c);
+            if (s_area > 0 && __dsub_rn(i1, i0) > Pd) {                                        // :304-310
+                is_area = true;
+                g.s_area = s_area;
+                g.step_a = __fdiv_rn(two_ha, (float)(s_area * P - 1));
+            }
+            inside = g.step >= 0.f && i0 >= 0.0 && i1 <= c.last;     // the index is monotone in k: every sample lies in the scan
+            g.lo_f = finish((double)(g.range - a.depth_f), g.range, c, a.centered);            // :327-334 (see cutout_kernel)
+            g.hi_f = finish((double)(g.range + a.depth_f), g.range, c, a.centered);
+            g.pad_f = clip_nan(finish(a.pad, g.range, c, a.centered), g.lo_f, g.hi_f);         // :326
+        }
+        if (!MULTI && store_pending) {                        // the previous group's tile must have been read by the TMA
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+        }
+
+        // ---- two-tap rows ---------------------------------------------------------------------------
+        if (valid && !is_area) {
+            float* dst = tile + lane * P;
+            if (inside) {
+                ExactRow r;
+                r.start = g.start; r.step_d = (double)g.step; r.range_d = (double)g.range; r.lo_f = g.lo_f; r.hi_f = g.hi_f;
+                if (mode == 1) exact_row_inside<1>(r, c, dpairs, ktab, rot, nchunks, dst);
+                else if (mode == 0) exact_row_inside<0>(r, c, dpairs, ktab, rot, nchunks, dst);
+                else exact_row_inside<2>(r, c, dpairs, ktab, rot, nchunks, dst);
+            } else {
+#pragma unroll 1
+                for (int k = 0; k < P; ++k) dst[k] = linear_exact(g, vals, k, c, nm1, a.centered);
+            }
+        }
+
+        // ---- area rows of the group: one at a time, the lanes along its samples (:310-323) --------------
+        unsigned m_area = __ballot_sync(0xffffffffu, valid && is_area);
+        while (m_area) {
+            const int src = __ffs(m_area) - 1;
+            m_area &= m_area - 1;
+            RowGeom r;
+            r.start = __shfl_sync(0xffffffffu, g.start, src);
+            r.step = __shfl_sync(0xffffffffu, g.step, src);
+            r.step_a = __shfl_sync(0xffffffffu, g.step_a, src);
+            r.range = __shfl_sync(0xffffffffu, g.range, src);
+            r.lo_f = __shfl_sync(0xffffffffu, g.lo_f, src);
+            r.hi_f = __shfl_sync(0xffffffffu, g.hi_f, src);
+            r.pad_f = __shfl_sync(0xffffffffu, g.pad_f, src);
+            r.s_area = s_area;
+            float* row = tile + src * P;
+            for (int k = lane; k < P; k += 32) row[k] = area_exact(r, vals, k, c, nm1, a.centered);
+        }
+
+        if (MULTI) {
+            __syncwarp();
+            const int q = P >> 2;
+            for (int t = lane; t < rows_here * q; t += 32) {
+                const int r = t / q, c4 = t - r * q;
+                st_stream_f4(reinterpret_cast<float4*>(out_b + ((size_t)(m0 + r) * a.S) * P + 4 * c4),
+                             *reinterpret_cast<const float4*>(tile + r * P + 4 * c4));
+            }
+            __syncwarp();
+        } else {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(out_b + (unsigned)(m0 * P), tile, (unsigned)(rows_here * P) * 4u);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            store_pending = true;
+        }
+    }
+    if (!MULTI && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+template <typename PhiT, bool MULTI>
+bool launch_cutout_scan_exact(const CutoutArgs& a, cudaStream_t stream, int* status) {
+    const int warps = kScanWarpsMax;
+    const size_t smem = sizeof(double2) * (size_t)(a.N + 1) + sizeof(double) * (size_t)a.P +
+                        ((size_t)((a.N + 3) & ~3) + (size_t)warps * 32 * a.P + (MULTI && !a.fixed ? (size_t)((a.N + 3) & ~3) : 0)) * sizeof(float);
+    if (smem > 110 * 1024) return false;
+    static bool attr_set[2][2][64] = {{{false}}};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    const int which = sizeof(PhiT) == 8;
+    if (dev < 64 && !attr_set[which][MULTI][dev]) {
+        if (cudaFuncSetAttribute(cutout_scan_exact_kernel<PhiT, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess) return false;
+        attr_set[which][MULTI][dev] = true;
+    }
+    int depth_exp = 0;
+    const int mode = !a.centered ? 0 : (frexp(a.depth, &depth_exp) == 0.5 ? 1 : 2);
+    cutout_scan_exact_kernel<PhiT, MULTI><<<MULTI ? a.B * a.S : a.B, warps * 32, smem, stream>>>(a, mode);
+    const cudaError_t e = cudaGetLastError();
+    *status = e == cudaSuccess ? POF_OK : cuda_fail(e, "cutout_scan_exact_kernel launch");
+    return true;
+}
+
 int scan_warps_for(int M) {
     static int forced = -1;
     if (forced < 0) {
@@ -1016,8 +1285,8 @@ int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64, int B, i
                 "pof_cutout_fwd: need B>=0, S>=1, N>=2, stride>=1 (got B=%d S=%d N=%d stride=%d)", B, S, N, stride);
     POF_REQUIRE(P >= 4 && (P % 4) == 0 && P <= 1024, POF_ERR_BAD_SHAPE,
                 "pof_cutout_fwd: num_cutout_pts must be a multiple of 4 in [4,1024] (got %d)", P);
-    POF_REQUIRE(numerics == POF_CUTOUT_EXACT || numerics == POF_CUTOUT_FAST, POF_ERR_BAD_PARAM,
-                "pof_cutout_fwd: numerics must be POF_CUTOUT_EXACT or POF_CUTOUT_FAST");
+    POF_REQUIRE(numerics == POF_CUTOUT_EXACT || numerics == POF_CUTOUT_FAST || numerics == POF_CUTOUT_EXACT_PIECES, POF_ERR_BAD_PARAM,
+                "pof_cutout_fwd: numerics must be POF_CUTOUT_EXACT, POF_CUTOUT_FAST or POF_CUTOUT_EXACT_PIECES");
     POF_REQUIRE(window_depth > 0.0, POF_ERR_BAD_PARAM, "pof_cutout_fwd: window_depth must be positive");
     POF_REQUIRE((long long)B * S * N < (1ll << 31), POF_ERR_BAD_SHAPE, "pof_cutout_fwd: B*S*N must fit int32");
     POF_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, POF_ERR_BAD_PARAM, "pof_cutout_fwd: out must be 16-byte aligned");
@@ -1054,6 +1323,10 @@ int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64, int B, i
         int status = POF_OK;
         if (phi_is_f64 ? launch_cutout_scan<double, false>(a, stream, &status) : launch_cutout_scan<float, false>(a, stream, &status)) return status;
     }
+    if (numerics == POF_CUTOUT_EXACT && S == 1) {                  // the same shape with the reference's own roundings
+        int status = POF_OK;
+        if (phi_is_f64 ? launch_cutout_scan_exact<double, false>(a, stream, &status) : launch_cutout_scan_exact<float, false>(a, stream, &status)) return status;
+    }
     if (area_mode || s_area_out) {
         if (!s_area_out && !half_alpha_in && !half_alpha_out) {       // one CTA per scan, nearest rows only, atomic max per sample
             POF_CUDA(cudaMemsetAsync(a.span_max, 0, (size_t)B * sizeof(double), stream));
@@ -1069,6 +1342,10 @@ int pof_cutout_fwd(const float* scans, const void* phi, int phi_is_f64, int B, i
     if (numerics == POF_CUTOUT_FAST && S > 1 && !coarse && N < kMaxStagedPts) {      // one CTA per scan (b, s) of the training samples
         int status = POF_OK;
         if (phi_is_f64 ? launch_cutout_scan<double, true>(a, stream, &status) : launch_cutout_scan<float, true>(a, stream, &status)) return status;
+    }
+    if (numerics == POF_CUTOUT_EXACT && S > 1) {
+        int status = POF_OK;
+        if (phi_is_f64 ? launch_cutout_scan_exact<double, true>(a, stream, &status) : launch_cutout_scan_exact<float, true>(a, stream, &status)) return status;
     }
     if (numerics == POF_CUTOUT_FAST) return phi_is_f64 ? launch_cutout<double, true>(a, stream) : launch_cutout<float, true>(a, stream);
     return phi_is_f64 ? launch_cutout<double, false>(a, stream) : launch_cutout<float, false>(a, stream);

@@ -466,8 +466,11 @@ class StreamingDetector:
         with self._precision():
             with self._timed("cutout"):      # one launch for all B sequences: [B, N, 1, P]
                 cutouts = ops.cutout(scans.unsqueeze(1), self.phi, fast=self.cutout_fast, **self.cutout_kwargs)
-            # FAST: cutout_scan_kernel does the span reduction, the half-angles and the samples in one launch
-            self.kernel_launches += 1 if self.cutout_fast else (2 if self.cutout_kwargs.get("area_mode") else 1)
+            # one CTA per scan does the span reduction, the half-angles and the samples in one launch (both numerics); EXACT on
+            # a scan too long for its shared-memory staging (16 B per beam) falls back to the span + pieces kernels
+            P = int(self.cutout_kwargs.get("num_cutout_pts", 48))
+            one_launch = self.cutout_fast or 16 * (N + 1) + 8 * P + 4 * ((N + 3) & ~3) + 512 * P <= 110 * 1024
+            self.kernel_launches += 1 if one_launch else (2 if self.cutout_kwargs.get("area_mode") else 1)
             chunk = self._chunk_channels_last if self.channels_last else self._chunk_ncl
             for b0 in range(0, B, self.seq_chunk):
                 chunk(cutouts, b0, min(B, b0 + self.seq_chunk), first, prev, nxt, pred_cls, pred_reg, feat_fused)

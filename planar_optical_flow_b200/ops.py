@@ -21,11 +21,13 @@ def _ptr(t):
 # --------------------------------------------------------------------------- cutout
 def cutout(scans, phi, stride=1, centered=True, fixed=False, window_width=1.66, window_depth=1.0,
            num_cutout_pts=48, padding_val=29.99, area_mode=False, out=None, return_s_area=False,
-           half_alpha=None, return_half_alpha=False, fast=False):
+           half_alpha=None, return_half_alpha=False, fast=False, exact_pieces=False):
     """Batched `scans_to_cutout` (reference: src/utils/utils.py:259-334).
 
     scans [B, S, N] float32 CUDA, phi [N] float32|float64 CUDA  ->  [B, M, S, P] float32,
     M = ceil(N / stride).  Each b is one independent reference call (its own `s_area`).
+    `fast` selects POF_CUTOUT_FAST; `exact_pieces` runs the EXACT arithmetic on the first (piece-per-thread) kernel,
+    which the tests hold against the default EXACT kernel bit for bit.
     """
     require_cuda_tensor(scans, "scans", torch.float32)
     require_cuda_tensor(phi, "phi")
@@ -57,7 +59,7 @@ def cutout(scans, phi, stride=1, centered=True, fixed=False, window_width=1.66, 
         ha_out = torch.empty((B, S, M), dtype=torch.float32, device=dev) if return_half_alpha else None
         check(L.pof_cutout_fwd(_ptr(scans), _ptr(phi), int(phi.dtype == torch.float64), B, S, N, int(stride), P,
                                float(window_width), float(window_depth), float(padding_val),
-                               int(bool(fixed)), int(bool(centered)), int(bool(area_mode)), int(bool(fast)),
+                               int(bool(fixed)), int(bool(centered)), int(bool(area_mode)), 1 if fast else (2 if exact_pieces else 0),
                                _ptr(out), _ptr(s_area), _ptr(half_alpha), _ptr(ha_out),
                                _ptr(ws), ws_bytes, current_stream_ptr(dev)),
               "pof_cutout_fwd")

@@ -46,11 +46,11 @@ def _ulp_distance(a, b):
     return np.abs(ia - ib)
 
 
-def _gpu_cutout(scans, phi, kw, stride=1, half_alpha=None, fast=False):
+def _gpu_cutout(scans, phi, kw, stride=1, half_alpha=None, fast=False, exact_pieces=False):
     s = torch.from_numpy(np.ascontiguousarray(scans, np.float32)).cuda().unsqueeze(0)
     ha = None if half_alpha is None else torch.from_numpy(np.ascontiguousarray(half_alpha, np.float32)).cuda().unsqueeze(0)
     out, ha_used = ops.cutout(s, torch.from_numpy(np.ascontiguousarray(phi)).cuda(), stride=stride,
-                              half_alpha=ha, return_half_alpha=True, fast=fast, **kw)
+                              half_alpha=ha, return_half_alpha=True, fast=fast, exact_pieces=exact_pieces, **kw)
     return out[0].cpu().numpy(), ha_used[0].cpu().numpy()
 
 
@@ -802,6 +802,88 @@ def test_cutout_span_reduction_paths_agree(fast, fixed):
         full, s_area = ops.cutout(scans, phi_d, fast=fast, return_s_area=True, **kw)
         assert torch.equal(plain, full), (S, int((plain != full).sum()))
         assert int(s_area.max()) >= 4 and int(s_area.min()) >= 0
+
+
+@pytest.mark.parametrize("flags", [dict(), dict(fixed=False), dict(centered=False), dict(area_mode=False), dict(window_depth=0.3),
+                                   dict(window_width=1.66, window_depth=1.0, num_cutout_pts=48), dict(num_cutout_pts=4),
+                                   dict(padding_val=float("inf"))])
+@pytest.mark.parametrize("phi_dtype", [np.float32, np.float64])
+def test_cutout_exact_kernels_are_bit_equal(flags, phi_dtype):
+    """The EXACT arithmetic has two kernels: one CTA per scan (what a call runs) and the first piece-per-thread one
+    (`exact_pieces`, the fallback for scans that do not fit shared memory).  Same operations in the same order, so the same
+    bits - NaN patterns included - on structured, adversarial, edge, all-area, non-finite and out-of-scan inputs, S = 1 and
+    S = 3, strided and ragged."""
+    kw = dict(CFG, **flags)
+    for shape in ("jrdb", "drow"):
+        phi = synth.phi_for(shape).astype(phi_dtype)
+        n = len(phi)
+        phi_d = torch.from_numpy(phi).cuda()
+        for S in (1, 3):
+            rows = [synth.structured_sequence(S, n, seed=3, phi=phi), synth.adversarial_scans(S, n, seed=4),
+                    synth.edge_scans(n, seed=5)[:S], np.full((S, n), 0.2, np.float32), np.full((S, n), 29.99, np.float32),
+                    np.linspace(0.004, 0.6, n, dtype=np.float32)[None].repeat(S, 0)]
+            rows[3][:, ::7] = 3.0
+            bad = synth.adversarial_scans(S, n, seed=6)
+            bad[:, 5] = np.inf
+            bad[:, 17:19] = np.inf
+            bad[:, 40] = np.nan
+            bad[:, n - 1] = np.inf
+            rows.append(bad)
+            scans = torch.from_numpy(np.stack(rows)).cuda()
+            for stride in (1, 3):
+                a, sa = ops.cutout(scans, phi_d, stride=stride, return_s_area=True, **kw)
+                b, sb = ops.cutout(scans, phi_d, stride=stride, return_s_area=True, exact_pieces=True, **kw)
+                assert torch.equal(sa, sb)
+                assert torch.equal(a.view(torch.int32), b.view(torch.int32)), (shape, S, stride, int((a.view(torch.int32) != b.view(torch.int32)).sum()))
+                a2 = ops.cutout(scans, phi_d, stride=stride, **kw)               # the plain call (per-scan span reduction)
+                assert torch.equal(a2.view(torch.int32), a.view(torch.int32))
+    for n in (2, 3, 5, 33, 129):
+        phi = synth.drow_phi(n).astype(phi_dtype)
+        scans = torch.from_numpy(synth.adversarial_scans(2, n, seed=n)[None]).cuda()
+        a = ops.cutout(scans, torch.from_numpy(phi).cuda(), **kw)
+        b = ops.cutout(scans, torch.from_numpy(phi).cuda(), exact_pieces=True, **kw)
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32)), n
+
+
+@pytest.mark.parametrize("flags", [dict(), dict(fixed=False), dict(centered=False), dict(window_depth=0.3), dict(area_mode=False)])
+@pytest.mark.parametrize("S", [1, 3])
+def test_cutout_infinite_ranges_match_the_reference(S, flags):
+    """`inf` (no return) is inside the reference's domain: a blend across an infinite beam is inf or NaN (inf - inf), a row whose
+    own range is infinite has NaN clip bounds after centring, and np.clip propagates every NaN (utils.py:300, 327-330).  Both EXACT
+    kernels reproduce the NaN and inf masks of the oracle (itself equal to the unmodified reference on these inputs) and the
+    finite samples to 1e-5."""
+    kw = dict(CFG, **flags)
+    for shape in ("jrdb", "drow"):
+        phi = synth.phi_for(shape)
+        n = len(phi)
+        scans = synth.adversarial_scans(S, n, seed=6)
+        scans[:, 5] = np.inf
+        scans[:, 17:19] = np.inf
+        scans[:, n // 2] = np.inf
+        scans[:, n - 1] = np.inf
+        with np.errstate(all="ignore"):
+            want = ocut.scans_to_cutout(scans, phi, **kw)
+            ha_ref = ocut.window_half_angle(scans, 1, kw["fixed"], kw["window_width"])
+        assert np.isnan(want).sum() > 50
+        finite = np.isfinite(want)
+        scale = float(np.abs(want[finite]).max())
+        for pieces in (False, True):
+            got, _ = _gpu_cutout(scans, phi, kw, half_alpha=ha_ref, exact_pieces=pieces)
+            assert np.array_equal(np.isnan(got), np.isnan(want)), (shape, pieces, int((np.isnan(got) != np.isnan(want)).sum()))
+            assert np.array_equal(np.isinf(got), np.isinf(want)) and np.array_equal(got[np.isinf(want)], want[np.isinf(want)])
+            assert np.abs(got[finite].astype(np.float64) - want[finite]).max() <= REL_TOL * scale
+            assert (got[finite] == want[finite]).mean() >= 0.9999
+
+
+def test_cutout_exact_kernel_at_full_size_equals_pieces_kernel():
+    """BASELINE configs[1] size (4096 JRDB scans): both EXACT kernels, every sample."""
+    phi = torch.from_numpy(synth.jrdb_phi()).cuda()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    scans = torch.rand(4096, 1, 1091, device="cuda", generator=g) * 24.7 + 0.3
+    scans[::3] = scans[::3] * 0.1 + 0.2                                       # a third of the scans close to the sensor: area rows
+    a = ops.cutout(scans, phi, **CFG)
+    b = ops.cutout(scans, phi, exact_pieces=True, **CFG)
+    assert torch.equal(a, b), int((a != b).sum())
 
 
 @pytest.mark.parametrize("M,L,C,pool", [(37, 56, 64, 1), (37, 56, 128, 2), (11, 28, 256, 2), (9, 14, 512, 2), (300, 1, 128, 1)])

@@ -26,18 +26,19 @@ for shape in ("jrdb", "drow") if not ONLY else ("jrdb",):
                 scans = np.tile(scans, (B // len(scans) + 1, 1, 1))[:B]
             s = torch.from_numpy(np.ascontiguousarray(scans)).to(dev)
             out = torch.empty((B, n, S, 56), device=dev)
-            for fast in (False, True):
+            for mode in ("EXACT", "EXACT-pieces", "FAST"):
+                fast = dict(fast=mode == "FAST", exact_pieces=mode == "EXACT-pieces")
                 for _ in range(3):
-                    _, sa = ops.cutout(s, phi_d, out=out, return_s_area=True, fast=fast, **CFG)
+                    _, sa = ops.cutout(s, phi_d, out=out, return_s_area=True, **fast, **CFG)
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for _ in range(10):
-                    ops.cutout(s, phi_d, out=out, fast=fast, **CFG)
+                    ops.cutout(s, phi_d, out=out, **fast, **CFG)
                 e1.record()
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / 10
                 gb = B * S * n * 228 / 1e9
-                print("%-5s %-11s B=%4d S=%2d %-5s %8.3f ms  %7.1f GB/s (%.1f%% of 6547)  s_area max %d" %
-                      (shape, kind, B, S, "FAST" if fast else "EXACT", ms, gb / ms * 1e3, 100 * gb / ms * 1e3 / 6547,
+                print("%-5s %-11s B=%4d S=%2d %-12s %8.3f ms  %7.1f GB/s (%.1f%% of 6547)  s_area max %d" %
+                      (shape, kind, B, S, mode, ms, gb / ms * 1e3, 100 * gb / ms * 1e3 / 6547,
                        int(sa.max())))
