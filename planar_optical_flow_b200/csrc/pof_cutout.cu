@@ -972,35 +972,81 @@ constexpr double kFloorMagic = 6755399441055744.0;      // 1.5 * 2^52
 
 struct ExactRow {
     double start, step_d, range_d;
-    float lo_f, hi_f;
+    float lo_f, hi_f, pad_f;
 };
 
 // MODE 0: not centred; 1: centred, window_depth a power of two; 2: centred, any window_depth
 template <int MODE>
-__device__ __forceinline__ void exact_row_inside(const ExactRow& r, const Consts& c, const double2* dpairs, const double* ktab,
-                                                 unsigned rot, int nchunks, float* dst) {
+__device__ __forceinline__ float exact_finish(double v, const ExactRow& r, const Consts& c) {
+    if (MODE != 0) {
+        v = __dsub_rn(v, r.range_d);                                                             // :329-330
+        v = MODE == 1 ? __dmul_rn(v, c.inv_depth) : div_depth(v, c);
+    }
+    return clip_nan((float)v, r.lo_f, r.hi_f);
+}
+// INSIDE: every sample of the row lies in the scan.  Otherwise (rows at the two ends of the scan) the :289 test selects the
+// padding value and the gather is clamped; |idx| < 2^30 is the caller's guarantee either way.
+template <int MODE, bool INSIDE>
+__device__ __forceinline__ float exact_sample(double kd, const ExactRow& r, const Consts& c, const double2* dpairs, int nm1) {
+    const double ang = fma(kd, r.step_d, r.start);                                               // :286-288
+    const double idx = div_by(__dsub_rn(ang, c.origin), c.pitch, c.inv_pitch);
+    const double t = __dadd_rd(idx, kFloorMagic);
+    const double ratio = __dsub_rn(idx, __dsub_rn(t, kFloorMagic));                              // :292-294
+    const int lo = __double2loint(t);
+    const double2 vd = dpairs[INSIDE ? lo : min(max(lo, 0), nm1)];
+    const float res = exact_finish<MODE>(__dadd_rn(vd.x, __dmul_rn(ratio, vd.y)), r, c);         // :300
+    return INSIDE || in_scan(idx, lo, nm1, c) ? res : r.pad_f;
+}
+// A lane keeps kExactChunks x 4 samples in flight.  All lanes walk the samples in the same order: (double)k is a broadcast
+// load and the gathers of neighbouring rows stay on neighbouring entries (the rotated order of the FAST kernel cost this
+// one 1.6x the ideal gather wavefronts, more than it saves in store conflicts).
+#ifndef POF_EXACT_CHUNKS
+#define POF_EXACT_CHUNKS 2
+#endif
+constexpr int kExactChunks = POF_EXACT_CHUNKS;
+template <int MODE, bool INSIDE>
+__device__ __forceinline__ void exact_row(const ExactRow& r, const Consts& c, const double2* dpairs, const double* ktab,
+                                          int nm1, int nchunks, float* dst) {
+    int ch = 0;
 #pragma unroll 1
-    for (int j = 0; j < nchunks; ++j) {
-        int ch = j + (int)rot;
-        if (ch >= nchunks) ch = 0;                            // rotated chunk order: conflict-free 16-byte stores
-        const int k0 = ch << 2;
+    for (; ch + kExactChunks <= nchunks; ch += kExactChunks) {
+        float res[4 * kExactChunks];
+#pragma unroll
+        for (int u = 0; u < 4 * kExactChunks; ++u) res[u] = exact_sample<MODE, INSIDE>(ktab[4 * ch + u], r, c, dpairs, nm1);
+#pragma unroll
+        for (int q = 0; q < kExactChunks; ++q)
+            *reinterpret_cast<float4*>(dst + 4 * (ch + q)) = make_float4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]);
+    }
+#pragma unroll 1
+    for (; ch < nchunks; ++ch) {
         float res[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const double ang = fma(ktab[k0 + u], r.step_d, r.start);                                     // :286-288
-            const double idx = div_by(__dsub_rn(ang, c.origin), c.pitch, c.inv_pitch);
-            const double t = __dadd_rd(idx, kFloorMagic);
-            const double ratio = __dsub_rn(idx, __dsub_rn(t, kFloorMagic));                              // :292-294
-            const double2 vd = dpairs[__double2loint(t)];
-            double v = __dadd_rn(vd.x, __dmul_rn(ratio, vd.y));                                          // :300
-            if (MODE != 0) {
-                v = __dsub_rn(v, r.range_d);                                                             // :329-330
-                v = MODE == 1 ? __dmul_rn(v, c.inv_depth) : div_depth(v, c);
-            }
-            res[u] = clip_nan((float)v, r.lo_f, r.hi_f);
-        }
-        *reinterpret_cast<float4*>(dst + k0) = make_float4(res[0], res[1], res[2], res[3]);
+        for (int u = 0; u < 4; ++u) res[u] = exact_sample<MODE, INSIDE>(ktab[4 * ch + u], r, c, dpairs, nm1);
+        *reinterpret_cast<float4*>(dst + 4 * ch) = make_float4(res[0], res[1], res[2], res[3]);
     }
+}
+template <bool INSIDE>
+__device__ __forceinline__ void exact_row_mode(int mode, const ExactRow& r, const Consts& c, const double2* dpairs, const double* ktab,
+                                               int nm1, int nchunks, float* dst) {
+    if (mode == 1) exact_row<1, INSIDE>(r, c, dpairs, ktab, nm1, nchunks, dst);
+    else if (mode == 0) exact_row<0, INSIDE>(r, c, dpairs, ktab, nm1, nchunks, dst);
+    else exact_row<2, INSIDE>(r, c, dpairs, ktab, nm1, nchunks, dst);
+}
+// One sample of an area-resampled row that lies inside the scan: the s_area nearest-beam taps in tap order (:310-323), the
+// rounding to the nearest beam (ties to even, like np.rint) taken from RN(ia + 1.5 * 2^52) instead of an F2I.
+template <int MODE>
+__device__ __forceinline__ float exact_area_sample(int k, const ExactRow& r, double step_a_d, int s_area, float s_area_f,
+                                                   const Consts& c, const float* vals, int nm1) {
+    double kd = (double)(k * s_area);
+    float acc = 0.f;
+#pragma unroll 2
+    for (int t = 0; t < s_area; ++t) {
+        const double ia = div_by(__dsub_rn(fma(kd, step_a_d, r.start), c.origin), c.pitch, c.inv_pitch);
+        const float tap = vals[min(max(__double2loint(__dadd_rn(ia, kFloorMagic)), 0), nm1)];
+        acc = t == 0 ? tap : __fadd_rn(acc, tap);
+        kd = __dadd_rn(kd, 1.0);
+    }
+    return exact_finish<MODE>((double)__fdiv_rn(acc, s_area_f), r, c);
 }
 
 template <typename PhiT, bool MULTI>
@@ -1090,7 +1136,6 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 4) cutout_scan_exact_kerne
         }
     }
 
-    const unsigned rot = nchunks_rot(P, lane);
     const int nchunks = P >> 2;
     float* out_b = a.out + (MULTI ? ((size_t)b * a.M * a.S + sc) * P : (size_t)b * a.M * P);
     bool store_pending = false;
@@ -1098,7 +1143,7 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 4) cutout_scan_exact_kerne
     for (int m0 = warp * 32; m0 < a.M; m0 += T) {
         const int rows_here = min(32, a.M - m0);
         const bool valid = lane < rows_here;
-        bool is_area = false, inside = false;
+        bool is_area = false, inside = false, bounded = false;
         RowGeom g;
         g.start = 0.0; g.step = g.step_a = g.range = g.lo_f = g.hi_f = g.pad_f = 0.f; g.s_area = 0;
         if (valid) {                                          // :274-285, as in cutout_kernel's phase 1
@@ -1118,6 +1163,7 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 4) cutout_scan_exact_kerne
                 g.step_a = __fdiv_rn(two_ha, (float)(s_area * P - 1));
             }
             inside = g.step >= 0.f && i0 >= 0.0 && i1 <= c.last;     // the index is monotone in k: every sample lies in the scan
+            bounded = g.step >= 0.f && fabs(i0) < 1.0e9 && fabs(i1) < 1.0e9;    // floor(idx) fits the low word of idx + 1.5 * 2^52
             g.lo_f = finish((double)(g.range - a.depth_f), g.range, c, a.centered);            // :327-334 (see cutout_kernel)
             g.hi_f = finish((double)(g.range + a.depth_f), g.range, c, a.centered);
             g.pad_f = clip_nan(finish(a.pad, g.range, c, a.centered), g.lo_f, g.hi_f);         // :326
@@ -1128,15 +1174,15 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 4) cutout_scan_exact_kerne
         }
 
         // ---- two-tap rows ---------------------------------------------------------------------------
-        if (valid && !is_area) {
-            float* dst = tile + lane * P;
-            if (inside) {
-                ExactRow r;
-                r.start = g.start; r.step_d = (double)g.step; r.range_d = (double)g.range; r.lo_f = g.lo_f; r.hi_f = g.hi_f;
-                if (mode == 1) exact_row_inside<1>(r, c, dpairs, ktab, rot, nchunks, dst);
-                else if (mode == 0) exact_row_inside<0>(r, c, dpairs, ktab, rot, nchunks, dst);
-                else exact_row_inside<2>(r, c, dpairs, ktab, rot, nchunks, dst);
-            } else {
+        ExactRow r;
+        r.start = g.start; r.step_d = (double)g.step; r.range_d = (double)g.range; r.lo_f = g.lo_f; r.hi_f = g.hi_f; r.pad_f = g.pad_f;
+        const bool two_tap = valid && !is_area;
+        if (__all_sync(0xffffffffu, !two_tap || inside)) {            // warp-uniform: the common group
+            if (two_tap) exact_row_mode<true>(mode, r, c, dpairs, ktab, nm1, nchunks, tile + lane * P);
+        } else if (two_tap) {                                         // a group at one end of the scan
+            if (bounded) exact_row_mode<false>(mode, r, c, dpairs, ktab, nm1, nchunks, tile + lane * P);
+            else {
+                float* dst = tile + lane * P;
 #pragma unroll 1
                 for (int k = 0; k < P; ++k) dst[k] = linear_exact(g, vals, k, c, nm1, a.centered);
             }
@@ -1147,17 +1193,29 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 4) cutout_scan_exact_kerne
         while (m_area) {
             const int src = __ffs(m_area) - 1;
             m_area &= m_area - 1;
-            RowGeom r;
-            r.start = __shfl_sync(0xffffffffu, g.start, src);
-            r.step = __shfl_sync(0xffffffffu, g.step, src);
-            r.step_a = __shfl_sync(0xffffffffu, g.step_a, src);
-            r.range = __shfl_sync(0xffffffffu, g.range, src);
-            r.lo_f = __shfl_sync(0xffffffffu, g.lo_f, src);
-            r.hi_f = __shfl_sync(0xffffffffu, g.hi_f, src);
-            r.pad_f = __shfl_sync(0xffffffffu, g.pad_f, src);
-            r.s_area = s_area;
+            RowGeom ra;
+            ra.start = __shfl_sync(0xffffffffu, g.start, src);
+            ra.step = __shfl_sync(0xffffffffu, g.step, src);
+            ra.step_a = __shfl_sync(0xffffffffu, g.step_a, src);
+            ra.range = __shfl_sync(0xffffffffu, g.range, src);
+            ra.lo_f = __shfl_sync(0xffffffffu, g.lo_f, src);
+            ra.hi_f = __shfl_sync(0xffffffffu, g.hi_f, src);
+            ra.pad_f = __shfl_sync(0xffffffffu, g.pad_f, src);
+            ra.s_area = s_area;
+            const bool ra_inside = __shfl_sync(0xffffffffu, (int)inside, src) != 0;
             float* row = tile + src * P;
-            for (int k = lane; k < P; k += 32) row[k] = area_exact(r, vals, k, c, nm1, a.centered);
+            if (ra_inside) {
+                ExactRow rr;
+                rr.start = ra.start; rr.step_d = 0.0; rr.range_d = (double)ra.range; rr.lo_f = ra.lo_f; rr.hi_f = ra.hi_f; rr.pad_f = ra.pad_f;
+                const double step_a_d = (double)ra.step_a;
+                const float s_area_f = (float)s_area;
+                for (int k = lane; k < P; k += 32)
+                    row[k] = mode == 1 ? exact_area_sample<1>(k, rr, step_a_d, s_area, s_area_f, c, vals, nm1)
+                           : mode == 0 ? exact_area_sample<0>(k, rr, step_a_d, s_area, s_area_f, c, vals, nm1)
+                                       : exact_area_sample<2>(k, rr, step_a_d, s_area, s_area_f, c, vals, nm1);
+            } else {
+                for (int k = lane; k < P; k += 32) row[k] = area_exact(ra, vals, k, c, nm1, a.centered);
+            }
         }
 
         if (MULTI) {
