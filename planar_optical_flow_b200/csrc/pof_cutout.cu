@@ -1049,11 +1049,36 @@ __device__ __forceinline__ float exact_area_sample(int k, const ExactRow& r, dou
     return exact_finish<MODE>((double)__fdiv_rn(acc, s_area_f), r, c);
 }
 
+// The same sample with the taps located on a 32.32 fixed-point index line (integer adds, no double operation per tap).
+// The line is within 2^-20 beam of the reference's double index for every tap - |start| < 64 rad, 1 / pitch < 1e5 and
+// s_area * P <= 4096 (the caller's conditions) bound the three roundings of the double index by 1.4e-9 beam, the
+// rounding of the line's origin by 3e-12 and the accumulated quantisation of its slope by 4096 * 2^-33 = 2^-21 - so both
+// round to the same beam unless the line passes within 2^-19 of a half-way point; then (one tap in 2.6e5, exact ties
+// included) the sample is recomputed with the double index.
+constexpr unsigned kTapGuard = 1u << 13;                      // 2^-19 beam in 32.32
+template <int MODE>
+__device__ __forceinline__ float exact_area_sample_fx(int k, const ExactRow& r, long long fx_base, long long fx_slope_a, double step_a_d,
+                                                      int s_area, float s_area_f, const Consts& c, const float* vals, int nm1) {
+    long long fa = fx_base + (long long)(k * s_area) * fx_slope_a + 0x80000000ll;      // +0.5: truncation rounds to nearest
+    float acc = 0.f;
+    bool close = false;
+#pragma unroll 4
+    for (int t = 0; t < s_area; ++t, fa += fx_slope_a) {
+        close |= (unsigned)fa + kTapGuard < 2u * kTapGuard;
+        const float tap = vals[min(max((int)hi32(fa), 0), nm1)];
+        acc = t == 0 ? tap : __fadd_rn(acc, tap);
+    }
+    if (close) return exact_area_sample<MODE>(k, r, step_a_d, s_area, s_area_f, c, vals, nm1);
+    return exact_finish<MODE>((double)__fdiv_rn(acc, s_area_f), r, c);
+}
+
 template <typename PhiT, bool MULTI>
 __global__ void __launch_bounds__(kScanWarpsMax * 32, 4) cutout_scan_exact_kernel(const CutoutArgs a, const int mode) {
     extern __shared__ __align__(16) float smem_f[];          // pairs [N+1] double2 | (double)k [P] | ranges [N] | per-warp tiles [32][P] | (MULTI, !fixed) reference ranges [N]
     __shared__ double warp_span[kScanWarpsMax];
     __shared__ float warp_min[kScanWarpsMax];
+    __shared__ int next_group;                               // row groups are handed out dynamically: groups with area rows cost several times the others
+    if (threadIdx.x == 0) next_group = 0;
     const Consts c = make_consts<PhiT>(a);
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
     const int b = MULTI ? blockIdx.x / a.S : blockIdx.x;
@@ -1077,7 +1102,8 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 4) cutout_scan_exact_kerne
     // ---- stage the scan; entry N repeats beam N-1 (inds_ct_high is clipped at N-1, :293) -----------------
     float dmin = 3.0e38f;
     for (int k = tid; k < P; k += T) ktab[k] = (double)k;
-    for (int i = tid; i <= a.N; i += T) {
+#pragma unroll 4
+    for (int i = tid; i <= a.N; i += T) {                    // (unrolled: the loads of four rounds are in flight together)
         const float v0 = __ldg(scan + min(i, nm1)), v1 = __ldg(scan + min(i + 1, nm1));
         dpairs[i] = make_double2((double)v0, (double)__fsub_rn(v1, v0));
         if (i < a.N) vals[i] = v0;
@@ -1139,8 +1165,13 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 4) cutout_scan_exact_kerne
     const int nchunks = P >> 2;
     float* out_b = a.out + (MULTI ? ((size_t)b * a.M * a.S + sc) * P : (size_t)b * a.M * P);
     bool store_pending = false;
+    const bool fx_taps = c.inv_pitch > 0.0 && c.inv_pitch < 1.0e5 && (long long)s_area * P <= 4096;
 
-    for (int m0 = warp * 32; m0 < a.M; m0 += T) {
+    for (;;) {
+        int m0 = 0;
+        if (lane == 0) m0 = atomicAdd(&next_group, 32);
+        m0 = __shfl_sync(0xffffffffu, m0, 0);
+        if (m0 >= a.M) break;
         const int rows_here = min(32, a.M - m0);
         const bool valid = lane < rows_here;
         bool is_area = false, inside = false, bounded = false;
@@ -1148,13 +1179,14 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 4) cutout_scan_exact_kerne
         g.start = 0.0; g.step = g.step_a = g.range = g.lo_f = g.hi_f = g.pad_f = 0.f; g.s_area = 0;
         if (valid) {                                          // :274-285, as in cutout_kernel's phase 1
             const int m = m0 + lane, i = m * a.stride;
+            const PhiT phi_i = phi[i];                       // (issued ahead of the arctangent that hides its latency)
             g.range = dvals[i];
             const float ratio = __fdiv_rn(a.half_width, fmaxf(g.range, 1e-2f));
             const float ha = ha_in ? __ldg(ha_in + m) : atan_f32(ratio);                       // :279
             if (ha_out) ha_out[m] = ha;
             const float two_ha = 2.0f * ha;
             g.step = __fdiv_rn(two_ha, (float)(P - 1));                                        // :282
-            g.start = (double)(phi[i] - (PhiT)ha);                                             // :284-285
+            g.start = (double)(phi_i - (PhiT)ha);                                              // :284-285
             const double i0 = sample_index(g.start, g.step, 0, c);
             const double i1 = sample_index(g.start, g.step, P - 1, c);
             if (s_area > 0 && __dsub_rn(i1, i0) > Pd) {                                        // :304-310
@@ -1164,9 +1196,16 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 4) cutout_scan_exact_kerne
             }
             inside = g.step >= 0.f && i0 >= 0.0 && i1 <= c.last;     // the index is monotone in k: every sample lies in the scan
             bounded = g.step >= 0.f && fabs(i0) < 1.0e9 && fabs(i1) < 1.0e9;    // floor(idx) fits the low word of idx + 1.5 * 2^52
-            g.lo_f = finish((double)(g.range - a.depth_f), g.range, c, a.centered);            // :327-334 (see cutout_kernel)
-            g.hi_f = finish((double)(g.range + a.depth_f), g.range, c, a.centered);
-            g.pad_f = clip_nan(finish(a.pad, g.range, c, a.centered), g.lo_f, g.hi_f);         // :326
+            if (mode == 1) {                                 // :327-334 (see cutout_kernel); the division is one exact product
+                const double rd = (double)g.range;
+                g.lo_f = (float)__dmul_rn(__dsub_rn((double)(g.range - a.depth_f), rd), c.inv_depth);
+                g.hi_f = (float)__dmul_rn(__dsub_rn((double)(g.range + a.depth_f), rd), c.inv_depth);
+                g.pad_f = clip_nan((float)__dmul_rn(__dsub_rn(a.pad, rd), c.inv_depth), g.lo_f, g.hi_f);      // :326
+            } else {
+                g.lo_f = finish((double)(g.range - a.depth_f), g.range, c, a.centered);
+                g.hi_f = finish((double)(g.range + a.depth_f), g.range, c, a.centered);
+                g.pad_f = clip_nan(finish(a.pad, g.range, c, a.centered), g.lo_f, g.hi_f);
+            }
         }
         if (!MULTI && store_pending) {                        // the previous group's tile must have been read by the TMA
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -1209,10 +1248,19 @@ __global__ void __launch_bounds__(kScanWarpsMax * 32, 4) cutout_scan_exact_kerne
                 rr.start = ra.start; rr.step_d = 0.0; rr.range_d = (double)ra.range; rr.lo_f = ra.lo_f; rr.hi_f = ra.hi_f; rr.pad_f = ra.pad_f;
                 const double step_a_d = (double)ra.step_a;
                 const float s_area_f = (float)s_area;
-                for (int k = lane; k < P; k += 32)
-                    row[k] = mode == 1 ? exact_area_sample<1>(k, rr, step_a_d, s_area, s_area_f, c, vals, nm1)
-                           : mode == 0 ? exact_area_sample<0>(k, rr, step_a_d, s_area, s_area_f, c, vals, nm1)
-                                       : exact_area_sample<2>(k, rr, step_a_d, s_area, s_area_f, c, vals, nm1);
+                if (fx_taps && fabs(ra.start) < 64.0) {       // (see exact_area_sample_fx)
+                    const long long fx_base = to_fixed(__dsub_rn(ra.start, c.origin) * c.inv_pitch);
+                    const long long fx_slope_a = to_fixed(step_a_d * c.inv_pitch);
+                    for (int k = lane; k < P; k += 32)
+                        row[k] = mode == 1 ? exact_area_sample_fx<1>(k, rr, fx_base, fx_slope_a, step_a_d, s_area, s_area_f, c, vals, nm1)
+                               : mode == 0 ? exact_area_sample_fx<0>(k, rr, fx_base, fx_slope_a, step_a_d, s_area, s_area_f, c, vals, nm1)
+                                           : exact_area_sample_fx<2>(k, rr, fx_base, fx_slope_a, step_a_d, s_area, s_area_f, c, vals, nm1);
+                } else {
+                    for (int k = lane; k < P; k += 32)
+                        row[k] = mode == 1 ? exact_area_sample<1>(k, rr, step_a_d, s_area, s_area_f, c, vals, nm1)
+                               : mode == 0 ? exact_area_sample<0>(k, rr, step_a_d, s_area, s_area_f, c, vals, nm1)
+                                           : exact_area_sample<2>(k, rr, step_a_d, s_area, s_area_f, c, vals, nm1);
+                }
             } else {
                 for (int k = lane; k < P; k += 32) row[k] = area_exact(ra, vals, k, c, nm1, a.centered);
             }

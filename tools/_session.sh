@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "cutout" 2>&1 | tail -3
-timeout 600 python tools/tune_cutout.py 2>&1 | grep -v "pieces" > gpurun_out/exact_sweep2.txt; cat gpurun_out/exact_sweep2.txt
+timeout 600 python tools/tune_cutout.py 2>&1 | grep "EXACT " | grep "4096\|512"
