@@ -587,10 +587,11 @@ def run_ours(args):
                                                      "note": "the kernel only writes (reads are 1/57 of its traffic): bandwidth of torch's fill kernel and of "
                                                              "a memset over the same 1 GB output buffer, measured in this run, for context; `frac` above "
                                                              "stays against the read+write copy peak"},
-                            "exact_arithmetic": {"achieved": sweep_gbs["exact"], "frac": sweep_gbs["exact"] / peak,
+                            "exact_arithmetic": {"kernel": "cutout_scan_exact_kernel (what scans_to_cutout and the engine run)",
+                                                 "achieved": sweep_gbs["exact"], "frac": sweep_gbs["exact"] / peak,
                                                  "avg_launch_ms": cut_sweep["exact"]},
                             "in_streaming_step": {"achieved": cut_gbs, "frac": cut_gbs / peak, "avg_launch_ms": cut_avg_ms,
-                                                  "note": "the engine's own cutout call (EXACT arithmetic, span + cutout launch) per step "
+                                                  "note": "the engine's own cutout call (EXACT arithmetic, one launch) per step "
                                                           "over %d sequences (64 MB): launch-latency bound at this size" % B}},
         "stage_ms_per_step": {"cutout": sum(cut_ms) / K, "gate": sum(gate_ms) / K, "nms": sum(nms_ms) / K,
                               "convolutions_tcgen05": sum(sum(v) for v in conv_ms.values()) / K,

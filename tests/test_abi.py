@@ -57,6 +57,8 @@ def test_argument_validation_happens_before_any_cuda_call(built_lib):
     one = ctypes.c_void_p(256)
     st = L.pof_cutout_fwd(one, one, 0, 1, 1, 450, 1, 55, 1.0, 0.5, 29.99, 1, 1, 1, 0, one, None, None, None, one, 8, None)
     assert st == -2 and "multiple of 4" in _lib.last_error()
+    st = L.pof_cutout_fwd(one, one, 0, 1, 1, 450, 1, 56, 1.0, 0.5, 29.99, 1, 1, 1, 3, one, None, None, None, one, 8, None)
+    assert st < 0 and "numerics" in _lib.last_error()          # 0 EXACT, 1 FAST, 2 EXACT_PIECES
     st = L.pof_spaam_gate_fwd(one, one, one, one, 1, 10, 3584, 128, 10, 0.5, ctypes.c_void_p(512), one, None, None, 0, None, None)
     assert st == -5 and "odd" in _lib.last_error()
     st = L.pof_spaam_gate_fwd(one, one, one, one, 1, 10, 3584, 128, 11, 0.5, one, one, None, None, 0, None, None)

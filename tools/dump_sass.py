@@ -30,6 +30,7 @@ FULL = {                       # file stem -> regex on the demangled name
     "cutout_scan_kernel_f32_multi_scan": r"cutout_scan_kernel<float, true>",
     "gate_stream_kernel_11_bwd_scores": r"gate_stream_kernel<11, 2>",
     "bn_act_bwd_kernel_pool2": r"bn_act_bwd_kernel<2>",
+    "cutout_scan_exact_kernel_f32": r"cutout_scan_exact_kernel<float, false>",
     "cutout_kernel_exact_f32_staged": r"cutout_kernel<float, false, true>",
     "nms_sweep_kernel": r"nms_sweep_kernel",
 }
