@@ -78,7 +78,8 @@ def parse():
     ap.add_argument("--graph", dest="graph", action="store_true", default=True,
                     help="replay each step as one CUDA graph per memory parity (default; +2.6 %% at 256 sequences, 1.5x at one)")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="issue every launch of a step from Python")
-    ap.add_argument("--workload", default="stream", choices=["stream", "train"])
+    ap.add_argument("--workload", default="stream", choices=["stream", "train", "cutout"],
+                    help="stream: the headline metric; train: BASELINE configs[3]; cutout: the scans_to_cutout-only sweep of configs[1]")
     return ap.parse_args()
 
 
@@ -788,6 +789,148 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- BASELINE configs[1]: the cutout-only sweep
+CUTOUT_SWEEP_BATCHES = (1, 4, 16, 64, 256, 1024, 4096)
+
+
+def cutout_sweep_scans(shape, batch):
+    """[batch, N] structured ranges (16 seeded walks tiled with per-scan jitter) and phi."""
+    import numpy as np
+
+    phi, seq = make_sequences(shape, min(batch, 256), 1, seed0=4000)
+    scans = seq[0]
+    if batch > scans.shape[0]:
+        rs = np.random.RandomState(7)
+        scans = np.tile(scans, (-(-batch // scans.shape[0]), 1))[:batch]
+        scans = np.clip(scans + rs.normal(0.0, 0.02, size=scans.shape).astype(np.float32), 0.05, 29.99)
+    return phi, np.ascontiguousarray(scans, dtype=np.float32)
+
+
+def cpu_reference_cutout_rows_per_s(shape, n_scans):
+    """The reference's NumPy `scans_to_cutout` (baseline/_ref, else the oracle port) looped over single scans on ONE host
+    thread, as SURVEY.md 8d prescribes for this sweep (the function is single-threaded NumPy)."""
+    from oracle import cutout as ocut
+
+    ref = reference_modules()
+    fn = ref[0].scans_to_cutout if ref is not None else ocut.scans_to_cutout
+    phi, scans = cutout_sweep_scans(shape, n_scans + 2)
+    for b in range(2):
+        fn(scans[b:b + 1], phi, stride=1, **CUTOUT_KW)
+    t0 = time.perf_counter()
+    for b in range(2, n_scans + 2):
+        fn(scans[b:b + 1], phi, stride=1, **CUTOUT_KW)
+    return n_scans / (time.perf_counter() - t0)
+
+
+def run_cutout(args):
+    """`scans_to_cutout`-only sweep on JRDB-shaped scans, batch 1-4096 on one GPU (BASELINE.json configs[1]).  A step = one
+    batched call over B scans.  `value` = scan rows/s at B = 4096 with EXACT arithmetic (what `scans_to_cutout` computes), ranges
+    resident in HBM; `e2e` = the same call from host ranges to host cutouts (the 1 GB result crosses PCIe)."""
+    import numpy as np
+    import torch
+
+    from planar_optical_flow_b200 import ops
+
+    if args.impl == "reference":
+        v = cpu_reference_cutout_rows_per_s(args.shape, max(args.steps, 1) * 32)
+        kind = cpu_reference_kind()
+        _JSON_OUT.write(json.dumps({
+            "impl": "reference", "metric": "scans_to_cutout scan rows/s", "value": v, "unit": "scans/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 32e3 / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "scans_to_cutout-only sweep, %s-shaped scans, batch 1-4096" % args.shape.upper()},
+            "cpu_baseline": {"value": v, "unit": "scans/s", "cores": 1, "kind": kind,
+                             "sample": "each step = 32 single-scan calls of the reference's NumPy scans_to_cutout on one host thread"},
+            "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}) + "\n")
+        _JSON_OUT.flush()
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    K, W = max(args.steps, 1), max(args.warmup, 3)
+    peak, peak_src = measured_hbm_peak()
+    P = CUTOUT_KW["num_cutout_pts"]
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    sweep, e2e = [], None
+    for B in CUTOUT_SWEEP_BATCHES:
+        phi, scans = cutout_sweep_scans(args.shape, B)
+        N = scans.shape[1]
+        phi_d = torch.from_numpy(np.ascontiguousarray(phi)).to(dev)
+        s_d = torch.from_numpy(scans).to(dev).unsqueeze(1)
+        out = torch.empty((B, N, 1, P), dtype=torch.float32, device=dev)
+        row = {"batch": B}
+        for name, fast in (("exact", False), ("fast", True)):
+            for _ in range(W + (200 if B >= 1024 else 20)):          # warm-up long enough for the clock to settle at this kernel's power
+                ops.cutout(s_d, phi_d, out=out, fast=fast, **CUTOUT_KW)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(K):
+                ops.cutout(s_d, phi_d, out=out, fast=fast, **CUTOUT_KW)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / K
+            row[name] = {"ms_per_call": ms, "scan_rows_per_s": B / (ms * 1e-3), "gbs": B * N * 228 / (ms * 1e-3) / 1e9,
+                         "frac": B * N * 228 / (ms * 1e-3) / 1e9 / peak}
+        sweep.append(row)
+        if B == CUTOUT_SWEEP_BATCHES[-1]:
+            # end to end: pinned host ranges -> device -> kernel -> pinned host cutouts, every step
+            h_in = torch.from_numpy(scans).pin_memory()
+            h_out = torch.empty((B, N, 1, P), dtype=torch.float32).pin_memory()
+            for _ in range(W):
+                s_d.copy_(h_in.unsqueeze(1), non_blocking=True)
+                ops.cutout(s_d, phi_d, out=out, **CUTOUT_KW)
+                h_out.copy_(out, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(K):
+                s_d.copy_(h_in.unsqueeze(1), non_blocking=True)
+                ops.cutout(s_d, phi_d, out=out, **CUTOUT_KW)
+                h_out.copy_(out, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / K
+            e2e = {"value": B / (ms * 1e-3), "unit": "scans/s", "h2d_bytes_per_step": int(h_in.numel() * 4),
+                   "d2h_bytes_per_step": int(h_out.numel() * 4), "ms_per_step": ms,
+                   "api": "ops.cutout on pinned host ranges, result copied back to pinned host memory (PCIe bound: 1 GB per call)"}
+            # parity spot: three of the timed scans against the oracle (reference half-angles fed in: every other operation is exact)
+            from oracle import cutout as ocut
+
+            worst, exact = 0.0, 1.0
+            for b in (0, B // 2, B - 1):
+                ha = ocut.window_half_angle(scans[b:b + 1], 1, CUTOUT_KW["fixed"], CUTOUT_KW["window_width"])
+                want = ocut.scans_to_cutout(scans[b:b + 1], phi, **CUTOUT_KW)
+                got = ops.cutout(s_d[b:b + 1], phi_d, half_alpha=torch.from_numpy(np.ascontiguousarray(ha, np.float32)).to(dev).unsqueeze(0),
+                                 **CUTOUT_KW)[0].cpu().numpy()
+                worst = max(worst, float(np.abs(got.astype(np.float64) - want).max() / max(np.abs(want).max(), 1e-30)))
+                exact = min(exact, float((got == want).mean()))
+    clocks = sampler.stop()
+    last = sweep[-1]
+    out_line = {
+        "metric": "scans_to_cutout scan rows/s (JRDB 1091-pt, batch 4096)", "value": last["exact"]["scan_rows_per_s"], "unit": "scans/s",
+        "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": last["exact"]["ms_per_call"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "scans_to_cutout-only sweep, %s-shaped scans (%d pts), batch 1-4096, EXACT arithmetic (the API default); "
+                               "FAST beside it" % (args.shape.upper(), N), "cutout_pts": P,
+                   "l2_policy": "1 GB of output per call at the quoted batch (L2 = 126 MB)"},
+        "e2e": e2e, "gpu_launches": K * 2 * len(CUTOUT_SWEEP_BATCHES), "sweep": sweep,
+        "parity_spot": {"max_rel_with_reference_half_angles": worst, "bit_equal_fraction": exact},
+        "roofline": {"kernel": "cutout_scan_exact_kernel", "bound": "hbm", "achieved": last["exact"]["gbs"], "peak": peak, "unit": "GB/s",
+                     "frac": last["exact"]["frac"], "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": CUTOUT_SWEEP_BATCHES[-1] * N * 228,
+                     "fast_arithmetic": {"kernel": "cutout_scan_kernel", "achieved": last["fast"]["gbs"], "frac": last["fast"]["frac"]}},
+        "clocks": clocks}
+    if not args.no_cpu_baseline:
+        v = cpu_reference_cutout_rows_per_s(args.shape, 256)
+        out_line["cpu_baseline"] = {"value": v, "unit": "scans/s", "cores": 1, "kind": cpu_reference_kind(),
+                                    "ideal_all_cores": v * (os.cpu_count() or 1), "host_cores": os.cpu_count(),
+                                    "sample": "256 single-scan calls of the reference's NumPy scans_to_cutout on one host thread "
+                                              "(the function is single-threaded; x cores = the ideal multi-process bound)"}
+    _JSON_OUT.write(json.dumps(out_line) + "\n")
+    _JSON_OUT.flush()
+
+
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -831,7 +974,9 @@ def _claim_stdout():
 if __name__ == "__main__":
     a = parse()
     _JSON_OUT = _claim_stdout()
-    if a.impl == "reference":
+    if a.workload == "cutout":
+        run_cutout(a)
+    elif a.impl == "reference":
         run_reference(a)
     elif a.workload == "train":
         run_train(a)
