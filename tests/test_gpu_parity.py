@@ -875,6 +875,17 @@ def test_cutout_infinite_ranges_match_the_reference(S, flags):
             assert (got[finite] == want[finite]).mean() >= 0.9999
 
 
+@pytest.mark.parametrize("n", [6000, 9000])
+def test_cutout_long_scans_take_the_fallback_kernels(n):
+    """Scans too long for the scan kernels' shared-memory staging (16 B per beam for EXACT, 8192 beams for any staging) fall
+    back to the piece kernels: same five-way check against the oracle, S = 1 and S = 2."""
+    phi = np.linspace(-np.pi, np.pi, n).astype(np.float32)
+    for S in (1, 2):
+        scans = synth.adversarial_scans(S, n, seed=n + S, lo=2.0)
+        scans[:, ::97] = 1.5                                              # a few close returns: area rows with a large s_area
+        _check_cutout(scans, phi, CFG)
+
+
 def test_cutout_exact_kernel_at_full_size_equals_pieces_kernel():
     """BASELINE configs[1] size (4096 JRDB scans): both EXACT kernels, every sample."""
     phi = torch.from_numpy(synth.jrdb_phi()).cuda()
