@@ -42,7 +42,10 @@ def test_stream_arm_prints_the_contract_line():
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     r = d["roofline"]
     assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert d["parity_spot"]["max_rel"] <= 1e-5 and d["parity_spot"]["mask_equal"]
+    # the 1e-5 bar is on identical cutouts; `max_rel` also carries NumPy's float32 arctan (1-2 ulp, host-CPU specific), which can
+    # flip a nearest-beam tap of an area row (tests/test_gpu_timed_config.py arbitrates that with float64)
+    assert d["parity_spot"]["max_rel_network_on_same_cutouts"] <= 1e-5 and d["parity_spot"]["max_rel"] <= 2e-4
+    assert d["parity_spot"]["mask_equal"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
 
 
