@@ -236,6 +236,7 @@ POF_API int pof_head_fwd(const float* y, const float* bias, long long M, int L, 
 #define POF_CONV_TC_SINGLE_CTA 0x10000   /* OR into chain_channels: one CTA per tile instead of an SM pair (cta_group::2) */
 #define POF_CONV_TC_STREAM_W   0x20000   /* OR into chain_channels: never keep the weights resident in shared memory (tuning) */
 #define POF_CONV_TC_NO_DEBIAS  0x40000   /* OR into chain_channels: pof_conv_tc_f16_fwd does not compensate the tensor core's truncating accumulation (tests) */
+#define POF_CONV_TC_NO_SPLIT_TILE 0x80000 /* OR into chain_channels: never split a cutout between the two CTAs of a pair (tuning / tests) */
 POF_API int pof_conv_tc_fwd(const float* a_split, const float* w_split, const float* bias,
                             long long Mcut, int LA, int Lout, int Cin, int Cout, int taps, int pad,
                             int pool, float slope, float* out_plain, float* out_split,

@@ -105,6 +105,8 @@ struct Params {
     int tiles_n;
     int Lout;            // output rows per cutout (= box height)
     int mt;              // cutouts per tile, mt * Lout <= 128
+    int split_h0;        // 0, or (SM pairs only) the pair's 256 rows hold 2 mt + 1 cutouts: the middle one is split, its first
+                         // split_h0 = 128 - mt * Lout rows go to the leader CTA's tile, the other Lout - split_h0 to the peer's
     int Cin, Cout, taps, pad, pool;
     int chain;           // k-blocks accumulated in tensor memory before a promotion to registers
     int w_resident;      // the CTA's share of ALL weight k-blocks stays in shared memory for the whole launch
@@ -320,7 +322,8 @@ __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? 
 
 template <int BN, int CG, bool F16>
 __global__ void __cluster_dims__(CG, 1, 1) __launch_bounds__((Cfg<BN, CG>::kThreads), 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Params p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_p0, const __grid_constant__ CUtensorMap map_p1, const Params p) {
     using C = Cfg<BN, CG>;
     constexpr int kKBlock = KBlock<F16>::value;
     extern __shared__ unsigned char smem_raw[];
@@ -341,7 +344,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // work items: (group of CG consecutive row tiles) x (column tile); a CTA takes row tile CG * g + rank
     const long long n_tiles = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;
     const long long first_tile = blockIdx.x / CG, tile_stride = gridDim.x / CG;
-    const int rows_tile = p.mt * p.Lout;
+    // Split tiles (p.split_h0 > 0): with Lout = 28 a CTA's 128 rows hold four cutouts and 16 idle rows; instead the pair's 256
+    // rows take NINE cutouts - the leader's tile = cutouts 0-3 + rows [0, h0) of cutout 4, the peer's = cutouts 5-8 + rows
+    // [h0, Lout) of cutout 4, each CTA loading its part of the middle cutout with its own box (the row shift of a tap crosses
+    // the cut into real rows, and leaves the cutout into the zero fill, exactly like the full boxes).  In both CTAs the
+    // whole cutouts come first in shared memory (the second box then starts 1024-byte aligned), so the peer's tile rows are not
+    // in output order: its epilogue stores the two segments separately.
+    const bool split = CG == 2 && p.split_h0 > 0;
+    const int rows_full = p.mt * p.Lout;                         // rows of whole cutouts in a CTA's tile
+    const int rows_tile = !split ? rows_full : rank == 0 ? rows_full + p.split_h0 : rows_full + p.Lout - p.split_h0;
+    const int per_pair = split ? 2 * p.mt + 1 : CG * p.mt;       // cutouts per work item
     // shared-memory plan: [resident weights: n_kb x (W hi | W lo)] [ring: stages x stage_bytes]
     const int n_stages = p.stages;
     const unsigned stage_bytes = p.w_resident ? C::kStageA : C::kStage;
@@ -373,7 +385,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 0) {
             // ------------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
-            const unsigned tx = CG * (2u * (unsigned)rows_tile * kRowBytes + (p.w_resident ? 0u : 2u * (unsigned)C::kBTile));   // both CTAs' loads land on the leader's barrier
+            const unsigned rows_pair = split ? (unsigned)(per_pair * p.Lout) : CG * (unsigned)rows_tile;
+            const unsigned tx = 2u * rows_pair * kRowBytes + CG * (p.w_resident ? 0u : 2u * (unsigned)C::kBTile);   // both CTAs' loads land on the leader's barrier
             int s = 0;
             unsigned ph = 0;
             bool ok = true;
@@ -395,11 +408,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             __syncwarp();
             for (long long tile = first_tile; tile < n_tiles && ok; tile += tile_stride) {
                 const int nt = (int)(tile % p.tiles_n);
-                const int m0 = (int)(((tile / p.tiles_n) * CG + rank) * p.mt);
+                const int m0 = (int)((tile / p.tiles_n) * per_pair + rank * (split ? p.mt + 1 : p.mt));
+                const int m_mid = (int)((tile / p.tiles_n) * per_pair + p.mt);          // split: the cutout shared with the peer
+                const int mid_row = rank == 0 ? 0 : p.split_h0;                         // ... and my first row of it
+                const CUtensorMap* map_mid = rank == 0 ? &map_p0 : &map_p1;
                 // the rows this CTA loads next (first column tile only: the others find them in L2 anyway)
                 const long long tile_nx = tile + tile_stride;
                 const bool warm = tile_nx < n_tiles && tile_nx % p.tiles_n == 0;
-                const int m0_nx = (int)(((tile_nx / p.tiles_n) * CG + rank) * p.mt);
+                const int m0_nx = (int)((tile_nx / p.tiles_n) * per_pair + rank * (split ? p.mt + 1 : p.mt));
                 const int n0 = nt * BN + (int)rank * (BN / CG);          // my share of the weight tile's rows (CG = 1: all of them)
                 int tap = 0, c0 = 0;
                 for (int kb = 0; kb < n_kb; ++kb) {
@@ -426,6 +442,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             if (rank == 0) mbar_expect_tx(full(s), tx);
                             tma_load_3d_pair(dst, &map_a, c0, tap - p.pad, m0, full(s));
                             tma_load_3d_pair(dst + kATile, &map_a, p.Cin + c0, tap - p.pad, m0, full(s));
+                            if (split) {
+                                const unsigned mid = dst + (unsigned)rows_full * kRowBytes;
+                                tma_load_3d_pair(mid, map_mid, c0, mid_row + tap - p.pad, m_mid, full(s));
+                                tma_load_3d_pair(mid + kATile, map_mid, p.Cin + c0, mid_row + tap - p.pad, m_mid, full(s));
+                            }
                             if (!p.w_resident) {
                                 tma_load_2d_pair(dst + 2 * kATile, &map_w, c0, (tap * 2 + 0) * p.Cout + n0, full(s));
                                 tma_load_2d_pair(dst + 2 * kATile + C::kBTile, &map_w, c0, (tap * 2 + 1) * p.Cout + n0, full(s));
@@ -530,13 +551,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // Each warp therefore transposes 32 x 32 blocks through shared memory and stores 4 rows x 128 bytes
             // per instruction.
             const int nt = (int)(tile % p.tiles_n);
-            const long long r0 = ((tile / p.tiles_n) * CG + rank) * p.mt * p.Lout + q * 32;     // output row of lane 0, before pooling
-            const bool valid = row < rows_tile && r0 + lane < p.Mcut * p.Lout;
+            // output row of lane 0, before pooling; lanes from `seg` on (the peer's part of a split cutout) are `seg_delta` rows away
+            long long r0 = ((tile / p.tiles_n) * CG + rank) * rows_full + q * 32;
+            int seg = 32, seg_delta = 0;
+            if (split) {
+                r0 = (tile / p.tiles_n) * per_pair * p.Lout + q * 32 + (rank == 0 ? 0 : kTileM + p.Lout - p.split_h0);
+                if (rank != 0) {
+                    seg = min(max(rows_full - q * 32, 0), 32);
+                    seg_delta = -(rows_full + p.Lout - p.split_h0);
+                }
+            }
+            const bool valid = row < rows_tile && r0 + lane + (lane >= seg ? seg_delta : 0) < p.Mcut * p.Lout;
             const unsigned vmask = __ballot_sync(0xffffffffu, valid);
             const int cbase = nt * BN + h * C::kAcc;
             float* stg = staging + e * (32 * kStagePitch);
             const int nrows = p.pool == 2 ? 16 : 32;                  // output rows this warp owns
             const long long orow0 = p.pool == 2 ? (r0 >> 1) : r0;
+            const int oseg = p.pool == 2 ? seg >> 1 : seg, oseg_delta = p.pool == 2 ? seg_delta / 2 : seg_delta;
             // one transposition pass: lane l's 16 words (16 floats or 32 halves of ITS row) -> rows of 64 bytes at
             // dst + j * ld (bytes): four lanes store one output row, eight rows per instruction
             auto flush16 = [&](const unsigned* w, char* dst, long long ld) {
@@ -548,7 +579,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int j = lane >> 2; j < nrows; j += 8) {
                     const int src = p.pool == 2 ? 2 * j : j;          // the lane that holds output row j
                     if ((vmask >> src) & 1u)
-                        st_stream_f4(reinterpret_cast<float4*>(dst + j * ld + (lane & 3) * 16),
+                        st_stream_f4(reinterpret_cast<float4*>(dst + (j + (j >= oseg ? oseg_delta : 0)) * ld + (lane & 3) * 16),
                                      *reinterpret_cast<const float4*>(stw + src * kStagePitch + (lane & 3) * 4));
                 }
                 __syncwarp();
@@ -642,7 +673,7 @@ EncodeTiledFn encode_tiled() {
 }
 
 template <int BN, int CG, bool F16>
-int launch(const CUtensorMap& ma, const CUtensorMap& mw, const Params& p, cudaStream_t stream) {
+int launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mp0, const CUtensorMap& mp1, const Params& p, cudaStream_t stream) {
     using C = Cfg<BN, CG>;
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -654,21 +685,22 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mw, const Params& p, cudaSt
     const long long tiles = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;
     const long long groups = sm_count() / CG;
     const int grid = CG * (int)(tiles < groups ? tiles : groups);
-    conv_tc_kernel<BN, CG, F16><<<grid, C::kThreads, C::kSmem, stream>>>(ma, mw, p);
+    conv_tc_kernel<BN, CG, F16><<<grid, C::kThreads, C::kSmem, stream>>>(ma, mw, mp0, mp1, p);
     POF_CUDA(cudaGetLastError());
     return POF_OK;
 }
 
 template <bool F16>
-int launch_any(int bn, int cg, const CUtensorMap& ma, const CUtensorMap& mw, const Params& p, cudaStream_t stream) {
+int launch_any(int bn, int cg, const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mp0, const CUtensorMap& mp1, const Params& p,
+               cudaStream_t stream) {
     if (cg == 2) {
-        if (bn == 256) return launch<256, 2, F16>(ma, mw, p, stream);
-        if (bn == 128) return launch<128, 2, F16>(ma, mw, p, stream);
-        return launch<64, 2, F16>(ma, mw, p, stream);
+        if (bn == 256) return launch<256, 2, F16>(ma, mw, mp0, mp1, p, stream);
+        if (bn == 128) return launch<128, 2, F16>(ma, mw, mp0, mp1, p, stream);
+        return launch<64, 2, F16>(ma, mw, mp0, mp1, p, stream);
     }
-    if (bn == 256) return launch<256, 1, F16>(ma, mw, p, stream);
-    if (bn == 128) return launch<128, 1, F16>(ma, mw, p, stream);
-    return launch<64, 1, F16>(ma, mw, p, stream);
+    if (bn == 256) return launch<256, 1, F16>(ma, mw, mp0, mp1, p, stream);
+    if (bn == 128) return launch<128, 1, F16>(ma, mw, mp0, mp1, p, stream);
+    return launch<64, 1, F16>(ma, mw, mp0, mp1, p, stream);
 }
 
 // f16 = false: fp32 containers holding TF32 hi / lo parts; f16 = true: binary16 hi / lo parts.
@@ -684,7 +716,7 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
     POF_REQUIRE(Cin >= kb && Cin % kb == 0, POF_ERR_BAD_SHAPE, "pof_conv_tc_fwd: Cin must be a multiple of %d (got %d)", kb, Cin);
     const int chain_flags = chain_channels;
     const int cg = (chain_channels & POF_CONV_TC_SINGLE_CTA) ? 1 : 2;      // high flag bits: tuning / tests only
-    chain_channels &= ~(POF_CONV_TC_SINGLE_CTA | POF_CONV_TC_STREAM_W | POF_CONV_TC_NO_DEBIAS);
+    chain_channels &= ~(POF_CONV_TC_SINGLE_CTA | POF_CONV_TC_STREAM_W | POF_CONV_TC_NO_DEBIAS | POF_CONV_TC_NO_SPLIT_TILE);
     // binary16 chains have half as many accumulation steps per channel: 128 channels cost what 64 TF32 channels do
     // (6-7e-7 of the fp64 result per layer; cuDNN's fp32 kernels: 1-2e-6)
     if (chain_channels == 0) chain_channels = f16 ? 128 : 64;
@@ -709,6 +741,13 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
     p.Lout = Lout;
     p.mt = kTileM / Lout;
     p.tiles_m = (Mcut + p.mt - 1) / p.mt;
+    p.split_h0 = 0;
+    if (cg == 2 && LA == Lout && !(chain_flags & POF_CONV_TC_NO_SPLIT_TILE) && (2 * p.mt + 1) * Lout <= 2 * kTileM && (kTileM - p.mt * Lout) % 2 == 0) {
+        // one more cutout fits the pair's 256 rows than two separate tiles hold (Lout = 28: 9 instead of 8, 252 rows busy instead of 224)
+        p.split_h0 = kTileM - p.mt * Lout;
+        const long long per_pair = 2 * p.mt + 1;
+        p.tiles_m = 2 * ((Mcut + per_pair - 1) / per_pair);          // the kernel counts work items as ceil(tiles_m / 2)
+    }
     p.tiles_n = Cout / bn;
     p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.pad = pad; p.pool = pool; p.slope = slope;
     p.chain = chain_channels / kb;
@@ -740,16 +779,21 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
     }
     const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
 
-    alignas(64) CUtensorMap ma, mw;
-    {   // A: [Mcut][LA][2 Cin], box (one 64-byte row of channels, Lout rows, mt cutouts); out-of-range rows read as zero
+    alignas(64) CUtensorMap ma, mw, mp0, mp1;
+    {   // A: [Mcut][LA][2 Cin], box (one 64-byte row of channels, Lout rows, mt cutouts); out-of-range rows read as zero.
+        // Split tiles: two more boxes over the same tensor, one cutout high - the leader's and the peer's part of the shared cutout.
         const cuuint64_t dims[3] = {(cuuint64_t)(2 * Cin), (cuuint64_t)LA, (cuuint64_t)Mcut};
         const cuuint64_t strides[2] = {(cuuint64_t)(2 * Cin) * esize, (cuuint64_t)LA * (2 * Cin) * esize};
-        const cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)Lout, (cuuint32_t)p.mt};
         const cuuint32_t es[3] = {1, 1, 1};
-        const CUresult r = enc(&ma, dt, 3, const_cast<void*>(a_split), dims, strides, box, es,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, kRowBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, POF_CONV_L2_PROMO,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        POF_REQUIRE(r == CUDA_SUCCESS, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+        CUtensorMap* maps[3] = {&ma, &mp0, &mp1};
+        const cuuint32_t heights[3] = {(cuuint32_t)Lout, (cuuint32_t)(p.split_h0 ? p.split_h0 : Lout), (cuuint32_t)(p.split_h0 ? Lout - p.split_h0 : Lout)};
+        for (int i = 0; i < 3; ++i) {
+            const cuuint32_t box[3] = {(cuuint32_t)kb, heights[i], i == 0 || !p.split_h0 ? (cuuint32_t)p.mt : 1u};
+            const CUresult r = enc(maps[i], dt, 3, const_cast<void*>(a_split), dims, strides, box, es,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, kRowBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, POF_CONV_L2_PROMO,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            POF_REQUIRE(r == CUDA_SUCCESS, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+        }
     }
     {   // W: [taps][2][Cout][Cin] seen as a [taps * 2 * Cout, Cin] matrix, box (one 64-byte row of channels, bn rows)
         const cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)taps * 2 * Cout};
@@ -761,7 +805,7 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         POF_REQUIRE(r == CUDA_SUCCESS, POF_ERR_BAD_PARAM, "pof_conv_tc_fwd: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
     }
-    return f16 ? launch_any<true>(bn, cg, ma, mw, p, stream) : launch_any<false>(bn, cg, ma, mw, p, stream);
+    return f16 ? launch_any<true>(bn, cg, ma, mw, mp0, mp1, p, stream) : launch_any<false>(bn, cg, ma, mw, mp0, mp1, p, stream);
 }
 
 }  // namespace

@@ -20,6 +20,7 @@ CFG = dict(fixed=True, centered=True, window_width=1.0, window_depth=0.5,
            num_cutout_pts=56, padding_val=29.99, area_mode=True)
 STREAM_W = 0x20000          # include/pof.h POF_CONV_TC_STREAM_W
 SINGLE_CTA = 0x10000        # include/pof.h POF_CONV_TC_SINGLE_CTA
+NO_SPLIT = 0x80000          # include/pof.h POF_CONV_TC_NO_SPLIT_TILE
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -51,6 +52,35 @@ ENGINE_LAYERS = [
     (7, 256, 128, 3, 1, 1),      # <128>
     (14, 256, 128, 14, 0, 1),    # <128>  the gate embedding: one GEMM over whole rows
 ]
+
+
+@pytest.mark.parametrize("Cout,pool", [(128, 1), (256, 2), (512, 1)])
+@pytest.mark.parametrize("M", [1, 4, 5, 8, 9, 10, 17, 130, 4001])
+def test_conv_tc_split_tiles_are_bit_equal(M, Cout, pool):
+    """Lout = 28: an SM pair's 256 accumulator rows take nine cutouts, the middle one split between the two CTAs (252 busy rows
+    instead of 224).  Tiling must not change a bit: same outputs, plain and operand split, as with POF_CONV_TC_NO_SPLIT_TILE, for
+    cutout counts around every multiple of 9 and 8, one and two column tiles, with and without the pool."""
+    LA, Cin, taps, pad = 28, 128, 3, 1
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + Cout)
+    x = torch.randn(M, LA, Cin, generator=g, device="cuda")
+    w = torch.randn(Cout, Cin, taps, generator=g, device="cuda") * (2.0 / (Cin * taps)) ** 0.5
+    b = torch.randn(Cout, generator=g, device="cuda") * 0.1
+    _, a = ops.act(x.view(M * LA, Cin), None, pool=1, slope=1.0, want_plain=False, want_split=True, parts=ops.SPLIT_F16)
+    ws, out_scale = _tc_weights(w)
+    outs = []
+    for flags in (0, NO_SPLIT):
+        status = ops.new_status(x.device)
+        plain, split = ops.conv_tc(a, ws, b, M, LA, LA, taps, pad, pool=pool, slope=0.1, want_plain=True, want_split=True,
+                                   out_scale=out_scale, chain_channels=flags, status=status)
+        assert ops.read_status(status) == 0
+        outs.append((plain.clone(), split.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]), int((outs[0][0] != outs[1][0]).sum())
+    assert torch.equal(outs[0][1].view(torch.int16), outs[1][1].view(torch.int16))
+    y = F.conv1d(x.permute(0, 2, 1).double(), w.double(), b.double(), padding=pad)
+    if pool == 2:
+        y = F.max_pool1d(y, 2)
+    want = torch.where(y > 0, y, y * 0.1).permute(0, 2, 1)
+    assert_rel(outs[0][0].view(M, LA // pool, Cout).double().cpu(), want.cpu(), tol=1.5e-6, what="split tiles vs fp64")
 
 
 @pytest.mark.parametrize("flags", [0, STREAM_W, SINGLE_CTA], ids=["default", "streamed-weights", "single-cta"])
