@@ -54,6 +54,33 @@ ENGINE_LAYERS = [
 ]
 
 
+@pytest.mark.parametrize("LA", [12, 48, 36])
+@pytest.mark.parametrize("M", [1, 3, 5, 6, 7, 20, 21, 22, 130, 1001])
+def test_conv_tc_split_tiles_other_row_counts(M, LA):
+    """The same for the other cutout heights that leave room for one more cutout per SM pair (num_cutout_pts = 48 gives 48- and
+    12-row layers: 5 and 21 cutouts per pair; 36 rows: 7): the peer's part of the shared cutout can start anywhere in its tile,
+    including on a warp boundary."""
+    Cin, Cout, taps, pad, pool = 64, 128, 3, 1, 2
+    g = torch.Generator(device="cuda").manual_seed(M * 11 + LA)
+    x = torch.randn(M, LA, Cin, generator=g, device="cuda")
+    w = torch.randn(Cout, Cin, taps, generator=g, device="cuda") * (2.0 / (Cin * taps)) ** 0.5
+    b = torch.randn(Cout, generator=g, device="cuda") * 0.1
+    _, a = ops.act(x.view(M * LA, Cin), None, pool=1, slope=1.0, want_plain=False, want_split=True, parts=ops.SPLIT_F16)
+    ws, out_scale = _tc_weights(w)
+    outs = []
+    for flags in (0, NO_SPLIT):
+        status = ops.new_status(x.device)
+        plain, split = ops.conv_tc(a, ws, b, M, LA, LA, taps, pad, pool=pool, slope=0.1, want_plain=True, want_split=True,
+                                   out_scale=out_scale, chain_channels=flags, status=status)
+        assert ops.read_status(status) == 0
+        outs.append((plain.clone(), split.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]), int((outs[0][0] != outs[1][0]).sum())
+    assert torch.equal(outs[0][1].view(torch.int16), outs[1][1].view(torch.int16))
+    y = F.max_pool1d(F.conv1d(x.permute(0, 2, 1).double(), w.double(), b.double(), padding=pad), 2)
+    want = torch.where(y > 0, y, y * 0.1).permute(0, 2, 1)
+    assert_rel(outs[0][0].view(M, LA // pool, Cout).double().cpu(), want.cpu(), tol=1.5e-6, what="split tiles vs fp64")
+
+
 @pytest.mark.parametrize("Cout,pool", [(128, 1), (256, 2), (512, 1)])
 @pytest.mark.parametrize("M", [1, 4, 5, 8, 9, 10, 17, 130, 4001])
 def test_conv_tc_split_tiles_are_bit_equal(M, Cout, pool):
