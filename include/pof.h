@@ -237,6 +237,7 @@ POF_API int pof_head_fwd(const float* y, const float* bias, long long M, int L, 
 #define POF_CONV_TC_STREAM_W   0x20000   /* OR into chain_channels: never keep the weights resident in shared memory (tuning) */
 #define POF_CONV_TC_NO_DEBIAS  0x40000   /* OR into chain_channels: pof_conv_tc_f16_fwd does not compensate the tensor core's truncating accumulation (tests) */
 #define POF_CONV_TC_NO_SPLIT_TILE 0x80000 /* OR into chain_channels: never split a cutout between the two CTAs of a pair (tuning / tests) */
+#define POF_CONV_TC_HALO 0x100000 /* OR into chain_channels: where it applies (64 input channels, k = 3), load a tile ONCE with its halo rows and run the taps on row-shifted views (measured: no faster; tests) */
 POF_API int pof_conv_tc_fwd(const float* a_split, const float* w_split, const float* bias,
                             long long Mcut, int LA, int Lout, int Cin, int Cout, int taps, int pad,
                             int pool, float slope, float* out_plain, float* out_split,

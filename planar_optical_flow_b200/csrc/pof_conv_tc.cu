@@ -105,6 +105,7 @@ struct Params {
     int tiles_n;
     int Lout;            // output rows per cutout (= box height)
     int mt;              // cutouts per tile, mt * Lout <= 128
+    int halo;            // 1: a tile's cutouts are loaded ONCE with their two halo rows, the three taps are row-shifted views (see the kernel)
     int split_h0;        // 0, or (SM pairs only) the pair's 256 rows hold 2 mt + 1 cutouts: the middle one is split, its first
                          // split_h0 = 128 - mt * Lout rows go to the leader CTA's tile, the other Lout - split_h0 to the peer's
     int Cin, Cout, taps, pad, pool;
@@ -354,6 +355,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int rows_full = p.mt * p.Lout;                         // rows of whole cutouts in a CTA's tile
     const int rows_tile = !split ? rows_full : rank == 0 ? rows_full + p.split_h0 : rows_full + p.Lout - p.split_h0;
     const int per_pair = split ? 2 * p.mt + 1 : CG * p.mt;       // cutouts per work item
+    // Halo tiles (p.halo; Cin = one k-block, k = 3, the weights resident): the layers with 56 rows per cutout are bound by the
+    // TMA's L2 -> shared-memory row rate, and a tile is loaded three times, once per tap.  Here a cutout comes in ONCE with its
+    // two padding rows - box rows -1 .. Lout, zero filled by the TMA like any row outside the cutout - and tap t multiplies the
+    // view that starts t rows further down: the descriptor's start address moves by t * 128 B (the 128-byte swizzle is a
+    // function of the absolute shared-memory address, so a row-shifted view of a tile the TMA wrote reads the right chunks).
+    // Accumulator lane i is then output row i - 2 c of cutout c = i / (Lout + 2); the two lanes between cutouts are not outputs.
+    // Same MMAs in the same order as the tap-by-tap form (tap 0, tap 1 | tap 2: the chains of a 64-channel layer), so the
+    // same bits.
+    const bool halo = p.halo != 0;
+    const int halo_rows = p.Lout + 2;
     // shared-memory plan: [resident weights: n_kb x (W hi | W lo)] [ring: stages x stage_bytes]
     const int n_stages = p.stages;
     const unsigned stage_bytes = p.w_resident ? C::kStageA : C::kStage;
@@ -406,6 +417,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
             __syncwarp();
+            if (halo) {                                        // one box per part and tile: (channels, Lout + 2 rows from row -1, mt cutouts)
+                const unsigned tx_h = CG * 2u * (unsigned)(p.mt * halo_rows) * kRowBytes;
+                for (long long tile = first_tile; tile < n_tiles && ok; tile += tile_stride) {
+                    const int m0 = (int)(((tile / p.tiles_n) * CG + rank) * p.mt);
+                    if (!(ok = mbar_wait_warp(empty(s), ph ^ 1u, p.status, 1))) break;
+                    const unsigned dst = ring + (unsigned)s * stage_bytes;
+                    if (elect_one()) {
+                        if (CG == 1) {
+                            mbar_expect_tx(full(s), tx_h);
+                            tma_load_3d(dst, &map_p0, 0, -1, m0, full(s));
+                            tma_load_3d(dst + kATile, &map_p0, p.Cin, -1, m0, full(s));
+                        } else {
+                            if (rank == 0) mbar_expect_tx(full(s), tx_h);
+                            tma_load_3d_pair(dst, &map_p0, 0, -1, m0, full(s));
+                            tma_load_3d_pair(dst + kATile, &map_p0, p.Cin, -1, m0, full(s));
+                        }
+                    }
+                    __syncwarp();
+                    if (++s == n_stages) { s = 0; ph ^= 1u; }
+                }
+            } else
             for (long long tile = first_tile; tile < n_tiles && ok; tile += tile_stride) {
                 const int nt = (int)(tile % p.tiles_n);
                 const int m0 = (int)((tile / p.tiles_n) * per_pair + rank * (split ? p.mt + 1 : p.mt));
@@ -474,9 +506,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const unsigned buf = ic & 1u;
                     const bool first = in_chain == 0, last = in_chain + 1 == p.chain || kb + 1 == n_kb;
                     if (first && !(ok = mbar_wait_warp(tempty(buf), ((ic >> 1) & 1u) ^ 1u, p.status, 2))) break;   // chain ic-2 promoted
-                    if (!(ok = mbar_wait_warp(full(s), ph, p.status, 3))) break;                // operands landed
+                    if ((!halo || kb == 0) && !(ok = mbar_wait_warp(full(s), ph, p.status, 3))) break;                // operands landed
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const unsigned st = ring + (unsigned)s * stage_bytes;
+                    const bool stage_done = !halo || kb + 1 == n_kb;          // halo: the three taps (= k-blocks) read one stage
+                    const unsigned st = ring + (unsigned)s * stage_bytes + (halo ? (unsigned)kb * kRowBytes : 0u);   // halo: the view of tap kb
                     const unsigned wst = p.w_resident ? base + (unsigned)kb * 2u * C::kBTile : st + 2 * kATile;
                     if (elect_one()) {
                         const unsigned long long a_hi = desc_hi | ((st >> 4) & 0x3fffu), a_lo = desc_hi | (((st + kATile) >> 4) & 0x3fffu);
@@ -493,16 +526,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int k = 0; k < kSteps; ++k) mma(a_hi + 2 * k, b_hi + 2 * k, 1);                 // main product last
                         if (CG == 1) {
-                            umma_commit(empty(s));
+                            if (stage_done) umma_commit(empty(s));
                             if (last) umma_commit(tfull(buf));
                         } else {
-                            umma_commit_pair(empty(s));                      // both CTAs' producers may refill their slot
+                            if (stage_done) umma_commit_pair(empty(s));      // both CTAs' producers may refill their slot
                             if (last) umma_commit_pair(tfull(buf));          // both CTAs' epilogues may read their rows
                         }
                     }
                     __syncwarp();
                     if (last) { ++ic; in_chain = 0; } else ++in_chain;
-                    if (++s == n_stages) { s = 0; ph ^= 1u; }
+                    if (stage_done && ++s == n_stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -561,7 +594,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     seg_delta = -(rows_full + p.Lout - p.split_h0);
                 }
             }
-            const bool valid = row < rows_tile && r0 + lane + (lane >= seg ? seg_delta : 0) < p.Mcut * p.Lout;
+            bool in_tile = row < rows_tile;
+            if (halo) {                                       // lane -> (cutout c, row l): at most one cutout boundary inside a warp (Lout + 2 >= 32)
+                const int c_first = (q * 32) / halo_rows, c = row / halo_rows, l = row - c * halo_rows;
+                r0 -= 2 * c_first;
+                seg = min((c_first + 1) * halo_rows - q * 32, 32);
+                seg_delta = -2;
+                in_tile = c < p.mt && l < p.Lout;
+            }
+            const bool valid = in_tile && r0 + lane + (lane >= seg ? seg_delta : 0) < p.Mcut * p.Lout;
             const unsigned vmask = __ballot_sync(0xffffffffu, valid);
             const int cbase = nt * BN + h * C::kAcc;
             float* stg = staging + e * (32 * kStagePitch);
@@ -716,7 +757,7 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
     POF_REQUIRE(Cin >= kb && Cin % kb == 0, POF_ERR_BAD_SHAPE, "pof_conv_tc_fwd: Cin must be a multiple of %d (got %d)", kb, Cin);
     const int chain_flags = chain_channels;
     const int cg = (chain_channels & POF_CONV_TC_SINGLE_CTA) ? 1 : 2;      // high flag bits: tuning / tests only
-    chain_channels &= ~(POF_CONV_TC_SINGLE_CTA | POF_CONV_TC_STREAM_W | POF_CONV_TC_NO_DEBIAS | POF_CONV_TC_NO_SPLIT_TILE);
+    chain_channels &= ~(POF_CONV_TC_SINGLE_CTA | POF_CONV_TC_STREAM_W | POF_CONV_TC_NO_DEBIAS | POF_CONV_TC_NO_SPLIT_TILE | POF_CONV_TC_HALO);
     // binary16 chains have half as many accumulation steps per channel: 128 channels cost what 64 TF32 channels do
     // (6-7e-7 of the fp64 result per layer; cuDNN's fp32 kernels: 1-2e-6)
     if (chain_channels == 0) chain_channels = f16 ? 128 : 64;
@@ -777,6 +818,13 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
         const long long st = p.w_resident ? (ring - w_bytes) / stage_a : ring / stage_full;
         p.stages = (int)(st < kMaxStages ? st : kMaxStages);
     }
+    // One load per tile instead of one per tap (see the kernel): a single k-block of channels, so the order of the MMAs and the
+    // chain boundaries are those of the tap-by-tap form.  OPT-IN (POF_CONV_TC_HALO): it cuts the L2 -> shared-memory traffic of the
+    // two 56-row layers by 2.9x and changes their time by -1.3 % / +1.5 % (64->128 0.844 -> 0.833 ms, 64->64 0.542 -> 0.550 ms at the
+    // bench's launch size) - those layers are not waiting for the TMA (ncu: the stall samples sit in the epilogue warps) - and the wider layers would pay for the halo
+    // rows with accumulator rows (126 -> 112 / 98 useful rows of 128 at 14 / 7 rows per cutout).
+    p.halo = p.w_resident && !p.split_h0 && (chain_flags & POF_CONV_TC_HALO) && Cin == kb && taps == 3 && pad == 1 && LA == Lout &&
+             Lout + 2 >= 32 && p.mt * (Lout + 2) <= kTileM;
     const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
 
     alignas(64) CUtensorMap ma, mw, mp0, mp1;
@@ -786,7 +834,9 @@ int conv_tc_any(bool f16, const void* a_split, const void* w_split, const float*
         const cuuint64_t strides[2] = {(cuuint64_t)(2 * Cin) * esize, (cuuint64_t)LA * (2 * Cin) * esize};
         const cuuint32_t es[3] = {1, 1, 1};
         CUtensorMap* maps[3] = {&ma, &mp0, &mp1};
-        const cuuint32_t heights[3] = {(cuuint32_t)Lout, (cuuint32_t)(p.split_h0 ? p.split_h0 : Lout), (cuuint32_t)(p.split_h0 ? Lout - p.split_h0 : Lout)};
+        // Halo tiles: the second map's box is two rows higher (the padding rows of a cutout, zero filled).
+        const cuuint32_t heights[3] = {(cuuint32_t)Lout, (cuuint32_t)(p.halo ? Lout + 2 : p.split_h0 ? p.split_h0 : Lout),
+                                       (cuuint32_t)(p.split_h0 ? Lout - p.split_h0 : Lout)};
         for (int i = 0; i < 3; ++i) {
             const cuuint32_t box[3] = {(cuuint32_t)kb, heights[i], i == 0 || !p.split_h0 ? (cuuint32_t)p.mt : 1u};
             const CUresult r = enc(maps[i], dt, 3, const_cast<void*>(a_split), dims, strides, box, es,

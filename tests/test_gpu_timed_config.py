@@ -21,6 +21,7 @@ CFG = dict(fixed=True, centered=True, window_width=1.0, window_depth=0.5,
 STREAM_W = 0x20000          # include/pof.h POF_CONV_TC_STREAM_W
 SINGLE_CTA = 0x10000        # include/pof.h POF_CONV_TC_SINGLE_CTA
 NO_SPLIT = 0x80000          # include/pof.h POF_CONV_TC_NO_SPLIT_TILE
+HALO = 0x100000             # include/pof.h POF_CONV_TC_HALO
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -52,6 +53,35 @@ ENGINE_LAYERS = [
     (7, 256, 128, 3, 1, 1),      # <128>
     (14, 256, 128, 14, 0, 1),    # <128>  the gate embedding: one GEMM over whole rows
 ]
+
+
+@pytest.mark.parametrize("LA,Cout,pool", [(56, 64, 1), (56, 128, 2), (56, 128, 1), (40, 64, 2), (62, 128, 1)])
+@pytest.mark.parametrize("M", [1, 2, 3, 4, 5, 130, 2001])
+def test_conv_tc_halo_tiles_are_bit_equal(M, LA, Cout, pool):
+    """With POF_CONV_TC_HALO a 64-channel k = 3 layer loads a tile ONCE, with the two padding rows of every cutout, and runs the
+    three taps on row-shifted views of it (instead of three loads): same MMAs in the same order, so the same bits as the default
+    form, for one and two cutouts per tile, odd cutout counts, with and without the pool; and the float64 convolution to 1.5e-6."""
+    Cin, taps, pad = 64, 3, 1
+    g = torch.Generator(device="cuda").manual_seed(M * 13 + LA + Cout)
+    x = torch.randn(M, LA, Cin, generator=g, device="cuda")
+    w = torch.randn(Cout, Cin, taps, generator=g, device="cuda") * (2.0 / (Cin * taps)) ** 0.5
+    b = torch.randn(Cout, generator=g, device="cuda") * 0.1
+    _, a = ops.act(x.view(M * LA, Cin), None, pool=1, slope=1.0, want_plain=False, want_split=True, parts=ops.SPLIT_F16)
+    ws, out_scale = _tc_weights(w)
+    outs = []
+    for flags in (HALO, 0):
+        status = ops.new_status(x.device)
+        plain, split = ops.conv_tc(a, ws, b, M, LA, LA, taps, pad, pool=pool, slope=0.1, want_plain=True, want_split=True,
+                                   out_scale=out_scale, chain_channels=flags, status=status)
+        assert ops.read_status(status) == 0
+        outs.append((plain.clone(), split.clone()))
+    y = F.conv1d(x.permute(0, 2, 1).double(), w.double(), b.double(), padding=pad)
+    if pool == 2:
+        y = F.max_pool1d(y, 2)
+    want = torch.where(y > 0, y, y * 0.1).permute(0, 2, 1)
+    assert_rel(outs[0][0].view(M, LA // pool, Cout).double().cpu(), want.cpu(), tol=1.5e-6, what="halo tiles vs fp64")
+    assert torch.equal(outs[0][0], outs[1][0]), int((outs[0][0] != outs[1][0]).sum())
+    assert torch.equal(outs[0][1].view(torch.int16), outs[1][1].view(torch.int16))
 
 
 @pytest.mark.parametrize("LA", [12, 48, 36])
