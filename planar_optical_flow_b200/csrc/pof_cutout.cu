@@ -969,8 +969,10 @@ __global__ void __launch_bounds__(POF_SCAN_LB_THREADS, POF_SCAN_LB_BLOCKS) cutou
 // finished 32-row group leaves as one bulk store - with the conversions taken out of the sample loop:
 //   * the scan is staged as DOUBLE pairs (v[i], (double)(v[i+1] - v[i])): one LDS.128 per sample, no F2F;
 //   * floor(idx) is the low word of RD(idx + 1.5 * 2^52) and its double is that sum minus the constant (both exact for
-//     0 <= idx < 2^31): no F2I / I2F.  Only rows whose first and last index lie inside the scan take this loop (the index
-//     is monotone along a row); rows that leave the scan and area-resampled rows call linear_exact / area_exact;
+//     |idx| < 2^31): no F2I / I2F.  Rows whose first and last index lie inside the scan (the index is monotone along a
+//     row) take the plain loop, groups at the two ends of the scan the same loop with the :289 test and a clamped gather;
+//     area rows are done by the whole warp with their taps on a guarded fixed-point line (exact_area_sample_fx); only
+//     geometry outside those guarantees (|idx| >= 1e9, NaN) falls back to linear_exact / area_exact;
 //   * (double)k comes from a P-entry table in shared memory;
 //   * for a power-of-two window_depth the correctly rounded division is one product.
 // 12 double operations and one F2F.F32.F64 per sample remain.
